@@ -1,0 +1,109 @@
+"""Packs a reference `model_state_dict` (checkpoint contract: networks/posenet_agent.py:117-173, key schema
+SURVEY.md §8b) into the two flat fp32 blobs the C ABI consumes (layouts: DESIGN.md §3, and
+genpose_b200/csrc/{encoder.cu: enc_spec/off_*, common.cuh: TrunkLayout}).
+
+  encoder blob : for level l in 0..3, scale s in 0..1 (in that order), with channels padded to multiples of 8
+                 (196 -> 200, zero filled):
+                     Wx [3][c1]  Wf [cin_f][c1]  b1 [c1]  W2 [c1][c2]  b2 [c2]  W3 [c2][c3]  b3 [c3]
+                 every matrix K-major ([in][out]); eval-mode BatchNorm2d folded in
+                 (pytorch_utils.py:20-32, eps 1e-5):  W' = W * g / sqrt(var + eps),  b' = beta - mean * g / sqrt(var + eps)
+  trunk blob   : fourier W [64] | L_t^T [128][128] | b_t | P1^T [9][256] | b | P2^T [256][256] | b |
+                 A_pts [1024][768] | A_t [128][768] | A_pose [256][768] | a [768] | O [9][256] | o_b [9] (+3 pad)
+                 where the three heads (rot_x, rot_y, trans; scorenet.py:149-170) are stacked along the 768
+                 axis and the 1408 input columns are split as [pts_feat | t_feat | pose_feat] (scorenet.py:204).
+"""
+from typing import Dict
+
+import numpy as np
+import torch
+
+from . import arch
+
+
+def _pad8(c: int) -> int:
+    return (c + 7) // 8 * 8
+
+
+def _fold(sd: Dict[str, torch.Tensor], prefix: str):
+    """conv (no bias) + eval BatchNorm -> (W' [cout, cin], b' [cout]) in float64."""
+    w = sd[f"{prefix}.conv.weight"].double()[:, :, 0, 0]
+    gamma = sd[f"{prefix}.bn.bn.weight"].double()
+    beta = sd[f"{prefix}.bn.bn.bias"].double()
+    mean = sd[f"{prefix}.bn.bn.running_mean"].double()
+    var = sd[f"{prefix}.bn.bn.running_var"].double()
+    scale = gamma / torch.sqrt(var + arch.BN_EPS)
+    return w * scale[:, None], beta - mean * scale
+
+
+def encoder_spec(l: int, s: int):
+    lv = arch.SA_LEVELS[l]
+    spec = lv.mlps[s]
+    return dict(cin_f=lv.c_in, c1=_pad8(spec[1]), c2=_pad8(spec[2]), c3=_pad8(spec[3]),
+                c1o=spec[1], c2o=spec[2], c3o=spec[3])
+
+
+def pack_encoder(sd: Dict[str, torch.Tensor], prefix: str = "pts_encoder") -> torch.Tensor:
+    chunks = []
+    for l in range(4):
+        for s in range(2):
+            m = encoder_spec(l, s)
+            base = f"{prefix}.SA_modules.{l}.mlps.{s}"
+            w1, b1 = _fold(sd, f"{base}.layer0")
+            w2, b2 = _fold(sd, f"{base}.layer1")
+            w3, b3 = _fold(sd, f"{base}.layer2")
+            assert w1.shape == (m["c1o"], 3 + m["cin_f"]), (w1.shape, m)
+            wx = torch.zeros(3, m["c1"], dtype=torch.float64)
+            wx[:, :m["c1o"]] = w1[:, :3].t()
+            wf = torch.zeros(m["cin_f"], m["c1"], dtype=torch.float64)
+            wf[:, :m["c1o"]] = w1[:, 3:].t()
+            pb1 = torch.zeros(m["c1"], dtype=torch.float64)
+            pb1[:m["c1o"]] = b1
+            pw2 = torch.zeros(m["c1"], m["c2"], dtype=torch.float64)
+            pw2[:m["c1o"], :m["c2o"]] = w2.t()
+            pb2 = torch.zeros(m["c2"], dtype=torch.float64)
+            pb2[:m["c2o"]] = b2
+            pw3 = torch.zeros(m["c2"], m["c3"], dtype=torch.float64)
+            pw3[:m["c2o"], :m["c3o"]] = w3.t()
+            pb3 = torch.zeros(m["c3"], dtype=torch.float64)
+            pb3[:m["c3o"]] = b3
+            chunks += [wx.reshape(-1), wf.reshape(-1), pb1, pw2.reshape(-1), pb2, pw3.reshape(-1), pb3]
+    return torch.cat(chunks).float().contiguous()
+
+
+def pack_trunk(sd: Dict[str, torch.Tensor], prefix: str = "pose_score_net") -> torch.Tensor:
+    g = lambda k: sd[f"{prefix}.{k}"].float()
+    heads_w = [g(f"fusion_tail_{h}.0.weight") for h in arch.HEADS]      # [256, 1408] each
+    heads_b = [g(f"fusion_tail_{h}.0.bias") for h in arch.HEADS]
+    out_w = [g(f"fusion_tail_{h}.2.weight") for h in arch.HEADS]        # [3, 256] each
+    out_b = [g(f"fusion_tail_{h}.2.bias") for h in arch.HEADS]
+    a = torch.cat(heads_w, dim=0)                                        # [768, 1408], n = head*256 + j
+    P, T = arch.PTS_FEAT_DIM, arch.T_EMBED_DIM
+    chunks = [
+        g("t_encoder.0.W").reshape(-1),                                  # fourier_w [64]
+        g("t_encoder.1.weight").t().contiguous().reshape(-1),            # t_w [128 in][128 out]
+        g("t_encoder.1.bias"),
+        g("pose_encoder.0.weight").t().contiguous().reshape(-1),         # p1_w [9][256]
+        g("pose_encoder.0.bias"),
+        g("pose_encoder.2.weight").t().contiguous().reshape(-1),         # p2_w [256][256]
+        g("pose_encoder.2.bias"),
+        a[:, :P].t().contiguous().reshape(-1),                           # a_pts [1024][768]
+        a[:, P:P + T].t().contiguous().reshape(-1),                      # a_t   [128][768]
+        a[:, P + T:].t().contiguous().reshape(-1),                       # a_pose [256][768]
+        torch.cat(heads_b),                                              # a_b [768]
+        torch.cat(out_w, dim=0).contiguous().reshape(-1),                # o_w [9][256]
+        torch.cat(out_b), torch.zeros(3),                                # o_b [9] + pad
+    ]
+    return torch.cat([c.float() for c in chunks]).contiguous()
+
+
+def encoder_floats() -> int:
+    n = 0
+    for l in range(4):
+        for s in range(2):
+            m = encoder_spec(l, s)
+            n += 3 * m["c1"] + m["cin_f"] * m["c1"] + m["c1"] + m["c1"] * m["c2"] + m["c2"] + m["c2"] * m["c3"] + m["c3"]
+    return n
+
+
+def trunk_floats() -> int:
+    return 64 + 128 * 128 + 128 + 9 * 256 + 256 + 256 * 256 + 256 + 1024 * 768 + 128 * 768 + 256 * 768 + 768 + 9 * 256 + 12

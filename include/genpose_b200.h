@@ -1,0 +1,156 @@
+/*
+ * genpose_b200 — C ABI of the B200-native (sm_100a) GenPose per-object inference hot path.
+ *
+ * Boundary rules (all entry points):
+ *   - plain C, `extern "C"`; raw DEVICE pointers unless a parameter is documented as host;
+ *   - caller owns every buffer (no hidden allocation, no internal state, re-entrant, thread-safe);
+ *   - work is enqueued on `stream` (a cudaStream_t passed as void*; NULL = legacy default stream) and
+ *     the call returns without synchronising;
+ *   - returns GPB_OK (0) or a negative GPB_E* code; never calls exit() (the reference's launchers
+ *     do: src/sampling_gpu.cu:39-43).  gpb_last_error_string() describes the last failure of the
+ *     calling thread.
+ *
+ * Reference paths below are relative to the GenPose checkout; "pointnet2/" abbreviates
+ * networks/pts_encoder/pointnet2_utils/pointnet2/.
+ */
+#ifndef GENPOSE_B200_H
+#define GENPOSE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GPB_OK 0
+#define GPB_EINVAL (-1)   /* bad argument (NULL pointer, unsupported shape) */
+#define GPB_ECUDA (-2)    /* a CUDA runtime call or launch failed */
+#define GPB_EWORKSPACE (-3) /* workspace too small */
+
+#define GPB_ABI_VERSION 1
+
+/* exported from libgenpose_b200.so (everything else is built with -fvisibility=hidden) */
+#if defined(__GNUC__)
+#define GPB_API __attribute__((visibility("default")))
+#else
+#define GPB_API
+#endif
+
+GPB_API int gpb_abi_version(void);
+GPB_API const char *gpb_last_error_string(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * (1) COMPAT LAYER — the four forward ops of the reference's pybind module `pointnet2_cuda`
+ *     (pointnet2/src/pointnet2_api.cpp:10-24), same argument order and buffer conventions, so the
+ *     reference's own pointnet2_utils.py can run on them unchanged.
+ *     Indices are bit-exact with the reference kernels, including tie-breaking.
+ * ---------------------------------------------------------------------------------------------- */
+
+/* replaces furthest_point_sampling_wrapper (pointnet2/src/sampling.cpp:40-51; kernel
+ * sampling_gpu.cu:93-209).  xyz [b,n,3] f32, temp [b,n] f32 scratch (the reference requires it
+ * pre-filled with 1e10, pointnet2_utils.py:27; this implementation ignores its contents but writes
+ * the final min-distances back for parity), idx [b,m] i32 out.  m <= n. */
+GPB_API int gpb_furthest_point_sampling(int b, int n, int m, const float *xyz, float *temp, int *idx, void *stream);
+
+/* replaces gather_points_wrapper (sampling.cpp:13-23; sampling_gpu.cu:8-24):
+ * out[b,c,j] = points[b,c,idx[b,j]];  points [b,c,n], idx [b,npoints], out [b,c,npoints]. */
+GPB_API int gpb_gather_points(int b, int c, int n, int npoints, const float *points, const int *idx, float *out,
+                      void *stream);
+
+/* replaces ball_query_wrapper (pointnet2/src/ball_query.cpp:16-28; ball_query_gpu.cu:9-45).
+ * new_xyz [b,m,3], xyz [b,n,3], idx [b,m,nsample] i32 out.  Unlike the reference the caller need not
+ * pre-zero idx (pointnet2_utils.py:219): empty balls are written as zeros. */
+GPB_API int gpb_ball_query(int b, int n, int m, float radius, int nsample, const float *new_xyz, const float *xyz,
+                   int *idx, void *stream);
+
+/* replaces group_points_wrapper (pointnet2/src/group_points.cpp:26-37; group_points_gpu.cu:47-66):
+ * out[b,c,i,s] = points[b,c,idx[b,i,s]];  points [b,c,n], idx [b,npoints,nsample]. */
+GPB_API int gpb_group_points(int b, int c, int n, int npoints, int nsample, const float *points, const int *idx,
+                     float *out, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (2) FUSED PATH — what networks/posenet_agent.py::PoseNet.pred_func / get_energy call.
+ *     Weight blobs are produced on the host by genpose_b200/weights.py from a reference
+ *     `model_state_dict` (BatchNorm folded, heads stacked, W1 split into [pts | t | pose] blocks);
+ *     their layouts are fixed by the gpb_*_weights_floats() sizes and documented in DESIGN.md §3.
+ * ---------------------------------------------------------------------------------------------- */
+
+/* number of floats in the packed encoder / score-trunk weight blobs */
+GPB_API size_t gpb_encoder_weights_floats(void);
+GPB_API size_t gpb_trunk_weights_floats(void);
+
+/* scratch bytes gpb_encode needs for a batch of B objects */
+GPB_API size_t gpb_encode_workspace_bytes(int B);
+
+/* replaces Pointnet2ClsMSG.forward (networks/pts_encoder/pointnet2.py:203-211) == GFObjectPose
+ * mode 'pts_feature' (networks/posenet.py:71-91,169-171).
+ * pts [B,1024,3] f32 (camera frame, metres, NOT centred) -> pts_feat [B,1024] f32.
+ * Optional debug outputs (may be NULL): fps_idx1 [B,512], fps_idx2 [B,256], fps_idx3 [B,128] i32. */
+GPB_API int gpb_encode(const float *pts, int B, const float *enc_weights, float *pts_feat, void *workspace,
+               size_t workspace_bytes, int *fps_idx1, int *fps_idx2, int *fps_idx3, void *stream);
+
+/* Per-object hoisted head bias: obj_bias[b, 0:768] = A_pts . pts_feat[b] + a   (the constant 67 % of
+ * PoseScoreNet.forward, networks/gf_algorithms/scorenet.py:204-216).  obj_bias [B,768]. */
+GPB_API int gpb_object_bias(const float *pts_feat, int B, const float *trunk_weights, float *obj_bias, void *stream);
+
+/* replaces GFObjectPose.forward(mode='score') (networks/posenet.py:160-162 ->
+ * PoseScoreNet.forward scorenet.py:178-222) for a batch-constant time t:
+ *   out[r, 0:9] = f_theta(pose[r], t, object row_object(r)) / (sigma(t) + 1e-7)     if divide_mode == 1
+ *               = f_theta / sigma(t)                                               if divide_mode == 2 (energynet.py:166-167)
+ *               = f_theta                                                          if divide_mode == 0
+ * rows R = B*K, row r belongs to object r / K.  pose [R,9], out [R,9]. */
+GPB_API int gpb_trunk_eval(const float *pose, int R, int K, float t, const float *obj_bias, const float *trunk_weights,
+                   int divide_mode, float *out, void *stream);
+
+/* scratch bytes the samplers need */
+GPB_API size_t gpb_sampler_workspace_bytes(int R, int num_steps);
+
+/* replaces cond_pc_sampler (networks/gf_algorithms/samplers.py:102-160), pose_mode 'rot_matrix', VE SDE.
+ *   x0 [R,9]            prior sample (sde.py:26-28: 50*randn), consumed read-only
+ *   step_noise          [T,2,R,9] explicit z1,z2 (parity mode) or NULL -> in-kernel Philox4x32-10 keyed by `seed`
+ *   pts_center [B,3]    added to the translation at the end (samplers.py:157)
+ *   time_grid [T]       torch.linspace(1, 1e-5, T) in fp32 (samplers.py:118), computed by the host so that
+ *                       the grid is bit-identical to the reference's
+ *   mean_x [R,9] out    the reference's `res` (last predictor mean, Gram-Schmidt'd, centre added)
+ *   process [R,T,9] out optional (NULL to skip): the recorded noisy iterates `xs` (samplers.py:153-156)
+ * One launch runs all T steps; the batch-mean gradient norm (samplers.py:130) is a grid-wide reduction. */
+GPB_API int gpb_sample_pc(const float *x0, int R, int K, int num_steps, float snr, const float *obj_bias,
+                  const float *trunk_weights, const float *pts_center, const float *step_noise,
+                  uint64_t seed, const float *time_grid, float *mean_x, float *process, void *workspace,
+                  size_t workspace_bytes, void *stream);
+
+/* replaces cond_ode_sampler (samplers.py:163-227) + scipy.integrate.solve_ivp(RK45) (samplers.py:205):
+ * Dormand-Prince 5(4) with SciPy's step controller, float64 state, fp32 score, one error norm over the
+ * whole [R*9] state, followed by the reference's Euler "denoise" step (:209-218).
+ *   x0 [R,9] f32        already-noised start (sigma(T0)*randn, plus init_x when tracking, :180)
+ *   pose [R,9] f64 out  (the reference returns float64, :206-207)
+ *   stats [4] i32 out   optional: nfev, accepted, rejected, status */
+GPB_API int gpb_sample_ode(const float *x0, int R, int K, float T0, float rtol, float atol, int denoise_steps,
+                   const float *obj_bias, const float *trunk_weights, const float *pts_center, double *pose,
+                   int *stats, void *workspace, size_t workspace_bytes, void *stream);
+
+/* replaces PoseNet.get_energy's arithmetic after the encoder (networks/posenet_agent.py:508-523 ->
+ * PoseEnergyNet.get_energy energynet.py:143-198, 'IP' decoupled): energy [B,K,2] = (rot, trans). */
+GPB_API int gpb_energy(const float *pose, int R, int K, float t, const float *obj_bias, const float *trunk_weights,
+               const float *pts_center, float *energy, void *stream);
+
+/* replaces sort_poses_by_energy (networks/reward.py:131-155) + sort_sRT_by_energy(ratio,'average')
+ * (utils/sgpa_utils.py:897-954) + average_quaternion_batch (utils/misc.py:227-249).
+ *   pose [B,K,9], energy [B,K,2] -> sorted_pose [B,K,9], sorted_energy [B,K,2], pooled_RT [B,4,4].
+ * K <= 128; keep = max(1, int(K * ratio)) is evaluated by the caller (sgpa_utils.py:912).  sorted_pose,
+ * sorted_energy and pooled_RT may each be NULL to skip that output. */
+GPB_API int gpb_rank_pool(const float *pose, const float *energy, int B, int K, int keep, float *sorted_pose,
+                  float *sorted_energy, float *pooled_RT, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (3) HOST-BUFFER CONVENIENCE — one call from host clouds to host poses (what bench.py's `e2e` times).
+ * ---------------------------------------------------------------------------------------------- */
+/* Kernel launch counter (for bench.py's gpu_launches claim): number of kernels this library has
+ * launched since load, across all threads. */
+GPB_API uint64_t gpb_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GENPOSE_B200_H */

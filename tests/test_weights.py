@@ -1,0 +1,60 @@
+"""CPU: host-side weight packing (BN fold, head stacking, W1 column split) against the oracle."""
+import numpy as np
+import torch
+
+from genpose_b200 import arch, synth, weights
+from oracle import genpose_oracle as O
+
+
+def test_pack_sizes_and_padding():
+    sd = synth.make_state_dict(0)
+    enc = weights.pack_encoder(sd)
+    trunk = weights.pack_trunk(sd)
+    assert enc.numel() == weights.encoder_floats() and trunk.numel() == weights.trunk_floats()
+    assert enc.dtype == torch.float32 and trunk.dtype == torch.float32
+
+
+def test_bn_fold_reproduces_shared_mlp():
+    """relu(W'.x + b') == relu(bn(conv(x))) for every folded layer (pytorch_utils.py:20-32)."""
+    sd = synth.make_state_dict(3)
+    rs = np.random.RandomState(0)
+    for l in range(4):
+        for s in range(2):
+            spec = arch.SA_LEVELS[l].mlps[s]
+            x = torch.from_numpy(rs.standard_normal((50, spec[0])).astype(np.float32))
+            ref = O._shared_mlp(sd, f"pts_encoder.SA_modules.{l}.mlps.{s}", x, 3, torch.float32)
+            h = x.double()
+            for j in range(3):
+                w, b = weights._fold(sd, f"pts_encoder.SA_modules.{l}.mlps.{s}.layer{j}")
+                h = torch.relu(h @ w.t() + b)
+            np.testing.assert_allclose(h.float().numpy(), ref.numpy(), rtol=2e-5, atol=2e-5)
+
+
+def test_trunk_pack_reproduces_score():
+    """Evaluate the hoisted form  O.relu(A_pose.pf + (A_pts.feat + a) + A_t.tf)  from the packed blob
+    with numpy and compare with the oracle's literal PoseScoreNet.forward."""
+    sd = synth.make_state_dict(5)
+    blob = weights.pack_trunk(sd).double().numpy()
+    off = 0
+
+    def take(n):
+        nonlocal off
+        out = blob[off:off + n]
+        off += n
+        return out
+    fw = take(64); tw = take(128 * 128).reshape(128, 128); tb = take(128)
+    p1 = take(9 * 256).reshape(9, 256); p1b = take(256); p2 = take(256 * 256).reshape(256, 256); p2b = take(256)
+    apts = take(1024 * 768).reshape(1024, 768); at = take(128 * 768).reshape(128, 768)
+    apose = take(256 * 768).reshape(256, 768); ab = take(768); ow = take(9 * 256).reshape(9, 256); ob = take(9)
+    rs = np.random.RandomState(1)
+    R = 6
+    feat = rs.standard_normal((R, 1024)); pose = rs.standard_normal((R, 9)); t = 0.37
+    xp = t * fw * 2 * np.pi
+    tf = np.maximum(np.concatenate([np.sin(xp), np.cos(xp)]) @ tw + tb, 0)
+    pf = np.maximum(np.maximum(pose @ p1 + p1b, 0) @ p2 + p2b, 0)
+    h = np.maximum(pf @ apose + (feat @ apts + ab) + tf @ at, 0)
+    f = np.stack([(h[:, (c // 3) * 256:(c // 3 + 1) * 256] * ow[c]).sum(1) + ob[c] for c in range(9)], 1)
+    ref = O.score(sd, torch.from_numpy(feat), torch.from_numpy(pose), torch.ones(R, 1, dtype=torch.float64) * t,
+                  dtype=torch.float64)
+    std = 0.01 * 5000.0 ** t
+    np.testing.assert_allclose(f / (std + 1e-7), ref.numpy(), rtol=1e-5, atol=1e-6)
