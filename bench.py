@@ -1,0 +1,318 @@
+#!/usr/bin/env python
+"""bench.py — pose-candidates/sec of the GenPose per-object inference hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config 2|3]
+
+One "step" = one pass of the hot path over one batch of synthetic input: B=64 objects x 1024 points per GPU,
+K=50 candidates, T=500 predictor-corrector steps (BASELINE.json configs[1]; --config 3 adds the energy
+network, ranking and pooling = configs[2]).  Prints ONE JSON line (rank 0).
+
+  value       whole-job pose-candidates/s with the clouds and prior noise already resident in HBM
+  e2e         the same through the reference-facing public API (PoseNet.pred_func [+ get_energy]) with HOST
+              buffers: pinned clouds -> H2D -> pipeline -> D2H of the poses, every step
+  roofline    dominant kernel (pc_sampler_kernel): algorithmic FLOPs (0.5335 MFLOP per
+              candidate-step) / CUDA-event duration, against the measured bf16 tensor peak
+  cpu_baseline  the oracle port (reference algorithm restated, oracle/) on this box's host cores, bounded sample
+  --impl reference  times that CPU implementation as its own arm (rank 0 only)
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+B_PER_GPU, K_CAND, T_STEPS = 64, 50, 500
+METRIC = "pose-candidates/sec (N=1024 pts, K=50, T=500)"
+UNIT = "pose-candidates/s"
+FLOP_PER_CAND_STEP = 2 * 266_752           # hoisted score evaluation
+FLOP_ENCODER_PER_OBJECT = 2.201e9
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return {"bf16_tflops": p["bf16_tflops"], "bf16_tflops_sustained": p.get("bf16_tflops_sustained", p["bf16_tflops"]),
+                "hbm_gbs": p["hbm_gbs"], "source": "measured (MEASURED_PEAKS.json)"}
+    return {"bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "hbm_gbs": 6650.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu_index, self.rows, self.proc, self.thr = gpu_index, [], None, None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu_index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thr = threading.Thread(target=self._read, daemon=True)
+            self.thr.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) < 7:
+                continue
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_oracle_rate(n_objects, K, T, config, seed=0, threads=None):
+    """Times the oracle port (reference algorithm on the CPU) on a bounded sample; returns (cands/s, seconds, detail)."""
+    from genpose_b200 import synth
+    from oracle import genpose_oracle as O
+    threads = threads or os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    sd = synth.make_state_dict(seed, kappa=-0.3)
+    clouds = synth.make_clouds(n_objects, seed)
+    data = synth.batch_from_clouds(clouds)
+    rows = n_objects * K
+    x0 = torch.from_numpy(synth.make_prior_noise(rows, seed))
+    noise = torch.from_numpy(synth.make_step_noise(T, rows, seed))
+    t0 = time.perf_counter()
+    feat = O.encode(sd, data["pts"])
+    t_enc = time.perf_counter() - t0
+    rep = feat.unsqueeze(1).repeat(1, K, 1).view(rows, -1)
+    cen = data["pts_center"].unsqueeze(1).repeat(1, K, 1).view(rows, -1)
+    pose = O.pc_sampler(sd, rep, cen, x0, noise, T).reshape(n_objects, K, 9)
+    t_all = time.perf_counter() - t0
+    if config == 3:
+        esd = synth.make_state_dict(seed + 100, kappa=-0.3)
+        en = O.get_energy(esd, data, pose)
+        O.rank_and_pool(pose, en)
+        t_all = time.perf_counter() - t0
+    return rows / t_all, t_all, {"encoder_s": round(t_enc, 3), "total_s": round(t_all, 3)}
+
+
+def run_reference_arm(args, rank, world):
+    """--impl reference: the reference's own CPU implementation of the path (oracle port: the reference is
+    Python + a CUDA-only extension and cannot travel to this box) on all host threads; rank 0 only."""
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    n_obj = args.ref_objects
+    for _ in range(args.warmup):
+        cpu_oracle_rate(1, K_CAND, 20, args.config, threads=cores)
+    rates, secs = [], []
+    for s in range(args.steps):
+        r, t, _ = cpu_oracle_rate(n_obj, K_CAND, T_STEPS, args.config, seed=s, threads=cores)
+        rates.append(r)
+        secs.append(t)
+    total_c = n_obj * K_CAND * args.steps
+    value = total_c / sum(secs)
+    sample = f"{n_obj} objects x K={K_CAND} x T={T_STEPS} per step (of the {B_PER_GPU}-object batch); oracle port, torch CPU fp32"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1000.0 * sum(secs) / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, world),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, world):
+    return {"workload": f"BASELINE configs[{args.config - 1}]: {B_PER_GPU} objects x 1024 pts per GPU, K={K_CAND}, T={T_STEPS}, "
+                        + ("ScoreNet PC sampling" if args.config == 2 else "Score + Energy rank + mean-pool"),
+            "global_batch_objects": B_PER_GPU * world, "candidates_per_object": K_CAND, "sampler": "pc", "sampling_steps": T_STEPS,
+            "parallelism": f"object-sharded dp{world}, one all-gather of poses", "l2_hygiene": "256 MiB buffer written between timed steps",
+            "noise": "in-kernel Philox4x32-10 (throughput mode)"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3])
+    ap.add_argument("--ref-objects", type=int, default=32, help="objects per step of the CPU reference arm / cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    from genpose_b200 import distributed as D
+    if args.impl == "reference":
+        rank = int(os.environ.get("RANK", "0"))
+        world = int(os.environ.get("WORLD_SIZE", "1"))
+        run_reference_arm(args, rank, world)
+        return
+
+    import torch.distributed as dist
+    from genpose_b200 import lib, ops, synth
+    from genpose_b200.pipeline import PosePipeline
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl ours needs a CUDA device (there is no CPU fallback)")
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    rank, world, local_rank = D.init_from_env("nccl")
+    dev = torch.device("cuda", local_rank)
+    peaks = load_peaks()
+
+    # ---- synthetic workload: each rank owns its own 64 objects (weak scaling) ------------------------------
+    seed = 100 + rank
+    sd = synth.make_state_dict(0, kappa=-0.3)
+    esd = synth.make_state_dict(100, kappa=-0.3) if args.config == 3 else None
+    pipe = PosePipeline(sd, esd, sampler="pc", sampling_steps=T_STEPS, noise_mode="philox")
+    eng = pipe.score_agent.net.engine
+    eeng = pipe.energy_agent.net.engine if esd is not None else None
+    clouds_host = torch.from_numpy(synth.make_clouds(B_PER_GPU, seed)).pin_memory()
+    clouds_dev = clouds_host.to(dev)
+    center_dev = clouds_dev.mean(dim=1).contiguous()
+    R = B_PER_GPU * K_CAND
+    x0_dev = torch.from_numpy(synth.make_prior_noise(R, seed)).to(dev)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    gathered = torch.empty(world * B_PER_GPU, K_CAND, 9, device=dev) if world > 1 else None
+    out_host = torch.empty(B_PER_GPU, K_CAND, 9).pin_memory()
+
+    def step_resident(i, ev=None):
+        feat = eng.encode(clouds_dev)
+        ob = eng.object_bias(feat)
+        if ev:
+            ev[0].record()
+        pose = eng.sample_pc(ob, center_dev, x0_dev, K_CAND, T_STEPS, seed=i)
+        if ev:
+            ev[1].record()
+        res = pose
+        if eeng is not None:
+            eob = eeng.object_bias(eeng.encode(clouds_dev))
+            en = eeng.energy(eob, center_dev, pose, K_CAND, 1e-5)
+            _, _, res = ops.rank_pool(pose.view(B_PER_GPU, K_CAND, 9), en.view(B_PER_GPU, K_CAND, 2))
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, pose.view(B_PER_GPU, K_CAND, 9))
+        return res
+
+    def step_e2e(i):
+        pts = clouds_host.to(dev, non_blocking=True)                        # H2D from pinned memory
+        data = PosePipeline.make_batch(pts)                                 # runner's batch dict (evaluation_single.py:394-403)
+        out = pipe.run(data, repeat_num=K_CAND)                             # PoseNet.pred_func [+ get_energy + rank/pool]
+        pose = out["pred_pose"]
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, pose.contiguous())
+        out_host.copy_(pose, non_blocking=True)                             # D2H of the result
+        torch.cuda.current_stream().synchronize()
+        return out_host
+
+    def timed(fn, n, with_kernel_events=False):
+        per_step, kernel_ms = [], []
+        for i in range(n):
+            flush.fill_(i & 0xFF)                                           # evict L2 between timed iterations
+            a, b = torch.cuda.Event(True), torch.cuda.Event(True)
+            kev = (torch.cuda.Event(True), torch.cuda.Event(True)) if with_kernel_events else None
+            torch.cuda.synchronize()
+            a.record()
+            fn(i, kev) if with_kernel_events else fn(i)
+            b.record()
+            torch.cuda.synchronize()
+            per_step.append(a.elapsed_time(b))
+            if kev:
+                kernel_ms.append(kev[0].elapsed_time(kev[1]))
+        return per_step, kernel_ms
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- warm-up, then the timed regions ----------------------------------------------------------------------
+    for i in range(max(args.warmup, 3)):
+        step_resident(i)
+        step_e2e(i)
+    sync_all()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    launches0 = lib.launch_count()
+    sync_all()
+    per_step, kernel_ms = timed(step_resident, args.steps, with_kernel_events=True)
+    sync_all()
+    launches = lib.launch_count() - launches0
+    per_step_e2e, _ = timed(step_e2e, args.steps)
+    sync_all()
+    clock_info = clocks.stop() if rank == 0 else None
+
+    total_ms = torch.tensor([sum(per_step), sum(per_step_e2e)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)                      # max over ranks
+    total_ms = total_ms.cpu().tolist()
+    cands = world * R * args.steps
+    value = cands / (total_ms[0] / 1000.0)
+    e2e_value = cands / (total_ms[1] / 1000.0)
+
+    if rank == 0:
+        k_ms = float(np.mean(kernel_ms))
+        ach = R * T_STEPS * FLOP_PER_CAND_STEP / (k_ms / 1000.0) / 1e12
+        peak = peaks["bf16_tflops_sustained"]
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": total_ms[0] / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": workload_config(args, world),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(clouds_host.numel() * 4 + R * 9 * 4),
+                    "d2h_bytes_per_step": int(out_host.numel() * 4), "ms_per_step": total_ms[1] / args.steps,
+                    "api": "PoseNet.pred_func(data, repeat_num=50)" + (" + PoseNet.get_energy + rank_pool" if args.config == 3 else "")},
+            "gpu_launches": int(launches),
+            "roofline": {"kernel": "pc_sampler_kernel (+ time_bias_table_kernel)", "bound": "tensor", "achieved": ach, "peak": peak,
+                         "unit": "TFLOP/s", "frac": ach / peak, "traffic": None, "kernel_ms": k_ms,
+                         "peak_kind": "bf16_tflops_sustained, " + peaks["source"],
+                         "note": "fp32 FFMA parity path: the tensor pipe is idle; fraction of the fp32-FFMA peak "
+                                 "(148 SM x 128 lanes x 2 x clk) is reported as frac_ffma",
+                         "algorithmic_flop_per_launch": R * T_STEPS * FLOP_PER_CAND_STEP},
+            "clocks": clock_info,
+        }
+        if clock_info and clock_info.get("sm_mhz"):
+            ffma_peak = 148 * 128 * 2 * clock_info["sm_mhz"] * 1e6 / 1e12
+            line["roofline"]["frac_ffma"] = ach / ffma_peak
+        if not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            cpu_oracle_rate(1, K_CAND, 10, args.config, threads=cores)      # page in
+            v, secs, detail = cpu_oracle_rate(args.ref_objects, K_CAND, T_STEPS, args.config, threads=cores)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": f"{args.ref_objects} of {B_PER_GPU} objects x K={K_CAND} x T={T_STEPS} ({secs:.1f} s), "
+                                              f"oracle port of the reference on torch CPU fp32", **detail}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

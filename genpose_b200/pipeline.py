@@ -1,0 +1,45 @@
+"""The per-object inference pipeline as one call: encoder -> K-candidate sampler -> (energy -> rank -> pool).
+This is `inference_pose` + `inference_energy` of runners/evaluation_single.py:356-489 without the pickle
+round-trip between the two agents.  It is built on the two agents' public methods
+(PoseNet.pred_func / get_energy), so it exercises exactly the reference-facing surface."""
+from types import SimpleNamespace
+from typing import Dict, Optional
+
+import torch
+
+from . import ops
+from .config import get_config
+from .posenet_agent import PoseNet
+
+
+def default_cfg(sampler="pc", sampling_steps=500, posenet_mode="score", noise_mode="philox", extra=()):
+    argv = ["--sampler_mode", sampler, "--posenet_mode", posenet_mode, "--noise_mode", noise_mode]
+    if sampling_steps is not None:
+        argv += ["--sampling_steps", str(sampling_steps)]
+    return get_config(argv + list(extra))
+
+
+class PosePipeline:
+    def __init__(self, score_state_dict, energy_state_dict=None, sampler="pc", sampling_steps=500, noise_mode="philox"):
+        self.score_agent = PoseNet(default_cfg(sampler, sampling_steps, "score", noise_mode))
+        self.score_agent.net.load_state_dict(score_state_dict)
+        self.energy_agent = None
+        if energy_state_dict is not None:
+            self.energy_agent = PoseNet(default_cfg(sampler, sampling_steps, "energy", noise_mode))
+            self.energy_agent.net.load_state_dict(energy_state_dict)
+
+    @staticmethod
+    def make_batch(pts: torch.Tensor) -> Dict[str, torch.Tensor]:
+        """The `data` dict of runners/evaluation_single.py:394-403 from device clouds [B,1024,3]."""
+        center = torch.mean(pts[:, :, :3], dim=1)
+        return {"pts": pts, "zero_mean_pts": pts - center.unsqueeze(1), "pts_center": center}
+
+    def run(self, data: Dict[str, torch.Tensor], repeat_num: int = 50, T0: Optional[float] = None, ratio: float = 0.6):
+        """-> dict(pred_pose [B,K,9], and with an energy net: energy [B,K,2], sorted_pose, sorted_energy, pooled_RT [B,4,4])."""
+        out = {"pred_pose": self.score_agent.pred_func(data, repeat_num=repeat_num, save_path=None, T0=T0)}
+        if self.energy_agent is not None:
+            pose = out["pred_pose"].float().contiguous()
+            energy = self.energy_agent.get_energy(data=data, pose_samples=pose, T=1e-5)            # evaluation_single.py:339-343
+            sp, se, rt = ops.rank_pool(pose, energy.contiguous(), ratio=ratio)                       # :344 + sgpa_utils.py:897
+            out.update(energy=energy, sorted_pose=sp, sorted_energy=se, pooled_RT=rt)
+        return out
