@@ -131,7 +131,9 @@ def test_encoder_levels_against_oracle(ops):
 @pytest.mark.parametrize("B,K,T", [(1, 1, 10), (3, 7, 40), (7, 50, 30), (2, 30, 500)])
 def test_pc_sampler_against_oracle(ops, B, K, T):
     seed = 30 + B
-    sd = synth.make_state_dict(seed, kappa=-0.3)
+    # the predictor's per-step gain is 17*sigma*|kappa|*dt: keep it < 1 at sigma = 50 (T = 10 needs a weaker field),
+    # otherwise the synthetic dynamics themselves diverge and no two fp32 implementations agree
+    sd = synth.make_state_dict(seed, kappa=-0.02 if T < 30 else -0.3)
     clouds = synth.make_clouds(B, seed)
     x0 = synth.make_prior_noise(B * K, seed)
     sn = synth.make_step_noise(T, B * K, seed)
