@@ -165,6 +165,8 @@ def main():
     ap.add_argument("--config", type=int, default=2, choices=[2, 3])
     ap.add_argument("--ref-objects", type=int, default=32, help="objects per step of the CPU reference arm / cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--precision", default="auto", choices=["auto", "bf16x3", "fp32"],
+                    help="dense layers of the sampler: tcgen05 bf16x3 (auto when the shape allows) or the fp32 FFMA parity kernel")
     args = ap.parse_args()
 
     from genpose_b200 import distributed as D
@@ -191,13 +193,15 @@ def main():
     seed = 100 + rank
     sd = synth.make_state_dict(0, kappa=-0.3)
     esd = synth.make_state_dict(100, kappa=-0.3) if args.config == 3 else None
-    pipe = PosePipeline(sd, esd, sampler="pc", sampling_steps=T_STEPS, noise_mode="philox")
+    pipe = PosePipeline(sd, esd, sampler="pc", sampling_steps=T_STEPS, noise_mode="philox", precision=args.precision)
     eng = pipe.score_agent.net.engine
     eeng = pipe.energy_agent.net.engine if esd is not None else None
     clouds_host = torch.from_numpy(synth.make_clouds(B_PER_GPU, seed)).pin_memory()
     clouds_dev = clouds_host.to(dev)
     center_dev = clouds_dev.mean(dim=1).contiguous()
     R = B_PER_GPU * K_CAND
+    use_tc = args.precision == "bf16x3" or (args.precision == "auto" and eng.tc_supported(R, K_CAND))
+    precision = "bf16x3" if use_tc else "fp32"
     x0_dev = torch.from_numpy(synth.make_prior_noise(R, seed)).to(dev)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
     gathered = torch.empty(world * B_PER_GPU, K_CAND, 9, device=dev) if world > 1 else None
@@ -208,7 +212,7 @@ def main():
         ob = eng.object_bias(feat)
         if ev:
             ev[0].record()
-        pose = eng.sample_pc(ob, center_dev, x0_dev, K_CAND, T_STEPS, seed=i)
+        pose = eng.sample_pc(ob, center_dev, x0_dev, K_CAND, T_STEPS, seed=i, precision=precision)
         if ev:
             ev[1].record()
         res = pose
@@ -285,16 +289,19 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": total_ms[0] / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": workload_config(args, world),
+            "dtype": "bf16x3 (bf16 tensor-core operands, error-compensated split, fp32 accumulate)" if use_tc else "f32",
+            "data": "synthetic", "config": workload_config(args, world),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(clouds_host.numel() * 4 + R * 9 * 4),
                     "d2h_bytes_per_step": int(out_host.numel() * 4), "ms_per_step": total_ms[1] / args.steps,
                     "api": "PoseNet.pred_func(data, repeat_num=50)" + (" + PoseNet.get_energy + rank_pool" if args.config == 3 else "")},
             "gpu_launches": int(launches),
-            "roofline": {"kernel": "pc_sampler_kernel (+ time_bias_table_kernel)", "bound": "tensor", "achieved": ach, "peak": peak,
+            "roofline": {"kernel": ("tc_pc_sampler_kernel" if use_tc else "pc_sampler_kernel") + " (+ time_bias_table_kernel)",
+                         "bound": "tensor", "achieved": ach, "peak": peak,
                          "unit": "TFLOP/s", "frac": ach / peak, "traffic": None, "kernel_ms": k_ms,
                          "peak_kind": "bf16_tflops_sustained, " + peaks["source"],
-                         "note": "fp32 FFMA parity path: the tensor pipe is idle; fraction of the fp32-FFMA peak "
-                                 "(148 SM x 128 lanes x 2 x clk) is reported as frac_ffma",
+                         "note": ("tcgen05 bf16x3: every algorithmic MAC costs 3 tensor-core MACs, so the tensor pipe does 3x `achieved`"
+                                  if use_tc else "fp32 FFMA parity path: the tensor pipe is idle; fraction of the fp32-FFMA peak "
+                                  "(148 SM x 128 lanes x 2 x clk) is reported as frac_ffma"),
                          "algorithmic_flop_per_launch": R * T_STEPS * FLOP_PER_CAND_STEP},
             "clocks": clock_info,
         }

@@ -41,6 +41,8 @@ _FLAGS = [
     ("pooling_mode", str, "nearest", {}),
     # genpose_b200 extension (not in the reference): 'philox' in-kernel noise or 'torch' generator-compatible noise
     ("noise_mode", str, "philox", {}),
+    # genpose_b200 extension: 'auto' | 'bf16x3' (tcgen05 tensor cores, error-compensated) | 'fp32' (FFMA parity kernel)
+    ("precision", str, "auto", {}),
 ]
 
 

@@ -21,6 +21,7 @@
 // output columns, keeps a 16-deep slice of their weights in registers (prefetching the next slice from
 // L2) and sweeps the tile's rows, whose activations are broadcast float4 reads from shared memory.
 #include "common.cuh"
+#include "sampler_common.cuh"
 
 namespace gpb {
 
@@ -207,18 +208,6 @@ __device__ __forceinline__ void trunk_tile(const TrunkSmem &s, const float *__re
     __syncthreads();
 }
 
-// F.normalize(v, eps=1e-12) pieces of pytorch3d rotation_6d_to_matrix as used by normalize_rotation
-// (utils/misc.py:259-265): b1 = a1/|a1|, b2 = normalize(a2 - (b1.a2) b1).
-__device__ __forceinline__ void gram_schmidt6(float *v) {
-    const float n1 = fmaxf(sqrtf(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]), 1e-12f);
-    const float b0 = v[0] / n1, b1 = v[1] / n1, b2 = v[2] / n1;
-    const float d = b0 * v[3] + b1 * v[4] + b2 * v[5];
-    const float c0 = v[3] - d * b0, c1 = v[4] - d * b1, c2 = v[5] - d * b2;
-    const float n2 = fmaxf(sqrtf(c0 * c0 + c1 * c1 + c2 * c2), 1e-12f);
-    v[0] = b0; v[1] = b1; v[2] = b2;
-    v[3] = c0 / n2; v[4] = c1 / n2; v[5] = c2 / n2;
-}
-
 // ---------------------------------------------------------------------------------------------------
 // object bias: obj_bias[b, n] = sum_k pts_feat[b,k] * A_pts[k][n] + a_b[n]; 8 objects per CTA
 // ---------------------------------------------------------------------------------------------------
@@ -318,43 +307,6 @@ trunk_eval_kernel(const float *__restrict__ pose, int R, int K, float t, const f
 // ---------------------------------------------------------------------------------------------------
 // predictor-corrector sampler (cond_pc_sampler, samplers.py:102-160)
 // ---------------------------------------------------------------------------------------------------
-struct PcParams {
-    const float *x0;          // [R,9]
-    int R, K, T;
-    float snr;
-    const float *obj_bias;    // [B,768]
-    const float *W;           // trunk weights
-    const float *pts_center;  // [B,3]
-    const float *noise;       // [T,2,R,9] or null
-    uint64_t seed;
-    const float *ts;          // [T] time grid (torch.linspace(1, eps, T), computed on the host in fp32)
-    const float *tb_table;    // [T,768]
-    float *partial;           // [2][gridDim] per-CTA sums of row norms
-    unsigned *barrier;        // monotonic arrival counter (zeroed before launch)
-    float *mean_x;            // [R,9] out
-    float *process;           // [R,T,9] out or null
-    int tiles_per_cta;
-};
-
-__device__ __forceinline__ void row_noise(const PcParams &p, int step, int which, int row, float *z) {
-    if (p.noise) {
-        const float *src = p.noise + (((size_t)step * 2 + which) * p.R + row) * 9;
-#pragma unroll
-        for (int c = 0; c < 9; ++c) z[c] = __ldg(src + c);
-    } else {
-        const uint2 key = make_uint2((unsigned)p.seed, (unsigned)(p.seed >> 32));
-        float buf[12];
-#pragma unroll
-        for (int q = 0; q < 3; ++q) {
-            const uint4 r = philox4x32_10(make_uint4((unsigned)row, (unsigned)step, (unsigned)(which * 3 + q), 0x47504232u), key);
-            const float2 a = box_muller(r.x, r.y), b = box_muller(r.z, r.w);
-            buf[4 * q + 0] = a.x; buf[4 * q + 1] = a.y; buf[4 * q + 2] = b.x; buf[4 * q + 3] = b.y;
-        }
-#pragma unroll
-        for (int c = 0; c < 9; ++c) z[c] = buf[c];
-    }
-}
-
 __global__ void __launch_bounds__(kNT, 1)
 pc_sampler_kernel(PcParams p) {
     extern __shared__ __align__(16) float smem[];
@@ -763,31 +715,10 @@ static int device_sm_count(int *out) {
     return GPB_OK;
 }
 
-struct SamplerWs {
-    float *tb_table;     // [T,768]
-    float *ts;           // [T]
-    float *partial;      // [2*1024] floats (PC)  /  doubles [4*1024] (ODE) share the slot
-    unsigned *barrier;   // [64] (256 B)
-    double *y, *ynew, *Kst;
-    size_t bytes;
-};
-static SamplerWs carve_sampler(void *base, int R, int T) {
-    SamplerWs w{};
-    size_t off = 0;
-    auto take = [&](size_t nbytes) {
-        char *p = base ? reinterpret_cast<char *>(base) + off : nullptr;
-        off += ((nbytes + 255) / 256) * 256;
-        return p;
-    };
-    w.barrier = reinterpret_cast<unsigned *>(take(256));
-    w.partial = reinterpret_cast<float *>(take(4 * 1024 * sizeof(double)));
-    w.ts = reinterpret_cast<float *>(take((size_t)(T > 0 ? T : 1) * sizeof(float)));
-    w.tb_table = reinterpret_cast<float *>(take((size_t)(T > 0 ? T : 1) * 768 * sizeof(float)));
-    w.y = reinterpret_cast<double *>(take((size_t)R * 9 * sizeof(double)));
-    w.ynew = reinterpret_cast<double *>(take((size_t)R * 9 * sizeof(double)));
-    w.Kst = reinterpret_cast<double *>(take((size_t)7 * R * 9 * sizeof(double)));
-    w.bytes = off;
-    return w;
+int launch_time_bias_table(const float *ts, int T, const float *W, float *table, cudaStream_t st) {
+    time_bias_table_kernel<<<T, kNT, 0, st>>>(ts, W, table);
+    GPB_LAUNCHED();
+    return GPB_OK;
 }
 
 }  // namespace gpb
@@ -863,8 +794,7 @@ extern "C" int gpb_sample_pc(const float *x0, int R, int K, int num_steps, float
     GPB_REQUIRE(smem <= 227 * 1024, "sample_pc: R=%d needs %zu B of shared memory per CTA; split the batch", R, smem);
 
     GPB_CUDA(cudaMemsetAsync(w.barrier, 0, 256, st));
-    time_bias_table_kernel<<<num_steps, kNT, 0, st>>>(time_grid, W, w.tb_table);
-    GPB_LAUNCHED();
+    if ((rc = launch_time_bias_table(time_grid, num_steps, W, w.tb_table, st))) return rc;
 
     PcParams p{};
     p.x0 = x0; p.R = R; p.K = K; p.T = num_steps; p.snr = snr;

@@ -87,6 +87,10 @@ class Engine:
                                        f"{trunk.numel()} vs {L.gpb_trunk_weights_floats()})")
         self.enc_w = enc.to(self.device)
         self.trunk_w = trunk.to(self.device)
+        tc = weights.pack_trunk_tc(state_dict)
+        if tc.numel() * 2 != L.gpb_trunk_tc_stream_bytes():
+            raise lib.GenPoseB200Error("tensor-core weight stream size disagrees with the library")
+        self.trunk_tc = tc.to(self.device)
         self._ws: Dict[Tuple[str, int], torch.Tensor] = {}
 
     def _workspace(self, kind: str, nbytes: int) -> torch.Tensor:
@@ -129,10 +133,22 @@ class Engine:
         return out
 
     # ---- a9: PC sampler -------------------------------------------------------------------------------
+    @staticmethod
+    def tc_supported(R: int, K: int) -> bool:
+        """tcgen05 sampler constraints: a 128-row tile spans <= 4 objects, one CTA per tile co-resident."""
+        sms = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
+        return 127 // K + 2 <= 4 and (R + 127) // 128 <= sms
+
     def sample_pc(self, obj_bias: torch.Tensor, pts_center: torch.Tensor, x0: torch.Tensor, K: int, num_steps: int,
                   step_noise: Optional[torch.Tensor] = None, seed: int = 0, snr: float = arch.SNR,
-                  return_process: bool = False):
+                  return_process: bool = False, precision: str = "fp32"):
+        """precision 'fp32' = FFMA parity kernel; 'bf16x3' = tcgen05 tensor-core kernel; 'auto' = tensor cores when
+        the shape allows."""
         R = x0.shape[0]
+        if precision == "auto":
+            precision = "bf16x3" if self.tc_supported(R, K) else "fp32"
+        if precision not in ("fp32", "bf16x3"):
+            raise lib.GenPoseB200Error(f"sample_pc: unknown precision {precision!r}")
         L = lib.load()
         ws = self._workspace("samp", L.gpb_sampler_workspace_bytes(R, num_steps))
         ts = time_grid(num_steps, self.device)
@@ -140,12 +156,16 @@ class Engine:
         process = torch.empty(R, num_steps, 9, dtype=torch.float32, device=self.device) if return_process else None
         if step_noise is not None and tuple(step_noise.shape) != (num_steps, 2, R, 9):
             raise lib.GenPoseB200Error(f"sample_pc: step_noise must be [T,2,R,9], got {tuple(step_noise.shape)}")
-        lib.check(L.gpb_sample_pc(
-            _chk(x0, torch.float32, "x0"), R, K, num_steps, float(snr), _chk(obj_bias, torch.float32, "obj_bias"),
-            self.trunk_w.data_ptr(), _chk(pts_center, torch.float32, "pts_center"),
-            0 if step_noise is None else _chk(step_noise, torch.float32, "step_noise"), int(seed) & (2 ** 64 - 1),
-            ts.data_ptr(), mean_x.data_ptr(), 0 if process is None else process.data_ptr(), ws.data_ptr(), ws.numel(),
-            _stream()), "sample_pc")
+        common = (0 if step_noise is None else _chk(step_noise, torch.float32, "step_noise"), int(seed) & (2 ** 64 - 1),
+                  ts.data_ptr(), mean_x.data_ptr(), 0 if process is None else process.data_ptr(), ws.data_ptr(), ws.numel(),
+                  _stream())
+        head = (_chk(x0, torch.float32, "x0"), R, K, num_steps, float(snr), _chk(obj_bias, torch.float32, "obj_bias"),
+                self.trunk_w.data_ptr())
+        if precision == "bf16x3":
+            lib.check(L.gpb_sample_pc_tc(*head, self.trunk_tc.data_ptr(), _chk(pts_center, torch.float32, "pts_center"), *common),
+                      "sample_pc_tc")
+        else:
+            lib.check(L.gpb_sample_pc(*head, _chk(pts_center, torch.float32, "pts_center"), *common), "sample_pc")
         return (mean_x, process) if return_process else mean_x
 
     # ---- a10: ODE sampler --------------------------------------------------------------------------------

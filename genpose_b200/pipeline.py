@@ -12,20 +12,21 @@ from .config import get_config
 from .posenet_agent import PoseNet
 
 
-def default_cfg(sampler="pc", sampling_steps=500, posenet_mode="score", noise_mode="philox", extra=()):
-    argv = ["--sampler_mode", sampler, "--posenet_mode", posenet_mode, "--noise_mode", noise_mode]
+def default_cfg(sampler="pc", sampling_steps=500, posenet_mode="score", noise_mode="philox", precision="auto", extra=()):
+    argv = ["--sampler_mode", sampler, "--posenet_mode", posenet_mode, "--noise_mode", noise_mode, "--precision", precision]
     if sampling_steps is not None:
         argv += ["--sampling_steps", str(sampling_steps)]
     return get_config(argv + list(extra))
 
 
 class PosePipeline:
-    def __init__(self, score_state_dict, energy_state_dict=None, sampler="pc", sampling_steps=500, noise_mode="philox"):
-        self.score_agent = PoseNet(default_cfg(sampler, sampling_steps, "score", noise_mode))
+    def __init__(self, score_state_dict, energy_state_dict=None, sampler="pc", sampling_steps=500, noise_mode="philox",
+                 precision="auto"):
+        self.score_agent = PoseNet(default_cfg(sampler, sampling_steps, "score", noise_mode, precision))
         self.score_agent.net.load_state_dict(score_state_dict)
         self.energy_agent = None
         if energy_state_dict is not None:
-            self.energy_agent = PoseNet(default_cfg(sampler, sampling_steps, "energy", noise_mode))
+            self.energy_agent = PoseNet(default_cfg(sampler, sampling_steps, "energy", noise_mode, precision))
             self.energy_agent.net.load_state_dict(energy_state_dict)
 
     @staticmethod

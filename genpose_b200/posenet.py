@@ -34,6 +34,9 @@ class GFObjectPose:
         # noise for the PC sampler: 'philox' (in-kernel, throughput) or 'torch' (torch.randn_like draws in the
         # reference's order on the CUDA generator -> same stream as the reference under torch.manual_seed)
         self.noise_mode = getattr(cfg, "noise_mode", "philox")
+        # engine of the dense layers inside the PC sampler: 'auto' (tcgen05 bf16x3 when the shape allows),
+        # 'bf16x3' (force tensor cores) or 'fp32' (FFMA parity kernel)
+        self.precision = getattr(cfg, "precision", "auto")
         self._philox_calls = 0
 
     # ---- nn.Module-like surface used by PoseNet --------------------------------------------------------
@@ -122,7 +125,7 @@ class GFObjectPose:
             if step_noise is None:
                 step_noise, seed = self._step_noise(num_steps, R, pts_feat.device)
             out = eng.sample_pc(ob, center, x0.float().contiguous(), repeat_num, num_steps, step_noise=step_noise,
-                                seed=seed, snr=0.16, return_process=return_process)
+                                seed=seed, snr=0.16, return_process=return_process, precision=self.precision)
             return out if return_process else (None, out)
         elif sampler == "ode":
             T0 = self.T if T0 is None else T0

@@ -107,3 +107,51 @@ def encoder_floats() -> int:
 
 def trunk_floats() -> int:
     return 64 + 128 * 128 + 128 + 9 * 256 + 256 + 256 * 256 + 256 + 1024 * 768 + 128 * 768 + 256 * 768 + 768 + 9 * 256 + 12
+
+
+# ---------------------------------------------------------------------------------------------------------
+# tcgen05 operand images (genpose_b200/csrc/tc_common.cuh, tc_sampler.cu)
+# ---------------------------------------------------------------------------------------------------------
+def split_bf16(w: torch.Tensor):
+    """w (fp32) -> (hi, lo) bf16 with hi = rn(w), lo = rn(w - hi)."""
+    hi = w.float().to(torch.bfloat16)
+    lo = (w.float() - hi.float()).to(torch.bfloat16)
+    return hi, lo
+
+
+def umma_image(w_bf16: torch.Tensor, variant: int = 0) -> torch.Tensor:
+    """[rows, K] bf16 -> canonical K-major no-swizzle operand image as int16 words.
+    variant 0 (used by the kernels): off(r,k) = (k/8)*(rows/8*128) + (r/8)*128 + (r%8)*16 + (k%8)*2  == [K/8][rows][8]
+    variant 1 (self-test only)     : off(r,k) = (r/8)*(K/8*128) + (k/8)*128 + (r%8)*16 + (k%8)*2     == [rows/8][K/8][8][8]"""
+    rows, K = w_bf16.shape
+    assert rows % 8 == 0 and K % 8 == 0
+    x = w_bf16.view(torch.int16).reshape(rows, K // 8, 8)
+    if variant == 0:
+        return x.permute(1, 0, 2).contiguous().reshape(-1)
+    return x.reshape(rows // 8, 8, K // 8, 8).permute(0, 2, 1, 3).contiguous().reshape(-1)
+
+
+def pack_trunk_tc(sd: Dict[str, torch.Tensor], prefix: str = "pose_score_net") -> torch.Tensor:
+    """The per-step weight stream of tc_pc_sampler_kernel: 65 stages of 16 KiB (int16 words):
+         stage 0        : P1 [256 x 16] (K padded 9 -> 16): hi image (8 KiB) | lo image (8 KiB)
+         stages 1..64   : for layer in (P2, head rot_x, head rot_y, head trans): for K-chunk kc in 0..7 (32 columns):
+                              hi image rows [4kc, 4kc+4) of [K/8][256][8]  (16 KiB), then the lo image chunk (16 KiB)
+    Head matrices are the pose-feature column block [:, 1152:1408] of fusion_tail_*.0.weight (scorenet.py:204)."""
+    g = lambda k: sd[f"{prefix}.{k}"].float()
+    stages = []
+    p1 = torch.zeros(256, 16)
+    p1[:, :9] = g("pose_encoder.0.weight")
+    hi, lo = split_bf16(p1)
+    stages.append(torch.cat([umma_image(hi), umma_image(lo)]))
+    off = arch.PTS_FEAT_DIM + arch.T_EMBED_DIM
+    layers = [g("pose_encoder.2.weight")] + [g(f"fusion_tail_{h}.0.weight")[:, off:] for h in arch.HEADS]
+    for w in layers:
+        assert tuple(w.shape) == (256, 256)
+        hi, lo = split_bf16(w)
+        ih, il = umma_image(hi).reshape(32, 256 * 8), umma_image(lo).reshape(32, 256 * 8)
+        for kc in range(8):
+            stages.append(ih[4 * kc: 4 * kc + 4].reshape(-1))
+            stages.append(il[4 * kc: 4 * kc + 4].reshape(-1))
+    out = torch.cat(stages).contiguous()
+    assert out.numel() * 2 == 65 * 16384
+    return out

@@ -120,6 +120,16 @@ GPB_API int gpb_sample_pc(const float *x0, int R, int K, int num_steps, float sn
                   uint64_t seed, const float *time_grid, float *mean_x, float *process, void *workspace,
                   size_t workspace_bytes, void *stream);
 
+/* Tensor-core (tcgen05, bf16x3 split, fp32 accumulate in TMEM) variant of gpb_sample_pc: same contract plus
+ * `tc_stream`, the bf16 operand-image stream of the trunk (gpb_trunk_tc_stream_bytes() bytes, produced by
+ * genpose_b200/weights.py::pack_trunk_tc).  Requires K >= 43 (a 128-row tile may span at most 4 objects) and
+ * ceil(R/128) <= #SMs; otherwise use gpb_sample_pc.  Poses agree with the fp32 path to ~2e-5. */
+GPB_API size_t gpb_trunk_tc_stream_bytes(void);
+GPB_API int gpb_sample_pc_tc(const float *x0, int R, int K, int num_steps, float snr, const float *obj_bias,
+                             const float *trunk_weights, const void *tc_stream, const float *pts_center,
+                             const float *step_noise, uint64_t seed, const float *time_grid, float *mean_x,
+                             float *process, void *workspace, size_t workspace_bytes, void *stream);
+
 /* replaces cond_ode_sampler (samplers.py:163-227) + scipy.integrate.solve_ivp(RK45) (samplers.py:205):
  * Dormand-Prince 5(4) with SciPy's step controller, float64 state, fp32 score, one error norm over the
  * whole [R*9] state, followed by the reference's Euler "denoise" step (:209-218).
@@ -149,6 +159,15 @@ GPB_API int gpb_rank_pool(const float *pose, const float *energy, int B, int K, 
 /* Kernel launch counter (for bench.py's gpu_launches claim): number of kernels this library has
  * launched since load, across all threads. */
 GPB_API uint64_t gpb_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * (4) SELF-TEST of the tcgen05 building block (one CTA: D[128,N] = A[128,K] . B[N,K]^T, bf16 split, fp32
+ *     accumulate in TMEM).  A fp32 row-major; Bhi/Blo = bf16 operand images in the canonical K-major
+ *     no-swizzle layout (genpose_b200/weights.py::umma_image).  variant/swap_fields select layout
+ *     conventions under test; n_terms 1..3 = how many of the bf16x3 products are accumulated.
+ * ---------------------------------------------------------------------------------------------- */
+GPB_API int gpb_selftest_umma(const float *A, const uint16_t *Bhi, const uint16_t *Blo, float *D, int K, int N,
+                              int variant, int swap_fields, int n_terms, void *stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,98 @@
+"""GPU: the tcgen05 path.  (1) the building block (operand images, smem/instruction descriptors, bulk copies,
+TMEM round trip) against a device matmul; (2) the tensor-core PC sampler against the reference goldens, the
+oracle and the fp32 FFMA kernel."""
+import numpy as np
+import pytest
+import torch
+
+from genpose_b200 import lib, synth, weights
+from oracle import genpose_oracle as O
+from tests import _cases
+
+pytestmark = pytest.mark.gpu
+
+
+def _selftest(K, N, variant, swap, n_terms, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    A = torch.randn(128, K, generator=g)
+    B = torch.randn(N, K, generator=g)
+    bhi, blo = weights.split_bf16(B)
+    D = torch.zeros(128, N, device="cuda")
+    Ad = A.cuda().contiguous()
+    ih = weights.umma_image(bhi, variant).cuda()
+    il = weights.umma_image(blo, variant).cuda()
+    lib.check(lib.load().gpb_selftest_umma(Ad.data_ptr(), ih.data_ptr(), il.data_ptr(), D.data_ptr(), K, N, variant, swap, n_terms,
+                                           torch.cuda.current_stream().cuda_stream), "selftest_umma")
+    torch.cuda.synchronize()
+    ahi, alo = weights.split_bf16(A)
+    terms = [ahi.double() @ bhi.double().t(), ahi.double() @ blo.double().t(), alo.double() @ bhi.double().t()]
+    ref = sum(terms[:n_terms])
+    exact = A.double() @ B.double().t()
+    return D.cpu().double(), ref, exact
+
+
+def test_umma_descriptor_conventions_report():
+    """Informational: which (layout variant, LBO/SBO field order) reproduces the matmul.  The kernels use (0, 0)."""
+    report = {}
+    for variant in (0, 1):
+        for swap in (0, 1):
+            d, ref, _ = _selftest(64, 256, variant, swap, 1)
+            report[(variant, swap)] = float((d - ref).abs().max())
+    print("umma conventions max|err|:", report)
+    assert report[(0, 0)] < 1e-3, report
+
+
+@pytest.mark.parametrize("K,N", [(16, 256), (64, 256), (128, 256), (64, 128), (32, 64)])
+def test_umma_bf16x3_matches_matmul(K, N):
+    d, ref, exact = _selftest(K, N, 0, 0, 3, seed=K + N)
+    assert float((d - ref).abs().max()) < 2e-4 * max(1.0, float(ref.abs().max()))       # same products, fp32 accumulate
+    assert float((d - exact).abs().max()) < 1e-3 * np.sqrt(K / 16)                        # ~2^-17 operand error per product
+
+
+@pytest.mark.parametrize("name", ["pc_B2_K5_T500", "pc_B3_K4_T50", "config1_pc_B1_K1_T10"])
+def test_tc_sampler_refuses_small_K(name):
+    from genpose_b200 import ops
+    case, g, inp = _cases.load(name)
+    eng = ops.Engine(inp["sd"])
+    assert not eng.tc_supported(case["B"] * case["K"], case["K"])
+
+
+@pytest.mark.parametrize("B,K,T", [(2, 50, 30), (3, 64, 100), (5, 50, 500), (64, 50, 20)])
+def test_tc_sampler_against_oracle_and_fp32_kernel(B, K, T):
+    from genpose_b200 import ops
+    seed = 50 + B
+    sd = synth.make_state_dict(seed, kappa=-0.3)
+    clouds = synth.make_clouds(B, seed)
+    x0 = synth.make_prior_noise(B * K, seed)
+    sn = synth.make_step_noise(T, B * K, seed)
+    data = synth.batch_from_clouds(clouds)
+    eng = ops.Engine(sd)
+    feat = eng.encode(torch.from_numpy(clouds).cuda())
+    ob = eng.object_bias(feat)
+    cen = data["pts_center"].cuda()
+    args = (ob, cen, torch.from_numpy(x0).cuda(), K, T)
+    p_tc, proc = eng.sample_pc(*args, step_noise=torch.from_numpy(sn).cuda(), precision="bf16x3", return_process=True)
+    p_32 = eng.sample_pc(*args, step_noise=torch.from_numpy(sn).cuda(), precision="fp32")
+    torch.cuda.synchronize()
+    assert torch.isfinite(p_tc).all() and torch.isfinite(proc).all()
+    d_kernels = float((p_tc - p_32).abs().max())
+    print(f"tc vs fp32 kernel: max|diff| {d_kernels:.3e}")
+    assert d_kernels <= 1e-3
+    if B * K <= 400:   # the CPU oracle finishes in seconds
+        ref_pose, _ = O.pred_func_pc(sd, data, K, T, torch.from_numpy(x0), torch.from_numpy(sn))
+        np.testing.assert_allclose(p_tc.cpu().numpy().reshape(B, K, 9), ref_pose.numpy(), rtol=0, atol=1e-3)
+
+
+def test_tc_sampler_philox_deterministic():
+    from genpose_b200 import ops
+    seed, B, K, T = 9, 4, 50, 40
+    sd = synth.make_state_dict(seed, kappa=-0.3)
+    eng = ops.Engine(sd)
+    data = synth.batch_from_clouds(synth.make_clouds(B, seed), device="cuda")
+    ob = eng.object_bias(eng.encode(data["pts"]))
+    x0 = torch.from_numpy(synth.make_prior_noise(B * K, seed)).cuda()
+    a = eng.sample_pc(ob, data["pts_center"], x0, K, T, seed=5, precision="bf16x3")
+    b = eng.sample_pc(ob, data["pts_center"], x0, K, T, seed=5, precision="bf16x3")
+    c = eng.sample_pc(ob, data["pts_center"], x0, K, T, seed=5, precision="fp32")
+    assert torch.equal(a, b)
+    assert float((a - c).abs().max()) <= 1e-3

@@ -20,5 +20,7 @@ for i in range(2):
     ob = eng.object_bias(feat)
     if what == "sampler":
         eng.sample_pc(ob, center, x0, K, T, seed=i)
+    if what == "tc_sampler":
+        eng.sample_pc(ob, center, x0, K, T, seed=i, precision="bf16x3")
 torch.cuda.synchronize()
 print("done", what)
