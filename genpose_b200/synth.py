@@ -137,6 +137,13 @@ def make_state_dict(seed: int = 0, kappa: float = 1.0, alpha: float = 0.05,
     return sd
 
 
+def stable_kappa(num_steps: int) -> float:
+    """Largest restoring strength (negative sign: the PC predictor as written moves AGAINST the score,
+    samplers.py:147-148) whose per-step gain 17*sigma_max*|kappa|*dt stays below 0.5, capped at 0.3.
+    Above gain ~2 the synthetic dynamics diverge and rounding differences are amplified without bound."""
+    return -min(0.3, 0.5 * (num_steps - 1) / (17.0 * arch.SIGMA_MAX))
+
+
 def make_prior_noise(rows: int, seed: int = 0, sigma: float = arch.SIGMA_MAX) -> np.ndarray:
     """x0 = sigma * randn [rows, 9] (ve_prior, sde.py:26-28); numpy stream for reproducibility."""
     rs = np.random.RandomState(3000 + seed)

@@ -133,7 +133,7 @@ def test_pc_sampler_against_oracle(ops, B, K, T):
     seed = 30 + B
     # the predictor's per-step gain is 17*sigma*|kappa|*dt: keep it < 1 at sigma = 50 (T = 10 needs a weaker field),
     # otherwise the synthetic dynamics themselves diverge and no two fp32 implementations agree
-    sd = synth.make_state_dict(seed, kappa=-0.02 if T < 30 else -0.3)
+    sd = synth.make_state_dict(seed, kappa=synth.stable_kappa(T))
     clouds = synth.make_clouds(B, seed)
     x0 = synth.make_prior_noise(B * K, seed)
     sn = synth.make_step_noise(T, B * K, seed)
@@ -152,7 +152,7 @@ def test_pc_sampler_philox_mode_statistics(ops):
     generator bit for bit; check it is deterministic in the seed, changes with it, and keeps the rotation
     part orthonormal."""
     seed, B, K, T = 5, 4, 25, 50
-    sd = synth.make_state_dict(seed, kappa=-0.3)
+    sd = synth.make_state_dict(seed, kappa=synth.stable_kappa(T))
     eng = ops.Engine(sd)
     clouds = synth.make_clouds(B, seed)
     data = synth.batch_from_clouds(clouds, device="cuda")

@@ -31,15 +31,12 @@ def _selftest(K, N, variant, swap, n_terms, seed=0):
     return D.cpu().double(), ref, exact
 
 
-def test_umma_descriptor_conventions_report():
-    """Informational: which (layout variant, LBO/SBO field order) reproduces the matmul.  The kernels use (0, 0)."""
-    report = {}
-    for variant in (0, 1):
-        for swap in (0, 1):
-            d, ref, _ = _selftest(64, 256, variant, swap, 1)
-            report[(variant, swap)] = float((d - ref).abs().max())
-    print("umma conventions max|err|:", report)
-    assert report[(0, 0)] < 1e-3, report
+def test_umma_single_product_exact():
+    """One bf16 x bf16 product term: the tensor core must reproduce the same-products reference to fp32
+    accumulation error.  (Layout variant 0 with (LBO, SBO) in their documented descriptor fields is what the
+    kernels use; the other conventions were probed once on hardware and fault)"""
+    d, ref, _ = _selftest(64, 256, 0, 0, 1)
+    assert float((d - ref).abs().max()) < 1e-4 * max(1.0, float(ref.abs().max()))
 
 
 @pytest.mark.parametrize("K,N", [(16, 256), (64, 256), (128, 256), (64, 128), (32, 64)])
@@ -61,7 +58,7 @@ def test_tc_sampler_refuses_small_K(name):
 def test_tc_sampler_against_oracle_and_fp32_kernel(B, K, T):
     from genpose_b200 import ops
     seed = 50 + B
-    sd = synth.make_state_dict(seed, kappa=-0.3)
+    sd = synth.make_state_dict(seed, kappa=synth.stable_kappa(T))
     clouds = synth.make_clouds(B, seed)
     x0 = synth.make_prior_noise(B * K, seed)
     sn = synth.make_step_noise(T, B * K, seed)
@@ -86,7 +83,7 @@ def test_tc_sampler_against_oracle_and_fp32_kernel(B, K, T):
 def test_tc_sampler_philox_deterministic():
     from genpose_b200 import ops
     seed, B, K, T = 9, 4, 50, 40
-    sd = synth.make_state_dict(seed, kappa=-0.3)
+    sd = synth.make_state_dict(seed, kappa=synth.stable_kappa(T))
     eng = ops.Engine(sd)
     data = synth.batch_from_clouds(synth.make_clouds(B, seed), device="cuda")
     ob = eng.object_bias(eng.encode(data["pts"]))

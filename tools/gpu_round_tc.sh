@@ -4,7 +4,7 @@ TAG=${1:-tc1}
 OUT=gpurun_out
 mkdir -p $OUT
 echo "== selftest + tc tests"
-timeout 300 python -m pytest tests/test_gpu_tc.py -q -x -s 2>&1 | tail -40 > $OUT/${TAG}_pytest_tc.log; tail -15 $OUT/${TAG}_pytest_tc.log
+timeout 300 python -m pytest tests/test_gpu_tc.py -q -s 2>&1 | tail -60 > $OUT/${TAG}_pytest_tc.log; tail -15 $OUT/${TAG}_pytest_tc.log
 if grep -q "passed" $OUT/${TAG}_pytest_tc.log && ! grep -q "failed" $OUT/${TAG}_pytest_tc.log; then
   echo "== full gpu suite"; timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -15 > $OUT/${TAG}_pytest_gpu.log; tail -4 $OUT/${TAG}_pytest_gpu.log
   echo "== bench auto (tc)"; timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline 2>&1 | tail -2 | tee $OUT/${TAG}_bench_tc.json
