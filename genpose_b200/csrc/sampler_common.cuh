@@ -33,6 +33,7 @@ struct PcParams {
     float *mean_x;            // [R,9] out
     float *process;           // [R,T,9] out or null
     int tiles_per_cta;
+    unsigned long long *dbg;  // optional [2][T][16] cycle stamps of CTA 0 (profiling aid; NULL in production)
 };
 
 __device__ __forceinline__ void row_noise(const PcParams &p, int step, int which, int row, float *z) {

@@ -1,25 +1,32 @@
 // Predictor-corrector sampler on the 5th-generation tensor cores (tcgen05 + TMEM), throughput mode.
 //
 // Same algorithm, launch contract and update code as pc_sampler_kernel (scorenet.cu); only the score network's
-// dense layers change engine: every layer is a 128-row x 256-column x K tcgen05.mma (kind::f16, bf16 operands,
-// fp32 accumulation in TMEM) evaluated as the error-compensated split
+// dense layers change engine: every layer is evaluated by tcgen05.mma (kind::f16, bf16 operands, fp32
+// accumulation in TMEM) as the error-compensated split
 //        A.B ~= Ahi.Bhi + Alo.Bhi + Ahi.Blo          (A = Ahi + Alo, B = Bhi + Blo, all bf16)
 // whose products are exact in fp32, so the result carries ~2^-17 relative error per operand instead of bf16's
 // 2^-9.  Measured in the oracle: final poses move by 2e-5 (single bf16: 9e-3, tf32: 8e-4) against
 // the 1e-3 parity bound.
 //
-// One CTA owns a 128-row tile of candidates for all T steps.  Roles (warp-specialised, 320 threads):
-//   warps 0-7  row warps.  Warp w reads TMEM lanes 32*(w%4).. (its rows) and columns [128*(w/4), +128).  They
-//              turn accumulators into the next layer's A operand (bias + ReLU + bf16 split, written straight
-//              into the canonical K-major operand image with conflict-free 16-byte stores), fold the three
-//              head outputs into the 9 score components, and (warps 0-3, one thread per row, pose state in
-//              registers) run the grid-wide gradient-norm reduction and the Langevin / Euler-Maruyama update.
-//   warp 8     one elected thread issues every tcgen05.mma and the tcgen05.commit's that publish "accumulator
-//              ready" / "weight stage free" on mbarriers; the warp also owns the TMEM allocation (512 columns =
-//              two 256-column accumulators, so a head's epilogue overlaps the next head's MMAs).
-//   warp 9     one elected thread streams the pre-tiled bf16 weight images (1,040 KiB per step, L2-resident) with
-//              cp.async.bulk into a 4 x 16 KiB ring, completing on mbarriers.
-// Per step and tile: P1 (K=16, x split in three bf16 pieces) -> P2 -> three heads, i.e. 5 + 4*48 MMAs.
+// One CTA owns a 128-row tile of candidates for all T steps; NOTHING of the per-step state leaves the SM:
+//   * activations never touch shared memory: the A operand of every layer lives in TENSOR MEMORY (written by the
+//     epilogue with tcgen05.st, lane = row, two bf16 per 32-bit column; consumed by the TS form of tcgen05.mma),
+//     TMEM map: D0 [0,128) D1 [128,256) accumulators (N = 128 "units", ping-pong), A_hi [256,384), A_lo [384,512);
+//   * the whole 227 KB of shared memory is therefore free for the weight stream: 12 slots x 16 KiB of pre-tiled bf16
+//     operand images (hi | lo; 1,040 KiB per step, L2-resident) fetched with cp.async.bulk on mbarriers, 12 K-chunks ahead;
+//   * pose state, noise and score of a row live in the registers of "its" thread.
+// Roles (warp-specialised, 320 threads):
+//   warps 0-7  row warps: warp w owns TMEM lanes 32*(w%4).. (rows) and the column sub-half w/4 of every unit.
+//              Layers 0/1: accumulator -> bias + ReLU -> bf16 hi/lo -> A operand (unit a is held in registers until
+//              the layer's last MMA has consumed the old A).  Heads: relu(acc + obj_bias + t_bias) . O, overlapped
+//              with the next unit's MMAs.  Warps 0-3 then run the grid-wide gradient-norm reduction and the
+//              Langevin / Euler-Maruyama update (noise for the step is generated while the tensor core works);
+//              warps 4-7 meanwhile refresh the (object bias + time bias) table for the next step.
+//   warp 8     one elected thread issues every tcgen05.mma / tcgen05.commit; the warp owns the TMEM allocation.
+//   warp 9     one elected thread runs the weight producer.
+// Per step and tile: 10 units (2 per layer), 10 + 4*96 MMAs of 128x128x16.
+// (The first working version kept A in shared memory, 128 KB, and could only prefetch 2 weight-slot pairs:
+//  tc_sampler_v1_smemA.cu.txt, 18.2 ms per 3200x500 launch.)
 #include "common.cuh"
 #include "sampler_common.cuh"
 #include "tc_common.cuh"
@@ -30,71 +37,65 @@ using namespace tc;
 constexpr int kTcRows = 128;
 constexpr int kTcRowWarps = 8;
 constexpr int kTcThreads = (kTcRowWarps + 2) * 32;
-constexpr uint32_t kStageBytes = 16384;
-constexpr int kStages = 4;
-constexpr int kStagesPerStep = 1 + 4 * 16;      // P1 (hi|lo in one stage) + 4 layers x 8 K-chunks x (hi, lo)
-constexpr uint32_t kLboA = 2048, kLboB = 4096, kSbo = 128;
+constexpr uint32_t kSlotBytes = 16384;
+constexpr int kSlots = 12;
+constexpr int kSlotsPerStep = 1 + 4 * 2 * 8;       // P1 (both units) + 4 layers x 2 units x 8 K-chunks, each slot = hi image | lo image
+constexpr uint32_t kLboB = 2048, kSbo = 128;       // 128-row operand images
 constexpr int kMaxObjPerTile = 4;
+constexpr uint32_t kColD = 0, kColAhi = 256, kColAlo = 384;
 using TL = TrunkLayout;
 
 // dynamic shared memory map (bytes)
-constexpr uint32_t kOffAhi = 0;
-constexpr uint32_t kOffAlo = kOffAhi + 65536;
-constexpr uint32_t kOffX = kOffAlo + 65536;                       // 3 pieces x 4 KiB (rows x 16 K)
-constexpr uint32_t kOffRing = kOffX + 3 * 4096;
-constexpr uint32_t kOffOb = kOffRing + kStages * kStageBytes;     // [4][768] fp32 object biases of this tile
-constexpr uint32_t kOffFpart = kOffOb + kMaxObjPerTile * 768 * 4; // [128][12] fp32 partial scores of the upper column half
+constexpr uint32_t kOffRing = 0;
+constexpr uint32_t kOffObt = kOffRing + kSlots * kSlotBytes;          // [4][768] fp32: obj_bias + t_bias(step)
+constexpr uint32_t kOffOw = kOffObt + kMaxObjPerTile * 768 * 4;       // [9][256] fp32 output layer + [16] bias
+constexpr uint32_t kOffBias = kOffOw + (9 * 256 + 16) * 4;            // p1_b [256] | p2_b [256]
+constexpr uint32_t kOffFpart = kOffBias + 512 * 4;                    // [128][12] fp32 partial scores of column sub-half 1
 constexpr uint32_t kTcSmemBytes = kOffFpart + 128 * 12 * 4;
-static_assert(kTcSmemBytes <= 227 * 1024 - 2048, "tc sampler shared memory budget");
+static_assert(kTcSmemBytes <= 227 * 1024 - 1024, "tc sampler shared memory budget");
 
 struct TcPcParams {
     PcParams pc;
-    const uint8_t *wstream;   // kStagesPerStep x 16 KiB of bf16 operand images (genpose_b200/weights.py::pack_trunk_tc)
+    const uint8_t *wstream;   // kSlotsPerStep x 8 KiB of bf16 operand images (genpose_b200/weights.py::pack_trunk_tc)
 };
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
-
-// write one row's pose as three bf16 pieces (x = x1 + x2 + x3 to 24 bits) into the K=16 operand images
-__device__ __forceinline__ void write_x_pieces(uint8_t *sX, int r, const float *x) {
-    __nv_bfloat16 p[3][16];
-#pragma unroll
-    for (int c = 0; c < 16; ++c) {
-        const float v = c < 9 ? x[c] : 0.f;
-        p[0][c] = __float2bfloat16_rn(v);
-        const float r1 = v - __bfloat162float(p[0][c]);
-        p[1][c] = __float2bfloat16_rn(r1);
-        p[2][c] = __float2bfloat16_rn(r1 - __bfloat162float(p[1][c]));
-    }
-#pragma unroll
-    for (int pc = 0; pc < 3; ++pc)
-#pragma unroll
-        for (int k8 = 0; k8 < 2; ++k8) {
-            const uint32_t off = (uint32_t)pc * 4096u + (uint32_t)k8 * kLboA + (uint32_t)(r >> 3) * kSbo + (uint32_t)(r & 7) * 16u;
-            *reinterpret_cast<uint4 *>(sX + off) =
-                make_uint4(pack_bf16(p[pc][8 * k8 + 0], p[pc][8 * k8 + 1]), pack_bf16(p[pc][8 * k8 + 2], p[pc][8 * k8 + 3]),
-                           pack_bf16(p[pc][8 * k8 + 4], p[pc][8 * k8 + 5]), pack_bf16(p[pc][8 * k8 + 6], p[pc][8 * k8 + 7]));
-        }
+__device__ __forceinline__ void red_release_add(unsigned *p, unsigned v) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-__global__ void __launch_bounds__(kTcThreads, 1)
+// bias + ReLU + bf16 hi/lo split of 32 accumulator columns -> 16 + 16 packed words (column pairs)
+__device__ __forceinline__ void relu_split32(const uint32_t (&v)[32], const float *bias, uint32_t *hi, uint32_t *lo) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const float2 bb = *reinterpret_cast<const float2 *>(bias + 2 * j);
+        split_bf16x2(fmaxf(__uint_as_float(v[2 * j]) + bb.x, 0.f), fmaxf(__uint_as_float(v[2 * j + 1]) + bb.y, 0.f), hi[j], lo[j]);
+    }
+}
+
+__global__ void __launch_bounds__(kTcThreads, 1)   // 10 warps are allocated as 12 (granularity 4): <= 168 registers per thread
 tc_pc_sampler_kernel(TcPcParams tp) {
     const PcParams &p = tp.pc;
     extern __shared__ __align__(1024) uint8_t smem[];
-    uint8_t *sAhi = smem + kOffAhi, *sAlo = smem + kOffAlo, *sX = smem + kOffX, *sRing = smem + kOffRing;
-    float *sOb = reinterpret_cast<float *>(smem + kOffOb);
+    uint8_t *sRing = smem + kOffRing;
+    float *sObt = reinterpret_cast<float *>(smem + kOffObt);
+    float *sOw = reinterpret_cast<float *>(smem + kOffOw);
+    float *sBias = reinterpret_cast<float *>(smem + kOffBias);
     float *sFpart = reinterpret_cast<float *>(smem + kOffFpart);
-    __shared__ __align__(8) uint64_t bar_full[kStages], bar_empty[kStages], bar_acc_full[2], bar_acc_empty[2], bar_x_ready, bar_a_ready;
+    __shared__ __align__(8) uint64_t bar_full[kSlots], bar_empty[kSlots], bar_acc_full[2], bar_acc_empty[2], bar_x_ready, bar_a_ready;
     __shared__ uint32_t s_tmem_base;
     __shared__ float s_red[4];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int row0 = blockIdx.x * kTcRows;
     const int obj_lo = row0 / p.K;
+    const int n_obj = (min(row0 + kTcRows, p.R) - 1) / p.K - obj_lo + 1;
+    const float *W = p.W;
 
     if (tid == 0) {
-        for (int s = 0; s < kStages; ++s) {
+        for (int s = 0; s < kSlots; ++s) {
             mbar_init(&bar_full[s], 1);
             mbar_init(&bar_empty[s], 1);
         }
@@ -107,199 +108,271 @@ tc_pc_sampler_kernel(TcPcParams tp) {
         fence_mbar_init();
     }
     if (warp == kTcRowWarps) tmem_alloc(&s_tmem_base, 512);
-    // object biases of the (at most 4) objects this tile touches
-    {
-        const int last_row = min(row0 + kTcRows, p.R) - 1;
-        const int n_obj = last_row / p.K - obj_lo + 1;
-        for (int i = tid; i < n_obj * 768; i += kTcThreads) sOb[i] = p.obj_bias[(size_t)obj_lo * 768 + i];
+    for (int i = tid; i < n_obj * 768; i += kTcThreads) sObt[i] = p.obj_bias[(size_t)obj_lo * 768 + i] + p.tb_table[i % 768];   // step 0
+    for (int i = tid; i < 9 * 256 + 12; i += kTcThreads) sOw[i] = W[TL::o_w + i];   // o_w then o_b are adjacent
+    for (int i = tid; i < 256; i += kTcThreads) {
+        sBias[i] = W[TL::p1_b + i];
+        sBias[256 + i] = W[TL::p2_b + i];
     }
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem_base = s_tmem_base;
-    const uint32_t idesc = make_idesc_bf16_f32(128, 256);
+    const uint32_t idesc = make_idesc_bf16_f32(128, 128);
+    const bool dbg_cta = p.dbg != nullptr && blockIdx.x == 0;
 
     if (warp == kTcRowWarps + 1) {
         // =============================== weight producer ===============================
         if (lane == 0) {
-            const uint32_t total = (uint32_t)p.T * kStagesPerStep;
+            const uint32_t total = (uint32_t)p.T * kSlotsPerStep;
             for (uint32_t it = 0; it < total; ++it) {
-                const uint32_t s = it % kStages;
-                mbar_wait(&bar_empty[s], ((it / kStages) & 1u) ^ 1u);
-                mbar_arrive_expect_tx(&bar_full[s], kStageBytes);
-                bulk_g2s(sRing + s * kStageBytes, tp.wstream + (size_t)(it % kStagesPerStep) * kStageBytes, kStageBytes, &bar_full[s]);
+                const uint32_t s = it % kSlots;
+                mbar_wait(&bar_empty[s], ((it / kSlots) & 1u) ^ 1u);
+                mbar_arrive_expect_tx(&bar_full[s], kSlotBytes);
+                bulk_g2s(sRing + s * kSlotBytes, tp.wstream + (size_t)(it % kSlotsPerStep) * kSlotBytes, kSlotBytes, &bar_full[s]);
             }
         }
     } else if (warp == kTcRowWarps) {
         // =============================== MMA issuer ===============================
-        if (lane == 0) {
-            const uint32_t ahi = smem_u32(sAhi), alo = smem_u32(sAlo), xb = smem_u32(sX), ring = smem_u32(sRing);
-            uint32_t g = 0, it = 0, xr = 0, ar = 0;
+        // The WHOLE warp runs this loop (uniform control flow => descriptors and TMEM addresses live in uniform registers);
+        // one elected lane issues each tcgen05.mma / tcgen05.commit.
+        {
+            const uint32_t ring = smem_u32(sRing);
+            const uint32_t t_ahi = tmem_base + kColAhi, t_alo = tmem_base + kColAlo;
+            uint32_t u = 0, it = 0, xr = 0, ar = 0;
             for (int step = 0; step < p.T; ++step) {
-                // ---- layer 0: h1_pre = x . P1^T   (K = 16; x1,x2,x3 pieces against P1 hi|lo)
+                unsigned long long *ds = (dbg_cta && lane == 0) ? p.dbg + ((size_t)p.T + step) * 16 : nullptr;
+                unsigned long long w_full = 0, w_a = 0, w_acc = 0, tq = 0;
+                if (ds) ds[0] = clock64();
+                // ---- layer 0: h1_pre = x . P1^T   (K = 16; x pieces x1,x2,x3 at A_hi[0,8),[8,16),[16,24); P1 hi|lo per unit)
                 mbar_wait(&bar_x_ready, xr & 1u);
                 ++xr;
+                if (ds) ds[1] = clock64();
                 {
-                    const uint32_t b = g & 1u, n = g >> 1;
-                    mbar_wait(&bar_acc_empty[b], (n & 1u) ^ 1u);
-                    const uint32_t s = it % kStages;
-                    mbar_wait(&bar_full[s], (it / kStages) & 1u);
-                    tc_fence_after_sync();
-                    const uint32_t d = tmem_base + b * 256u;
-                    const uint64_t bhi = make_smem_desc(ring + s * kStageBytes, kLboB, kSbo);
-                    const uint64_t blo = make_smem_desc(ring + s * kStageBytes + 8192u, kLboB, kSbo);
-                    const uint64_t x1 = make_smem_desc(xb, kLboA, kSbo), x2 = make_smem_desc(xb + 4096u, kLboA, kSbo),
-                                   x3 = make_smem_desc(xb + 8192u, kLboA, kSbo);
-                    umma_bf16(d, x1, bhi, idesc, false);
-                    umma_bf16(d, x2, bhi, idesc, true);
-                    umma_bf16(d, x3, bhi, idesc, true);
-                    umma_bf16(d, x1, blo, idesc, true);
-                    umma_bf16(d, x2, blo, idesc, true);
-                    umma_commit(&bar_empty[s]);
+                    const uint32_t s = it % kSlots;
+                    mbar_wait(&bar_full[s], (it / kSlots) & 1u);
+                    for (int half = 0; half < 2; ++half) {
+                        const uint32_t b = u & 1u, n = u >> 1;
+                        mbar_wait(&bar_acc_empty[b], (n & 1u) ^ 1u);
+                        tc_fence_after_sync();
+                        const uint32_t d = tmem_base + kColD + b * 128u;
+                        const uint64_t bhi = make_smem_desc(ring + s * kSlotBytes + (uint32_t)half * 8192u, kLboB, kSbo);
+                        const uint64_t blo = make_smem_desc(ring + s * kSlotBytes + (uint32_t)half * 8192u + 4096u, kLboB, kSbo);
+                        if (elect_one_sync()) {
+                            umma_bf16_ts(d, t_ahi + 0u, bhi, idesc, false);
+                            umma_bf16_ts(d, t_ahi + 8u, bhi, idesc, true);
+                            umma_bf16_ts(d, t_ahi + 16u, bhi, idesc, true);
+                            umma_bf16_ts(d, t_ahi + 0u, blo, idesc, true);
+                            umma_bf16_ts(d, t_ahi + 8u, blo, idesc, true);
+                            if (half == 1) umma_commit(&bar_empty[s]);
+                            umma_commit(&bar_acc_full[b]);
+                        }
+                        __syncwarp();
+                        ++u;
+                    }
                     ++it;
-                    umma_commit(&bar_acc_full[b]);
-                    ++g;
                 }
-                // ---- layers 1..4: P2, head rot_x, head rot_y, head trans   (K = 256 each)
+                // ---- layers 1..4: P2, head rot_x, head rot_y, head trans   (K = 256, two N = 128 units each)
                 for (int layer = 1; layer <= 4; ++layer) {
+                    if (ds) tq = clock64();
                     if (layer <= 2) {
                         mbar_wait(&bar_a_ready, ar & 1u);
                         ++ar;
                     }
-                    const uint32_t b = g & 1u, n = g >> 1;
-                    mbar_wait(&bar_acc_empty[b], (n & 1u) ^ 1u);
-                    tc_fence_after_sync();
-                    const uint32_t d = tmem_base + b * 256u;
-                    bool acc = false;
-                    for (int kc = 0; kc < 8; ++kc) {
-                        const uint32_t s0 = it % kStages, s1 = (it + 1) % kStages;
-                        mbar_wait(&bar_full[s0], (it / kStages) & 1u);
-                        mbar_wait(&bar_full[s1], ((it + 1) / kStages) & 1u);
-                        tc_fence_after_sync();
-#pragma unroll
-                        for (int j = 0; j < 2; ++j) {
-                            const uint32_t k8 = (uint32_t)kc * 4u + 2u * j;
-                            const uint64_t a_hi = make_smem_desc(ahi + k8 * kLboA, kLboA, kSbo);
-                            const uint64_t a_lo = make_smem_desc(alo + k8 * kLboA, kLboA, kSbo);
-                            const uint64_t b_hi = make_smem_desc(ring + s0 * kStageBytes + 2u * j * kLboB, kLboB, kSbo);
-                            const uint64_t b_lo = make_smem_desc(ring + s1 * kStageBytes + 2u * j * kLboB, kLboB, kSbo);
-                            umma_bf16(d, a_hi, b_hi, idesc, acc);
-                            acc = true;
-                            umma_bf16(d, a_lo, b_hi, idesc, true);
-                            umma_bf16(d, a_hi, b_lo, idesc, true);
-                        }
-                        umma_commit(&bar_empty[s0]);
-                        umma_commit(&bar_empty[s1]);
-                        it += 2;
+                    if (ds) {
+                        w_a += clock64() - tq;
+                        ds[2 + layer] = clock64();
                     }
-                    umma_commit(&bar_acc_full[b]);
-                    ++g;
+                    for (int half = 0; half < 2; ++half) {
+                        const uint32_t b = u & 1u, n = u >> 1;
+                        if (ds) tq = clock64();
+                        mbar_wait(&bar_acc_empty[b], (n & 1u) ^ 1u);
+                        if (ds) w_acc += clock64() - tq;
+                        const uint32_t d = tmem_base + kColD + b * 128u;
+#pragma unroll 1
+                        for (int kc = 0; kc < 8; ++kc) {
+                            const uint32_t s = it % kSlots;
+                            if (ds) tq = clock64();
+                            mbar_wait(&bar_full[s], (it / kSlots) & 1u);
+                            if (ds) w_full += clock64() - tq;
+                            tc_fence_after_sync();
+                            const uint32_t sb = ring + s * kSlotBytes;
+                            const uint32_t acol = (uint32_t)kc * 16u;                    // K index / 2
+                            if (elect_one_sync()) {
+#pragma unroll
+                                for (int j = 0; j < 2; ++j) {
+                                    const uint64_t b_hi = make_smem_desc(sb + 2u * j * kLboB, kLboB, kSbo);
+                                    const uint64_t b_lo = make_smem_desc(sb + 8192u + 2u * j * kLboB, kLboB, kSbo);
+                                    umma_bf16_ts(d, t_ahi + acol + 8u * j, b_hi, idesc, (kc | j) != 0);
+                                    umma_bf16_ts(d, t_alo + acol + 8u * j, b_hi, idesc, true);
+                                    umma_bf16_ts(d, t_ahi + acol + 8u * j, b_lo, idesc, true);
+                                }
+                                umma_commit(&bar_empty[s]);
+                                if (kc == 7) umma_commit(&bar_acc_full[b]);
+                            }
+                            __syncwarp();
+                            ++it;
+                        }
+                        ++u;
+                    }
+                }
+                if (ds) {
+                    ds[7] = clock64();
+                    ds[8] = w_full;
+                    ds[9] = w_a;
+                    ds[10] = w_acc;
                 }
             }
         }
     } else {
         // =============================== row warps ===============================
-        const int q = warp & 3, half = warp >> 2;
+        const int q = warp & 3, cs = warp >> 2;
         const int r = q * 32 + lane;              // row of the tile == TMEM lane
         const int row = row0 + r;                 // global candidate row
         const bool valid = row < p.R;
-        const int cb = half * 128;                // this warp's column half
-        const uint32_t tm_lane = (uint32_t)(q * 32) << 16;
-        const uint32_t a_row_off = (uint32_t)(r >> 3) * kSbo + (uint32_t)(r & 7) * 16u;
-        const float *ob_row = sOb + (size_t)((valid ? row : p.R - 1) / p.K - obj_lo) * 768;
-        const float *W = p.W;
+        const uint32_t tm_row = tmem_base + ((uint32_t)(q * 32) << 16);
+        const float *obt_row = sObt + (size_t)((valid ? row : p.R - 1) / p.K - obj_lo) * 768;
+        const bool dbg = dbg_cta && tid == 0;
 
         float x[9];
 #pragma unroll
-        for (int c = 0; c < 9; ++c) x[c] = (valid && half == 0) ? p.x0[(size_t)row * 9 + c] : 0.f;
-        if (half == 0) {
-            write_x_pieces(sX, r, x);
-            fence_proxy_async_smem();
+        for (int c = 0; c < 9; ++c) x[c] = (valid && cs == 0) ? p.x0[(size_t)row * 9 + c] : 0.f;
+        auto publish_x = [&]() {   // three bf16 pieces of the pose row -> A_hi[0,24)
+            uint32_t pc[3][8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                __nv_bfloat16 b1[2], b2[2], b3[2];
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int c = 2 * j + e;
+                    const float v = c < 9 ? x[c < 9 ? c : 0] : 0.f;
+                    b1[e] = __float2bfloat16_rn(v);
+                    const float r1 = v - __bfloat162float(b1[e]);
+                    b2[e] = __float2bfloat16_rn(r1);
+                    b3[e] = __float2bfloat16_rn(r1 - __bfloat162float(b2[e]));
+                }
+                pc[0][j] = pack_bf16(b1[0], b1[1]);
+                pc[1][j] = pack_bf16(b2[0], b2[1]);
+                pc[2][j] = pack_bf16(b3[0], b3[1]);
+            }
+            tmem_st8(tm_row + kColAhi + 0u, pc[0]);
+            tmem_st8(tm_row + kColAhi + 8u, pc[1]);
+            tmem_st8(tm_row + kColAhi + 16u, pc[2]);
+            tmem_st_wait();
+            tc_fence_before_sync();
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar_x_ready);
-        }
+        };
+        if (cs == 0) publish_x();
+
         const float step_size = p.ts[0] - p.ts[1];
         const float sqrt_step = sqrtf(step_size);
         const float snr_norm = (float)((double)p.snr * 3.0);
-        uint32_t g = 0;
+        uint32_t u = 0;
         unsigned bar_target = 0;
 
         for (int step = 0; step < p.T; ++step) {
-            // ---- epilogues of layers 0 and 1: accumulator -> bias + ReLU -> bf16 hi/lo -> A operand image ----
-            for (int layer = 0; layer < 2; ++layer) {
-                const uint32_t b = g & 1u, n = g >> 1;
-                mbar_wait(&bar_acc_full[b], n & 1u);
-                tc_fence_after_sync();
-                const float *bias = W + (layer == 0 ? TL::p1_b : TL::p2_b);
+            unsigned long long *ds = dbg ? p.dbg + (size_t)step * 16 : nullptr;
+            if (ds) ds[0] = clock64();
+            // ---- layers 0 and 1: accumulator -> bias + ReLU -> bf16 hi/lo -> A operand in tensor memory ----
 #pragma unroll 1
-                for (int c0 = cb; c0 < cb + 128; c0 += 32) {
-                    uint32_t v[32];
-                    tmem_ld32(tmem_base + tm_lane + b * 256u + (uint32_t)c0, v);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int j8 = 0; j8 < 4; ++j8) {
-                        uint32_t hi[4], lo[4];
-                        const float4 b0 = __ldg(reinterpret_cast<const float4 *>(bias + c0 + 8 * j8));
-                        const float4 b1 = __ldg(reinterpret_cast<const float4 *>(bias + c0 + 8 * j8 + 4));
-                        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            __nv_bfloat16 h0, l0, h1, l1;
-                            split_bf16(fmaxf(__uint_as_float(v[8 * j8 + 2 * e]) + bb[2 * e], 0.f), h0, l0);
-                            split_bf16(fmaxf(__uint_as_float(v[8 * j8 + 2 * e + 1]) + bb[2 * e + 1], 0.f), h1, l1);
-                            hi[e] = pack_bf16(h0, h1);
-                            lo[e] = pack_bf16(l0, l1);
-                        }
-                        const uint32_t off = (uint32_t)((c0 >> 3) + j8) * kLboA + a_row_off;
-                        *reinterpret_cast<uint4 *>(sAhi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                        *reinterpret_cast<uint4 *>(sAlo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            for (int layer = 0; layer < 2; ++layer) {
+                const float *bias = sBias + layer * 256 + cs * 64;
+                uint32_t hi[32], lo[32];
+                {   // unit a: columns [0,128) of the layer; this thread: [cs*64, +64)
+                    const uint32_t b = u & 1u, n = u >> 1;
+                    mbar_wait(&bar_acc_full[b], n & 1u);
+                    if (ds) ds[1 + 2 * layer] = clock64();
+                    tc_fence_after_sync();
+                    {
+                        uint32_t v[32];
+                        tmem_ld32(tm_row + kColD + b * 128u + (uint32_t)cs * 64u, v);
+                        tmem_ld_wait();
+                        relu_split32(v, bias, hi, lo);
+                        tmem_ld32(tm_row + kColD + b * 128u + (uint32_t)cs * 64u + 32u, v);
+                        tmem_ld_wait();
+                        tc_fence_before_sync();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&bar_acc_empty[b]);
+                        relu_split32(v, bias + 32, hi + 16, lo + 16);
                     }
+                    ++u;
                 }
-                fence_proxy_async_smem();
-                tc_fence_before_sync();
-                __syncwarp();
-                if (lane == 0) {
-                    mbar_arrive(&bar_acc_empty[b]);
-                    mbar_arrive(&bar_a_ready);
+                {   // unit b: once its accumulator is complete every MMA of the layer has consumed the old A
+                    const uint32_t b = u & 1u, n = u >> 1;
+                    mbar_wait(&bar_acc_full[b], n & 1u);
+                    tc_fence_after_sync();
+                    tmem_st32(tm_row + kColAhi + (uint32_t)cs * 32u, hi);
+                    tmem_st32(tm_row + kColAlo + (uint32_t)cs * 32u, lo);
+                    {
+                        uint32_t v[32];
+                        tmem_ld32(tm_row + kColD + b * 128u + (uint32_t)cs * 64u, v);
+                        tmem_ld_wait();
+                        relu_split32(v, bias + 128, hi, lo);
+                        tmem_ld32(tm_row + kColD + b * 128u + (uint32_t)cs * 64u + 32u, v);
+                        tmem_ld_wait();
+                        tc_fence_before_sync();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&bar_acc_empty[b]);
+                        relu_split32(v, bias + 128 + 32, hi + 16, lo + 16);
+                    }
+                    tmem_st32(tm_row + kColAhi + 64u + (uint32_t)cs * 32u, hi);
+                    tmem_st32(tm_row + kColAlo + 64u + (uint32_t)cs * 32u, lo);
+                    tmem_st_wait();
+                    tc_fence_before_sync();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&bar_a_ready);
+                    ++u;
                 }
-                ++g;
+                if (ds) ds[2 + 2 * layer] = clock64();
             }
-            // ---- epilogues of the three heads: relu(acc + obj_bias + t_bias) . O  -> 3 score components each ----
-            const float *tb = p.tb_table + (size_t)step * 768;
+            // noise of this step, generated while the tensor core runs the heads (warps 0-3 own the rows)
+            float z1[9], z2[9];
+            if (cs == 0 && valid) {
+                row_noise(p, step, 0, row, z1);
+                row_noise(p, step, 1, row, z2);
+            }
+            named_bar_sync(3, kTcRowWarps * 32);      // sObt holds obj_bias + t_bias of THIS step (written by warps 4-7)
+            // ---- heads: relu(acc + obj_bias + t_bias) . O   -> 3 score components per head ----
             float f[9];
 #pragma unroll 1
             for (int h = 0; h < 3; ++h) {
-                const uint32_t b = g & 1u, n = g >> 1;
-                mbar_wait(&bar_acc_full[b], n & 1u);
-                tc_fence_after_sync();
                 float o0 = 0.f, o1 = 0.f, o2 = 0.f;
-                const float *w0 = W + TL::o_w + (size_t)(3 * h) * 256;
 #pragma unroll 1
-                for (int c0 = cb; c0 < cb + 128; c0 += 32) {
-                    uint32_t v[32];
-                    tmem_ld32(tmem_base + tm_lane + b * 256u + (uint32_t)c0, v);
+                for (int half = 0; half < 2; ++half) {
+                    const uint32_t b = u & 1u, n = u >> 1;
+                    mbar_wait(&bar_acc_full[b], n & 1u);
+                    if (ds && half == 0) ds[5 + 2 * h] = clock64();
+                    tc_fence_after_sync();
+                    uint32_t v0[32], v1[32];
+                    tmem_ld32(tm_row + kColD + b * 128u + (uint32_t)cs * 64u, v0);
+                    tmem_ld32(tm_row + kColD + b * 128u + (uint32_t)cs * 64u + 32u, v1);
                     tmem_ld_wait();
+                    tc_fence_before_sync();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&bar_acc_empty[b]);
+                    const int n0 = h * 256 + half * 128 + cs * 64;                 // first stacked hidden unit of this slice
+                    const float *ob = obt_row + n0;
+                    const float *w0 = sOw + (size_t)(3 * h) * 256 + half * 128 + cs * 64;
 #pragma unroll
-                    for (int j4 = 0; j4 < 8; ++j4) {
-                        const int c = c0 + 4 * j4;
-                        const float4 ob = *reinterpret_cast<const float4 *>(ob_row + h * 256 + c);
-                        const float4 t4 = __ldg(reinterpret_cast<const float4 *>(tb + h * 256 + c));
-                        const float4 wa = __ldg(reinterpret_cast<const float4 *>(w0 + c));
-                        const float4 wb = __ldg(reinterpret_cast<const float4 *>(w0 + 256 + c));
-                        const float4 wc = __ldg(reinterpret_cast<const float4 *>(w0 + 512 + c));
-                        const float h0 = fmaxf(__uint_as_float(v[4 * j4 + 0]) + ob.x + t4.x, 0.f);
-                        const float h1 = fmaxf(__uint_as_float(v[4 * j4 + 1]) + ob.y + t4.y, 0.f);
-                        const float h2 = fmaxf(__uint_as_float(v[4 * j4 + 2]) + ob.z + t4.z, 0.f);
-                        const float h3 = fmaxf(__uint_as_float(v[4 * j4 + 3]) + ob.w + t4.w, 0.f);
+                    for (int j4 = 0; j4 < 16; ++j4) {
+                        const float4 o4 = *reinterpret_cast<const float4 *>(ob + 4 * j4);
+                        const float4 wa = *reinterpret_cast<const float4 *>(w0 + 4 * j4);
+                        const float4 wb = *reinterpret_cast<const float4 *>(w0 + 256 + 4 * j4);
+                        const float4 wc = *reinterpret_cast<const float4 *>(w0 + 512 + 4 * j4);
+                        const uint32_t *vv = j4 < 8 ? &v0[4 * j4] : &v1[4 * j4 - 32];
+                        const float h0 = fmaxf(__uint_as_float(vv[0]) + o4.x, 0.f);
+                        const float h1 = fmaxf(__uint_as_float(vv[1]) + o4.y, 0.f);
+                        const float h2 = fmaxf(__uint_as_float(vv[2]) + o4.z, 0.f);
+                        const float h3 = fmaxf(__uint_as_float(vv[3]) + o4.w, 0.f);
                         o0 = fmaf(h3, wa.w, fmaf(h2, wa.z, fmaf(h1, wa.y, fmaf(h0, wa.x, o0))));
                         o1 = fmaf(h3, wb.w, fmaf(h2, wb.z, fmaf(h1, wb.y, fmaf(h0, wb.x, o1))));
                         o2 = fmaf(h3, wc.w, fmaf(h2, wc.z, fmaf(h1, wc.y, fmaf(h0, wc.x, o2))));
                     }
+                    ++u;
                 }
-                tc_fence_before_sync();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&bar_acc_empty[b]);
-                if (half == 1) {
+                if (ds) ds[6 + 2 * h] = clock64();
+                if (cs == 1) {
                     sFpart[r * 12 + 3 * h + 0] = o0;
                     sFpart[r * 12 + 3 * h + 1] = o1;
                     sFpart[r * 12 + 3 * h + 2] = o2;
@@ -308,10 +381,18 @@ tc_pc_sampler_kernel(TcPcParams tp) {
                     f[3 * h + 1] = o1;
                     f[3 * h + 2] = o2;
                 }
-                ++g;
             }
-            named_bar_sync(1, kTcRowWarps * 32);      // upper-half partials are in sFpart
-            if (half == 1) continue;                  // warps 4-7 go straight to the next step's epilogues
+            named_bar_sync(1, kTcRowWarps * 32);      // sub-half 1 partials are in sFpart; everyone is done with sObt
+            if (ds) ds[11] = clock64();
+            if (cs == 1) {
+                // warps 4-7: table of (object bias + time bias) for the NEXT step, while warps 0-3 reduce and update
+                if (step + 1 < p.T) {
+                    const float *tbn = p.tb_table + (size_t)(step + 1) * 768;
+                    for (int i = tid - 128; i < n_obj * 768; i += 128)
+                        sObt[i] = __ldg(p.obj_bias + (size_t)obj_lo * 768 + i) + __ldg(tbn + i % 768);
+                }
+                continue;
+            }
 
             // ---- score, batch-mean gradient norm, update (warps 0-3: one thread per row) ----
             const float t = p.ts[step];
@@ -320,31 +401,41 @@ tc_pc_sampler_kernel(TcPcParams tp) {
             float gr[9], n2 = 0.f;
 #pragma unroll
             for (int c = 0; c < 9; ++c) {
-                gr[c] = ((f[c] + sFpart[r * 12 + c]) + __ldg(W + TL::o_b + c)) / stdv;
+                gr[c] = ((f[c] + sFpart[r * 12 + c]) + sOw[9 * 256 + c]) / stdv;
                 n2 = fmaf(gr[c], gr[c], n2);
             }
             const float wsum = warp_sum(valid ? sqrtf(n2) : 0.f);
             if (lane == 0) s_red[q] = wsum;
             named_bar_sync(2, 128);
+            bar_target += gridDim.x;
             if (tid == 0) {
                 p.partial[(step & 1) * gridDim.x + blockIdx.x] = (s_red[0] + s_red[1]) + (s_red[2] + s_red[3]);
-                __threadfence();
-                bar_target += gridDim.x;
-                atomicAdd(p.barrier, 1u);
+                red_release_add(p.barrier, 1u);
                 while (ld_acquire_u32(p.barrier) < bar_target) {
                 }
-                __threadfence();
-            } else {
-                bar_target += gridDim.x;
             }
             named_bar_sync(2, 128);
-            float tot = 0.f;
-            for (int i = 0; i < (int)gridDim.x; ++i) tot += __ldcg(p.partial + (step & 1) * gridDim.x + i);
+            if (ds) ds[12] = clock64();
+            float tot = 0.f;   // every warp: lanes fetch the per-CTA partials in parallel, fixed-shape shuffle tree => identical everywhere
+            for (int i = lane; i < (int)gridDim.x; i += 32) tot += __ldcg(p.partial + (step & 1) * gridDim.x + i);
+            tot = warp_sum(tot);
             const float grad_norm = tot / (float)p.R;
             const PcStepConsts sc = pc_step_consts(grad_norm, snr_norm, sigma, step_size, sqrt_step);
-            float m[9];
             if (valid) {
-                pc_row_update(p, sc, step, row, x, gr, m);
+                float m[9];
+#pragma unroll
+                for (int c = 0; c < 9; ++c) x[c] = (x[c] + sc.ls * gr[c]) + sc.sq2ls * z1[c];           // corrector (samplers.py:132)
+                {
+                    const float n1 = sqrtf(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);                    // (:142-143), no eps
+                    const float n3 = sqrtf(x[3] * x[3] + x[4] * x[4] + x[5] * x[5]);
+                    x[0] /= n1; x[1] /= n1; x[2] /= n1;
+                    x[3] /= n3; x[4] /= n3; x[5] /= n3;
+                }
+#pragma unroll
+                for (int c = 0; c < 9; ++c) m[c] = x[c] + (0.0f - sc.g2 * gr[c]) * sc.step_size;        // predictor mean (:147-148), sign as written
+#pragma unroll
+                for (int c = 0; c < 9; ++c) x[c] = m[c] + (sc.g * sc.sqrt_step) * z2[c];                // (:149)
+                gram_schmidt6(x);                                                                        // (:152)
                 const float *ctr = p.pts_center + (size_t)(row / p.K) * 3;
                 if (p.process) {
                     float *dst = p.process + ((size_t)row * p.T + step) * 9;
@@ -359,10 +450,8 @@ tc_pc_sampler_kernel(TcPcParams tp) {
                     for (int c = 0; c < 9; ++c) p.mean_x[(size_t)row * 9 + c] = m[c];
                 }
             }
-            write_x_pieces(sX, r, x);
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&bar_x_ready);
+            publish_x();
+            if (ds) ds[13] = clock64();
         }
     }
     tc_fence_before_sync();
@@ -374,12 +463,12 @@ tc_pc_sampler_kernel(TcPcParams tp) {
 
 using namespace gpb;
 
-extern "C" size_t gpb_trunk_tc_stream_bytes(void) { return (size_t)kStagesPerStep * kStageBytes; }
+extern "C" size_t gpb_trunk_tc_stream_bytes(void) { return (size_t)kSlotsPerStep * kSlotBytes; }
 
-extern "C" int gpb_sample_pc_tc(const float *x0, int R, int K, int num_steps, float snr, const float *obj_bias, const float *W,
-                                const void *tc_stream, const float *pts_center, const float *step_noise, uint64_t seed,
-                                const float *time_grid, float *mean_x, float *process, void *workspace, size_t workspace_bytes,
-                                void *stream) {
+extern "C" int gpb_sample_pc_tc_dbg(const float *x0, int R, int K, int num_steps, float snr, const float *obj_bias, const float *W,
+                                    const void *tc_stream, const float *pts_center, const float *step_noise, uint64_t seed,
+                                    const float *time_grid, float *mean_x, float *process, void *workspace, size_t workspace_bytes,
+                                    unsigned long long *dbg, void *stream) {
     GPB_REQUIRE(R >= 0 && K >= 1 && num_steps >= 2, "sample_pc_tc: need R >= 0, K >= 1, num_steps >= 2");
     if (R == 0) return GPB_OK;
     GPB_REQUIRE(x0 && obj_bias && W && tc_stream && pts_center && time_grid && mean_x && workspace, "sample_pc_tc: NULL buffer");
@@ -409,11 +498,19 @@ extern "C" int gpb_sample_pc_tc(const float *x0, int R, int K, int num_steps, fl
     p.x0 = x0; p.R = R; p.K = K; p.T = num_steps; p.snr = snr;
     p.obj_bias = obj_bias; p.W = W; p.pts_center = pts_center; p.noise = step_noise; p.seed = seed;
     p.ts = time_grid; p.tb_table = w.tb_table; p.partial = w.partial; p.barrier = w.barrier;
-    p.mean_x = mean_x; p.process = process; p.tiles_per_cta = 1;
+    p.mean_x = mean_x; p.process = process; p.tiles_per_cta = 1; p.dbg = dbg;
     tp.wstream = reinterpret_cast<const uint8_t *>(tc_stream);
     GPB_CUDA(cudaFuncSetAttribute(tc_pc_sampler_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes));
     void *args[] = {&tp};
     GPB_CUDA(cudaLaunchCooperativeKernel((void *)tc_pc_sampler_kernel, dim3(grid), dim3(kTcThreads), args, kTcSmemBytes, st));
     g_launches.fetch_add(1);
     return GPB_OK;
+}
+
+extern "C" int gpb_sample_pc_tc(const float *x0, int R, int K, int num_steps, float snr, const float *obj_bias, const float *W,
+                                const void *tc_stream, const float *pts_center, const float *step_noise, uint64_t seed,
+                                const float *time_grid, float *mean_x, float *process, void *workspace, size_t workspace_bytes,
+                                void *stream) {
+    return gpb_sample_pc_tc_dbg(x0, R, K, num_steps, snr, obj_bias, W, tc_stream, pts_center, step_noise, seed, time_grid, mean_x,
+                                process, workspace, workspace_bytes, nullptr, stream);
 }

@@ -12,7 +12,7 @@ using namespace tc;
 
 __global__ void __launch_bounds__(192, 1)
 umma_selftest_kernel(const float *__restrict__ A, const uint16_t *__restrict__ Bhi, const uint16_t *__restrict__ Blo,
-                     float *__restrict__ D, int K, int N, int variant, int swap_fields, int n_terms) {
+                     float *__restrict__ D, int K, int N, int variant, int swap_fields, int n_terms, int a_tmem) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t a_bytes = 128u * K * 2u, b_bytes = (uint32_t)N * K * 2u;
     uint8_t *sAhi = smem, *sAlo = sAhi + a_bytes, *sBhi = sAlo + a_bytes, *sBlo = sBhi + b_bytes;
@@ -31,7 +31,7 @@ umma_selftest_kernel(const float *__restrict__ A, const uint16_t *__restrict__ B
         mbar_init(&bar_mma, 1);
         fence_mbar_init();
     }
-    if (warp == 4) tmem_alloc(&tmem_base_s, 256);
+    if (warp == 4) tmem_alloc(&tmem_base_s, 512);
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
@@ -62,10 +62,28 @@ umma_selftest_kernel(const float *__restrict__ A, const uint16_t *__restrict__ B
             *reinterpret_cast<uint4 *>(sAlo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
         }
         fence_proxy_async_smem();   // generic-proxy stores -> async proxy (tensor core reads)
+        if (a_tmem) {   // the same rows straight into tensor memory: hi at columns [256, 256+K/2), lo at [384, 384+K/2)
+            for (int c0 = 0; c0 < K / 2; c0 += 8) {
+                uint32_t hi[8], lo[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    __nv_bfloat16 h0, l0, h1, l1;
+                    split_bf16(A[(size_t)r * K + 2 * (c0 + j)], h0, l0);
+                    split_bf16(A[(size_t)r * K + 2 * (c0 + j) + 1], h1, l1);
+                    hi[j] = pack_bf16(h0, h1);
+                    lo[j] = pack_bf16(l0, l1);
+                }
+                const uint32_t ta = tmem_base + ((uint32_t)(warp * 32) << 16);
+                tmem_st8(ta + 256u + (uint32_t)c0, hi);
+                tmem_st8(ta + 384u + (uint32_t)c0, lo);
+            }
+            tmem_st_wait();
+            tc_fence_before_sync();
+        }
     }
     __syncthreads();
 
-    if (warp == 4 && lane == 0) {   // MMA issuer
+    if (warp == 4) {   // MMA issuer: the whole warp runs the loop, one elected lane issues
         mbar_wait(&bar_b, 0);
         tc_fence_after_sync();
         const uint32_t idesc = make_idesc_bf16_f32(128, N);
@@ -76,11 +94,16 @@ umma_selftest_kernel(const float *__restrict__ A, const uint16_t *__restrict__ B
             for (int k16 = 0; k16 < K / 16; ++k16) {
                 const uint64_t ad = swap_fields ? make_smem_desc(a0 + k16 * 2 * a_lbo, a_sbo, a_lbo) : make_smem_desc(a0 + k16 * 2 * a_lbo, a_lbo, a_sbo);
                 const uint64_t bd = swap_fields ? make_smem_desc(b0 + k16 * 2 * b_lbo, b_sbo, b_lbo) : make_smem_desc(b0 + k16 * 2 * b_lbo, b_lbo, b_sbo);
-                umma_bf16(tmem_base, ad, bd, idesc, acc);
+                if (elect_one_sync()) {
+                    if (a_tmem) umma_bf16_ts(tmem_base, tmem_base + (term == 2 ? 384u : 256u) + (uint32_t)k16 * 8u, bd, idesc, acc);
+                    else umma_bf16(tmem_base, ad, bd, idesc, acc);
+                }
+                __syncwarp();
                 acc = true;
             }
         }
-        umma_commit(&bar_mma);
+        if (elect_one_sync()) umma_commit(&bar_mma);
+        __syncwarp();
     }
     if (warp < 4) {   // epilogue: TMEM -> global
         mbar_wait(&bar_mma, 0);
@@ -96,7 +119,7 @@ umma_selftest_kernel(const float *__restrict__ A, const uint16_t *__restrict__ B
     }
     tc_fence_before_sync();
     __syncthreads();
-    if (warp == 4) tmem_dealloc(tmem_base, 256);
+    if (warp == 4) tmem_dealloc(tmem_base, 512);
 }
 
 }  // namespace gpb
@@ -104,13 +127,13 @@ umma_selftest_kernel(const float *__restrict__ A, const uint16_t *__restrict__ B
 using namespace gpb;
 
 extern "C" int gpb_selftest_umma(const float *A, const uint16_t *Bhi, const uint16_t *Blo, float *D, int K, int N, int variant,
-                                 int swap_fields, int n_terms, void *stream) {
+                                 int swap_fields, int n_terms, int a_tmem, void *stream) {
     GPB_REQUIRE(A && Bhi && Blo && D, "selftest_umma: NULL buffer");
     GPB_REQUIRE(K % 16 == 0 && K >= 16 && N % 16 == 0 && N >= 16 && N <= 256, "selftest_umma: K %% 16, N %% 16, N <= 256");
     const size_t smem = (size_t)2 * 128 * K * 2 + (size_t)2 * N * K * 2;
     GPB_REQUIRE(smem <= 200 * 1024, "selftest_umma: operands do not fit shared memory");
     GPB_CUDA(cudaFuncSetAttribute(umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    umma_selftest_kernel<<<1, 192, smem, (cudaStream_t)stream>>>(A, Bhi, Blo, D, K, N, variant, swap_fields, n_terms);
+    umma_selftest_kernel<<<1, 192, smem, (cudaStream_t)stream>>>(A, Bhi, Blo, D, K, N, variant, swap_fields, n_terms, a_tmem);
     GPB_LAUNCHED();
     return GPB_OK;
 }

@@ -132,26 +132,29 @@ def umma_image(w_bf16: torch.Tensor, variant: int = 0) -> torch.Tensor:
 
 
 def pack_trunk_tc(sd: Dict[str, torch.Tensor], prefix: str = "pose_score_net") -> torch.Tensor:
-    """The per-step weight stream of tc_pc_sampler_kernel: 65 stages of 16 KiB (int16 words):
-         stage 0        : P1 [256 x 16] (K padded 9 -> 16): hi image (8 KiB) | lo image (8 KiB)
-         stages 1..64   : for layer in (P2, head rot_x, head rot_y, head trans): for K-chunk kc in 0..7 (32 columns):
-                              hi image rows [4kc, 4kc+4) of [K/8][256][8]  (16 KiB), then the lo image chunk (16 KiB)
+    """The per-step weight stream of tc_pc_sampler_kernel: 65 slots of 16 KiB (int16 words).  Operand images are 128-row
+    [K/8][128][8] blocks of one N = 128 "unit" (output neurons [0,128) = unit a, [128,256) = unit b):
+         slot 0        : P1 (K padded 9 -> 16): unit a hi (4 KiB) | lo (4 KiB) | unit b hi | lo
+         slots 1..64   : for layer in (P2, head rot_x, head rot_y, head trans): for unit in (a, b):
+                             for K-chunk kc in 0..7 (32 input columns): hi image chunk (8 KiB) | lo image chunk (8 KiB)
     Head matrices are the pose-feature column block [:, 1152:1408] of fusion_tail_*.0.weight (scorenet.py:204)."""
     g = lambda k: sd[f"{prefix}.{k}"].float()
-    stages = []
+    slots = []
     p1 = torch.zeros(256, 16)
     p1[:, :9] = g("pose_encoder.0.weight")
-    hi, lo = split_bf16(p1)
-    stages.append(torch.cat([umma_image(hi), umma_image(lo)]))
+    parts = []
+    for unit in range(2):
+        hi, lo = split_bf16(p1[128 * unit: 128 * unit + 128])
+        parts += [umma_image(hi), umma_image(lo)]
+    slots.append(torch.cat(parts))
     off = arch.PTS_FEAT_DIM + arch.T_EMBED_DIM
     layers = [g("pose_encoder.2.weight")] + [g(f"fusion_tail_{h}.0.weight")[:, off:] for h in arch.HEADS]
     for w in layers:
         assert tuple(w.shape) == (256, 256)
-        hi, lo = split_bf16(w)
-        ih, il = umma_image(hi).reshape(32, 256 * 8), umma_image(lo).reshape(32, 256 * 8)
-        for kc in range(8):
-            stages.append(ih[4 * kc: 4 * kc + 4].reshape(-1))
-            stages.append(il[4 * kc: 4 * kc + 4].reshape(-1))
-    out = torch.cat(stages).contiguous()
-    assert out.numel() * 2 == 65 * 16384
-    return out
+        for unit in range(2):
+            hi, lo = split_bf16(w[128 * unit: 128 * unit + 128])
+            ih, il = umma_image(hi).reshape(32, 128 * 8), umma_image(lo).reshape(32, 128 * 8)
+            for kc in range(8):
+                slots.append(torch.cat([ih[4 * kc: 4 * kc + 4].reshape(-1), il[4 * kc: 4 * kc + 4].reshape(-1)]))
+    assert all(sl.numel() * 2 == 16384 for sl in slots) and len(slots) == 65
+    return torch.cat(slots).contiguous()

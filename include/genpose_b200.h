@@ -130,6 +130,14 @@ GPB_API int gpb_sample_pc_tc(const float *x0, int R, int K, int num_steps, float
                              const float *step_noise, uint64_t seed, const float *time_grid, float *mean_x,
                              float *process, void *workspace, size_t workspace_bytes, void *stream);
 
+/* Same, with an optional cycle-stamp buffer (device, [2][T][16] u64; NULL = off): CTA 0's row thread 0 and MMA thread
+ * record clock64() at the phase boundaries of every step (tools/tc_phase_times.py decodes them). */
+GPB_API int gpb_sample_pc_tc_dbg(const float *x0, int R, int K, int num_steps, float snr, const float *obj_bias,
+                                 const float *trunk_weights, const void *tc_stream, const float *pts_center,
+                                 const float *step_noise, uint64_t seed, const float *time_grid, float *mean_x,
+                                 float *process, void *workspace, size_t workspace_bytes, unsigned long long *dbg,
+                                 void *stream);
+
 /* replaces cond_ode_sampler (samplers.py:163-227) + scipy.integrate.solve_ivp(RK45) (samplers.py:205):
  * Dormand-Prince 5(4) with SciPy's step controller, float64 state, fp32 score, one error norm over the
  * whole [R*9] state, followed by the reference's Euler "denoise" step (:209-218).
@@ -164,10 +172,11 @@ GPB_API uint64_t gpb_launch_count(void);
  * (4) SELF-TEST of the tcgen05 building block (one CTA: D[128,N] = A[128,K] . B[N,K]^T, bf16 split, fp32
  *     accumulate in TMEM).  A fp32 row-major; Bhi/Blo = bf16 operand images in the canonical K-major
  *     no-swizzle layout (genpose_b200/weights.py::umma_image).  variant/swap_fields select layout
- *     conventions under test; n_terms 1..3 = how many of the bf16x3 products are accumulated.
+ *     conventions under test; n_terms 1..3 = how many of the bf16x3 products are accumulated; a_tmem = 1 feeds the
+ *     A operand from tensor memory (tcgen05.st + the TS form of tcgen05.mma) instead of shared memory.
  * ---------------------------------------------------------------------------------------------- */
 GPB_API int gpb_selftest_umma(const float *A, const uint16_t *Bhi, const uint16_t *Blo, float *D, int K, int N,
-                              int variant, int swap_fields, int n_terms, void *stream);
+                              int variant, int swap_fields, int n_terms, int a_tmem, void *stream);
 
 #ifdef __cplusplus
 }

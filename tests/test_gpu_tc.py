@@ -12,7 +12,7 @@ from tests import _cases
 pytestmark = pytest.mark.gpu
 
 
-def _selftest(K, N, variant, swap, n_terms, seed=0):
+def _selftest(K, N, variant, swap, n_terms, seed=0, a_tmem=0):
     g = torch.Generator().manual_seed(seed)
     A = torch.randn(128, K, generator=g)
     B = torch.randn(N, K, generator=g)
@@ -21,7 +21,7 @@ def _selftest(K, N, variant, swap, n_terms, seed=0):
     Ad = A.cuda().contiguous()
     ih = weights.umma_image(bhi, variant).cuda()
     il = weights.umma_image(blo, variant).cuda()
-    lib.check(lib.load().gpb_selftest_umma(Ad.data_ptr(), ih.data_ptr(), il.data_ptr(), D.data_ptr(), K, N, variant, swap, n_terms,
+    lib.check(lib.load().gpb_selftest_umma(Ad.data_ptr(), ih.data_ptr(), il.data_ptr(), D.data_ptr(), K, N, variant, swap, n_terms, a_tmem,
                                            torch.cuda.current_stream().cuda_stream), "selftest_umma")
     torch.cuda.synchronize()
     ahi, alo = weights.split_bf16(A)
@@ -44,6 +44,13 @@ def test_umma_bf16x3_matches_matmul(K, N):
     d, ref, exact = _selftest(K, N, 0, 0, 3, seed=K + N)
     assert float((d - ref).abs().max()) < 2e-4 * max(1.0, float(ref.abs().max()))       # same products, fp32 accumulate
     assert float((d - exact).abs().max()) < 1e-3 * np.sqrt(K / 16)                        # ~2^-17 operand error per product
+
+
+@pytest.mark.parametrize("K,N", [(16, 256), (64, 128), (128, 256)])
+def test_umma_a_operand_from_tensor_memory(K, N):
+    """The TS form: A written with tcgen05.st (lane = row, two bf16 per 32-bit column), B from shared memory."""
+    d, ref, exact = _selftest(K, N, 0, 0, 3, seed=7 * K + N, a_tmem=1)
+    assert float((d - ref).abs().max()) < 2e-4 * max(1.0, float(ref.abs().max()))
 
 
 @pytest.mark.parametrize("name", ["pc_B2_K5_T500", "pc_B3_K4_T50", "config1_pc_B1_K1_T10"])
