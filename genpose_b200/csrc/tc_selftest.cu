@@ -12,7 +12,8 @@ using namespace tc;
 
 __global__ void __launch_bounds__(192, 1)
 umma_selftest_kernel(const float *__restrict__ A, const uint16_t *__restrict__ Bhi, const uint16_t *__restrict__ Blo,
-                     float *__restrict__ D, int K, int N, int variant, int swap_fields, int n_terms, int a_tmem) {
+                     float *__restrict__ D, int K, int N, int variant, int swap_fields, int n_terms, int a_tmem, int repeat,
+                     unsigned long long *__restrict__ cycles_out) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t a_bytes = 128u * K * 2u, b_bytes = (uint32_t)N * K * 2u;
     uint8_t *sAhi = smem, *sAlo = sAhi + a_bytes, *sBhi = sAlo + a_bytes, *sBlo = sBhi + b_bytes;
@@ -89,6 +90,8 @@ umma_selftest_kernel(const float *__restrict__ A, const uint16_t *__restrict__ B
         const uint32_t idesc = make_idesc_bf16_f32(128, N);
         const uint32_t ahi = smem_u32(sAhi), alo = smem_u32(sAlo), bhi = smem_u32(sBhi), blo = smem_u32(sBlo);
         bool acc = false;
+        const unsigned long long t_start = clock64();
+        for (int rep = 0; rep < repeat; ++rep)
         for (int term = 0; term < n_terms; ++term) {   // 0: Ahi.Bhi  1: Ahi.Blo  2: Alo.Bhi
             const uint32_t a0 = term == 2 ? alo : ahi, b0 = term == 1 ? blo : bhi;
             for (int k16 = 0; k16 < K / 16; ++k16) {
@@ -104,6 +107,12 @@ umma_selftest_kernel(const float *__restrict__ A, const uint16_t *__restrict__ B
         }
         if (elect_one_sync()) umma_commit(&bar_mma);
         __syncwarp();
+        const unsigned long long t_issued = clock64();
+        mbar_wait(&bar_mma, 0);
+        if (cycles_out && lane == 0) {
+            cycles_out[0] = t_issued - t_start;      // issue time of repeat * n_terms * K/16 MMAs
+            cycles_out[1] = clock64() - t_start;     // until the last one has completed
+        }
     }
     if (warp < 4) {   // epilogue: TMEM -> global
         mbar_wait(&bar_mma, 0);
@@ -127,13 +136,13 @@ umma_selftest_kernel(const float *__restrict__ A, const uint16_t *__restrict__ B
 using namespace gpb;
 
 extern "C" int gpb_selftest_umma(const float *A, const uint16_t *Bhi, const uint16_t *Blo, float *D, int K, int N, int variant,
-                                 int swap_fields, int n_terms, int a_tmem, void *stream) {
+                                 int swap_fields, int n_terms, int a_tmem, int repeat, unsigned long long *cycles_out, void *stream) {
     GPB_REQUIRE(A && Bhi && Blo && D, "selftest_umma: NULL buffer");
     GPB_REQUIRE(K % 16 == 0 && K >= 16 && N % 16 == 0 && N >= 16 && N <= 256, "selftest_umma: K %% 16, N %% 16, N <= 256");
     const size_t smem = (size_t)2 * 128 * K * 2 + (size_t)2 * N * K * 2;
     GPB_REQUIRE(smem <= 200 * 1024, "selftest_umma: operands do not fit shared memory");
     GPB_CUDA(cudaFuncSetAttribute(umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    umma_selftest_kernel<<<1, 192, smem, (cudaStream_t)stream>>>(A, Bhi, Blo, D, K, N, variant, swap_fields, n_terms, a_tmem);
+    umma_selftest_kernel<<<1, 192, smem, (cudaStream_t)stream>>>(A, Bhi, Blo, D, K, N, variant, swap_fields, n_terms, a_tmem, repeat < 1 ? 1 : repeat, cycles_out);
     GPB_LAUNCHED();
     return GPB_OK;
 }

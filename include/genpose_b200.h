@@ -173,10 +173,12 @@ GPB_API uint64_t gpb_launch_count(void);
  *     accumulate in TMEM).  A fp32 row-major; Bhi/Blo = bf16 operand images in the canonical K-major
  *     no-swizzle layout (genpose_b200/weights.py::umma_image).  variant/swap_fields select layout
  *     conventions under test; n_terms 1..3 = how many of the bf16x3 products are accumulated; a_tmem = 1 feeds the
- *     A operand from tensor memory (tcgen05.st + the TS form of tcgen05.mma) instead of shared memory.
+ *     A operand from tensor memory (tcgen05.st + the TS form of tcgen05.mma) instead of shared memory; repeat > 1 re-issues
+ *     the whole K loop (timing aid: cycles_out[0] = issue cycles, cycles_out[1] = cycles until completion; may be NULL).
  * ---------------------------------------------------------------------------------------------- */
 GPB_API int gpb_selftest_umma(const float *A, const uint16_t *Bhi, const uint16_t *Blo, float *D, int K, int N,
-                              int variant, int swap_fields, int n_terms, int a_tmem, void *stream);
+                              int variant, int swap_fields, int n_terms, int a_tmem, int repeat,
+                              unsigned long long *cycles_out, void *stream);
 
 #ifdef __cplusplus
 }

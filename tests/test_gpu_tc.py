@@ -21,7 +21,7 @@ def _selftest(K, N, variant, swap, n_terms, seed=0, a_tmem=0):
     Ad = A.cuda().contiguous()
     ih = weights.umma_image(bhi, variant).cuda()
     il = weights.umma_image(blo, variant).cuda()
-    lib.check(lib.load().gpb_selftest_umma(Ad.data_ptr(), ih.data_ptr(), il.data_ptr(), D.data_ptr(), K, N, variant, swap, n_terms, a_tmem,
+    lib.check(lib.load().gpb_selftest_umma(Ad.data_ptr(), ih.data_ptr(), il.data_ptr(), D.data_ptr(), K, N, variant, swap, n_terms, a_tmem, 1, 0,
                                            torch.cuda.current_stream().cuda_stream), "selftest_umma")
     torch.cuda.synchronize()
     ahi, alo = weights.split_bf16(A)
