@@ -163,7 +163,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", type=int, default=2, choices=[2, 3])
-    ap.add_argument("--ref-objects", type=int, default=32, help="objects per step of the CPU reference arm / cpu_baseline sample")
+    ap.add_argument("--ref-objects", type=int, default=8, help="objects per step of the CPU reference arm / cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--precision", default="auto", choices=["auto", "bf16x3", "fp32"],
                     help="dense layers of the sampler: tcgen05 bf16x3 (auto when the shape allows) or the fp32 FFMA parity kernel")

@@ -142,7 +142,7 @@ tc_pc_sampler_kernel(TcPcParams tp) {
             uint32_t u = 0, it = 0, xr = 0, ar = 0;
             for (int step = 0; step < p.T; ++step) {
                 unsigned long long *ds = (dbg_cta && lane == 0) ? p.dbg + ((size_t)p.T + step) * 16 : nullptr;
-                unsigned long long w_full = 0, w_a = 0, w_acc = 0, tq = 0;
+                unsigned long long w_full = 0, w_a = 0, w_acc = 0, tq = 0, w_issue = 0, w_fence = 0;
                 if (ds) ds[0] = clock64();
                 // ---- layer 0: h1_pre = x . P1^T   (K = 16; x pieces x1,x2,x3 at A_hi[0,8),[8,16),[16,24); P1 hi|lo per unit)
                 mbar_wait(&bar_x_ready, xr & 1u);
@@ -189,30 +189,39 @@ tc_pc_sampler_kernel(TcPcParams tp) {
                         mbar_wait(&bar_acc_empty[b], (n & 1u) ^ 1u);
                         if (ds) w_acc += clock64() - tq;
                         const uint32_t d = tmem_base + kColD + b * 128u;
-#pragma unroll 1
-                        for (int kc = 0; kc < 8; ++kc) {
-                            const uint32_t s = it % kSlots;
-                            if (ds) tq = clock64();
-                            mbar_wait(&bar_full[s], (it / kSlots) & 1u);
-                            if (ds) w_full += clock64() - tq;
-                            tc_fence_after_sync();
-                            const uint32_t sb = ring + s * kSlotBytes;
-                            const uint32_t acol = (uint32_t)kc * 16u;                    // K index / 2
-                            if (elect_one_sync()) {
+                        // all 8 weight slots of the unit: lanes 0-7 wait on one mbarrier each (one wait latency instead of 8)
+                        if (ds) tq = clock64();
+                        if (lane < 8) {
+                            const uint32_t itl = it + (uint32_t)lane;
+                            mbar_wait(&bar_full[itl % kSlots], (itl / kSlots) & 1u);
+                        }
+                        __syncwarp();
+                        if (ds) { w_full += clock64() - tq; tq = clock64(); }
+                        tc_fence_after_sync();
+                        if (ds) { w_fence += clock64() - tq; tq = clock64(); }
+                        const uint32_t s_first = it % kSlots;
+                        if (elect_one_sync()) {       // one issue group per unit: 48 MMAs, 8 slot releases, accumulator-ready
+#pragma unroll
+                            for (int kc = 0; kc < 8; ++kc) {
+                                uint32_t s = s_first + (uint32_t)kc;
+                                s = s >= (uint32_t)kSlots ? s - (uint32_t)kSlots : s;
+                                const uint32_t sb = ring + s * kSlotBytes;
 #pragma unroll
                                 for (int j = 0; j < 2; ++j) {
                                     const uint64_t b_hi = make_smem_desc(sb + 2u * j * kLboB, kLboB, kSbo);
                                     const uint64_t b_lo = make_smem_desc(sb + 8192u + 2u * j * kLboB, kLboB, kSbo);
-                                    umma_bf16_ts(d, t_ahi + acol + 8u * j, b_hi, idesc, (kc | j) != 0);
-                                    umma_bf16_ts(d, t_alo + acol + 8u * j, b_hi, idesc, true);
-                                    umma_bf16_ts(d, t_ahi + acol + 8u * j, b_lo, idesc, true);
+                                    const uint32_t ac = (uint32_t)kc * 16u + 8u * j;      // K index / 2
+                                    umma_bf16_ts(d, t_ahi + ac, b_hi, idesc, (kc | j) != 0);
+                                    umma_bf16_ts(d, t_alo + ac, b_hi, idesc, true);
+                                    umma_bf16_ts(d, t_ahi + ac, b_lo, idesc, true);
                                 }
                                 umma_commit(&bar_empty[s]);
-                                if (kc == 7) umma_commit(&bar_acc_full[b]);
                             }
-                            __syncwarp();
-                            ++it;
+                            umma_commit(&bar_acc_full[b]);
                         }
+                        __syncwarp();
+                        if (ds) w_issue += clock64() - tq;
+                        it += 8;
                         ++u;
                     }
                 }
@@ -221,6 +230,8 @@ tc_pc_sampler_kernel(TcPcParams tp) {
                     ds[8] = w_full;
                     ds[9] = w_a;
                     ds[10] = w_acc;
+                    ds[11] = w_issue;
+                    ds[12] = w_fence;
                 }
             }
         }
@@ -274,6 +285,9 @@ tc_pc_sampler_kernel(TcPcParams tp) {
         for (int step = 0; step < p.T; ++step) {
             unsigned long long *ds = dbg ? p.dbg + (size_t)step * 16 : nullptr;
             if (ds) ds[0] = clock64();
+            const float t = p.ts[step];
+            const float sigma = sigma_of_t(t);
+            const float stdv = sigma + 1e-7f;
             // ---- layers 0 and 1: accumulator -> bias + ReLU -> bf16 hi/lo -> A operand in tensor memory ----
 #pragma unroll 1
             for (int layer = 0; layer < 2; ++layer) {
@@ -395,9 +409,6 @@ tc_pc_sampler_kernel(TcPcParams tp) {
             }
 
             // ---- score, batch-mean gradient norm, update (warps 0-3: one thread per row) ----
-            const float t = p.ts[step];
-            const float sigma = sigma_of_t(t);
-            const float stdv = sigma + 1e-7f;
             float gr[9], n2 = 0.f;
 #pragma unroll
             for (int c = 0; c < 9; ++c) {
@@ -409,10 +420,12 @@ tc_pc_sampler_kernel(TcPcParams tp) {
             named_bar_sync(2, 128);
             bar_target += gridDim.x;
             if (tid == 0) {
+                if (ds) ds[14] = clock64();
                 p.partial[(step & 1) * gridDim.x + blockIdx.x] = (s_red[0] + s_red[1]) + (s_red[2] + s_red[3]);
                 red_release_add(p.barrier, 1u);
                 while (ld_acquire_u32(p.barrier) < bar_target) {
                 }
+                if (ds) ds[15] = clock64();
             }
             named_bar_sync(2, 128);
             if (ds) ds[12] = clock64();

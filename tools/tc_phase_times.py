@@ -36,6 +36,7 @@ print("row thread 0 (cycles, mean over steps):")
 for n, a, b in zip(names, idx[:-1], idx[1:]):
     print(f"  {n:22s} {np.mean(row[:, b] - row[:, a]):9.0f}")
 print(f"  step total             {np.mean(row[1:, 0] - row[:-1, 0]):9.0f}")
+print(f"  (of the barrier phase: score+norm+named barrier {np.mean(row[:, 14] - row[:, 11]):7.0f}, publish+poll {np.mean(row[:, 15] - row[:, 14]):7.0f}, release named barrier {np.mean(row[:, 12] - row[:, 15]):7.0f})")
 print("MMA thread:")
 print(f"  wait x_ready           {np.mean(mma[:, 1] - mma[:, 0]):9.0f}")
 for l in range(1, 5):
@@ -44,4 +45,6 @@ for l in range(1, 5):
 print(f"  waiting on weights     {np.mean(mma[:, 8]):9.0f}   (sum over the step)")
 print(f"  waiting on A operand   {np.mean(mma[:, 9]):9.0f}")
 print(f"  waiting on acc buffers {np.mean(mma[:, 10]):9.0f}")
+print(f"  inside issue groups    {np.mean(mma[:, 11]):9.0f}   (32 groups of 12 MMAs per step)")
+print(f"  tcgen05 fences         {np.mean(mma[:, 12]):9.0f}")
 print(f"  step total             {np.mean(mma[1:, 0] - mma[:-1, 0]):9.0f}")
