@@ -8,7 +8,13 @@
 // 2^-9.  Measured in the oracle: final poses move by 2e-5 (single bf16: 9e-3, tf32: 8e-4) against
 // the 1e-3 parity bound.
 //
-// One CTA owns a 128-row tile of candidates for all T steps; NOTHING of the per-step state leaves the SM:
+// FOUR CTAs share a 128-row tile of candidates for all T steps ("tile team", rank = blockIdx.x & 3): every rank runs
+// layers 0 and 1 (P1, P2) redundantly — they are the sequential prefix — and then only ITS 192-column slice of the
+// 768 stacked head units (N = 128 + N = 64 MMAs), so the head phase costs one quarter of the tensor time.  The ranks'
+// partial score components are summed by rank 0 (the leader, which alone owns the pose state, the noise, the grid-wide
+// gradient-norm reduction and the update); the exchange uses global-memory mailboxes with release/acquire counters
+// (peers -> leader: 9 partial sums per row; leader -> peers: the new pose rows).  Inside a CTA nothing of the per-step
+// state leaves the SM:
 //   * activations never touch shared memory: the A operand of every layer lives in TENSOR MEMORY (written by the
 //     epilogue with tcgen05.st, lane = row, two bf16 per 32-bit column; consumed by the TS form of tcgen05.mma),
 //     TMEM map: D0 [0,128) D1 [128,256) accumulators (N = 128 "units", ping-pong), A_hi [256,384), A_lo [384,512);
@@ -24,9 +30,9 @@
 //              warps 4-7 meanwhile refresh the (object bias + time bias) table for the next step.
 //   warp 8     one elected thread issues every tcgen05.mma / tcgen05.commit; the warp owns the TMEM allocation.
 //   warp 9     one elected thread runs the weight producer.
-// Per step and tile: 10 units (2 per layer), 10 + 4*96 MMAs of 128x128x16.
-// (The first working version kept A in shared memory, 128 KB, and could only prefetch 2 weight-slot pairs:
-//  tc_sampler_v1_smemA.cu.txt, 18.2 ms per 3200x500 launch.)
+// Per step and CTA: layer 0 (10 MMAs), layer 1 (2 x 48 MMAs of 128x128x16), head slice (48 of 128x128x16 + 48 of 128x64x16).
+// History (3200 rows x 500 steps, one B200): A in shared memory + 2-deep weight ring 18.2 ms; A in TMEM, deep ring,
+// warp-uniform issue, one issue group per unit 12.6 ms (one CTA per tile, all three heads); this version: see DESIGN.md §5.
 #include "common.cuh"
 #include "sampler_common.cuh"
 #include "tc_common.cuh"
@@ -39,7 +45,12 @@ constexpr int kTcRowWarps = 8;
 constexpr int kTcThreads = (kTcRowWarps + 2) * 32;
 constexpr uint32_t kSlotBytes = 16384;
 constexpr int kSlots = 12;
-constexpr int kSlotsPerStep = 1 + 4 * 2 * 8;       // P1 (both units) + 4 layers x 2 units x 8 K-chunks, each slot = hi image | lo image
+constexpr int kTeam = 4;                           // CTAs per tile
+constexpr int kCommonSlots = 1 + 16;               // P1 (both units) + P2 (2 units x 8 K-chunks); slot = hi image | lo image
+constexpr int kHeadSlots = 8 + 4;                  // head slice: 128-row unit (8 K-chunks) + 64-row unit (2 K-chunks per slot)
+constexpr int kSlotsPerCtaStep = kCommonSlots + kHeadSlots;      // 29 slots = 464 KiB per CTA and step
+constexpr int kSlotsPerStep = kCommonSlots + kTeam * kHeadSlots; // 65 slots in the global stream
+constexpr uint32_t kLboB64 = 1024;                 // 64-row operand images
 constexpr uint32_t kLboB = 2048, kSbo = 128;       // 128-row operand images
 constexpr int kMaxObjPerTile = 4;
 constexpr uint32_t kColD = 0, kColAhi = 256, kColAlo = 384;
@@ -52,11 +63,14 @@ constexpr uint32_t kOffOw = kOffObt + kMaxObjPerTile * 768 * 4;       // [9][256
 constexpr uint32_t kOffBias = kOffOw + (9 * 256 + 16) * 4;            // p1_b [256] | p2_b [256]
 constexpr uint32_t kOffFpart = kOffBias + 512 * 4;                    // [128][12] fp32 partial scores of column sub-half 1
 constexpr uint32_t kTcSmemBytes = kOffFpart + 128 * 12 * 4;
-static_assert(kTcSmemBytes <= 227 * 1024 - 1024, "tc sampler shared memory budget");
+static_assert(kTcSmemBytes <= 227 * 1024 - 768, "tc sampler shared memory budget");
 
 struct TcPcParams {
     PcParams pc;
-    const uint8_t *wstream;   // kSlotsPerStep x 8 KiB of bf16 operand images (genpose_b200/weights.py::pack_trunk_tc)
+    const uint8_t *wstream;   // kSlotsPerStep x 16 KiB of bf16 operand images (genpose_b200/weights.py::pack_trunk_tc)
+    float *xch_f;             // [tiles][3 peers][128][9]  partial head sums, peers -> leader
+    float *xch_x;             // [tiles][128][9]           new pose rows, leader -> peers
+    unsigned *xch_cnt;        // [tiles][2]                monotonic counters: [0] peers' partials published, [1] poses published
 };
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
@@ -89,10 +103,14 @@ tc_pc_sampler_kernel(TcPcParams tp) {
     __shared__ float s_red[4];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int row0 = blockIdx.x * kTcRows;
+    const int tile = blockIdx.x / kTeam, rank = blockIdx.x % kTeam;   // rank 0 = leader of the tile team
+    const int n_tiles = gridDim.x / kTeam;
+    const int row0 = tile * kTcRows;
     const int obj_lo = row0 / p.K;
     const int n_obj = (min(row0 + kTcRows, p.R) - 1) / p.K - obj_lo + 1;
     const float *W = p.W;
+    const int n_lo = rank * 192;                  // this rank's slice [n_lo, n_lo + 192) of the 768 stacked head units
+    const int hA = n_lo / 256, hB = (n_lo + 191) / 256;   // the (at most two) heads the slice touches
 
     if (tid == 0) {
         for (int s = 0; s < kSlots; ++s) {
@@ -118,121 +136,144 @@ tc_pc_sampler_kernel(TcPcParams tp) {
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem_base = s_tmem_base;
-    const uint32_t idesc = make_idesc_bf16_f32(128, 128);
+    const uint32_t idesc128 = make_idesc_bf16_f32(128, 128), idesc64 = make_idesc_bf16_f32(128, 64);
     const bool dbg_cta = p.dbg != nullptr && blockIdx.x == 0;
 
     if (warp == kTcRowWarps + 1) {
         // =============================== weight producer ===============================
         if (lane == 0) {
-            const uint32_t total = (uint32_t)p.T * kSlotsPerStep;
+            const uint32_t total = (uint32_t)p.T * kSlotsPerCtaStep;
             for (uint32_t it = 0; it < total; ++it) {
                 const uint32_t s = it % kSlots;
+                const uint32_t idx = it % kSlotsPerCtaStep;
+                const uint32_t src = idx < (uint32_t)kCommonSlots ? idx : idx + (uint32_t)(rank * kHeadSlots);
                 mbar_wait(&bar_empty[s], ((it / kSlots) & 1u) ^ 1u);
                 mbar_arrive_expect_tx(&bar_full[s], kSlotBytes);
-                bulk_g2s(sRing + s * kSlotBytes, tp.wstream + (size_t)(it % kSlotsPerStep) * kSlotBytes, kSlotBytes, &bar_full[s]);
+                bulk_g2s(sRing + s * kSlotBytes, tp.wstream + (size_t)src * kSlotBytes, kSlotBytes, &bar_full[s]);
             }
         }
     } else if (warp == kTcRowWarps) {
         // =============================== MMA issuer ===============================
         // The WHOLE warp runs this loop (uniform control flow => descriptors and TMEM addresses live in uniform registers);
-        // one elected lane issues each tcgen05.mma / tcgen05.commit.
-        {
-            const uint32_t ring = smem_u32(sRing);
-            const uint32_t t_ahi = tmem_base + kColAhi, t_alo = tmem_base + kColAlo;
-            uint32_t u = 0, it = 0, xr = 0, ar = 0;
-            for (int step = 0; step < p.T; ++step) {
-                unsigned long long *ds = (dbg_cta && lane == 0) ? p.dbg + ((size_t)p.T + step) * 16 : nullptr;
-                unsigned long long w_full = 0, w_a = 0, w_acc = 0, tq = 0, w_issue = 0, w_fence = 0;
-                if (ds) ds[0] = clock64();
-                // ---- layer 0: h1_pre = x . P1^T   (K = 16; x pieces x1,x2,x3 at A_hi[0,8),[8,16),[16,24); P1 hi|lo per unit)
-                mbar_wait(&bar_x_ready, xr & 1u);
-                ++xr;
-                if (ds) ds[1] = clock64();
-                {
-                    const uint32_t s = it % kSlots;
-                    mbar_wait(&bar_full[s], (it / kSlots) & 1u);
-                    for (int half = 0; half < 2; ++half) {
-                        const uint32_t b = u & 1u, n = u >> 1;
-                        mbar_wait(&bar_acc_empty[b], (n & 1u) ^ 1u);
-                        tc_fence_after_sync();
-                        const uint32_t d = tmem_base + kColD + b * 128u;
-                        const uint64_t bhi = make_smem_desc(ring + s * kSlotBytes + (uint32_t)half * 8192u, kLboB, kSbo);
-                        const uint64_t blo = make_smem_desc(ring + s * kSlotBytes + (uint32_t)half * 8192u + 4096u, kLboB, kSbo);
-                        if (elect_one_sync()) {
-                            umma_bf16_ts(d, t_ahi + 0u, bhi, idesc, false);
-                            umma_bf16_ts(d, t_ahi + 8u, bhi, idesc, true);
-                            umma_bf16_ts(d, t_ahi + 16u, bhi, idesc, true);
-                            umma_bf16_ts(d, t_ahi + 0u, blo, idesc, true);
-                            umma_bf16_ts(d, t_ahi + 8u, blo, idesc, true);
-                            if (half == 1) umma_commit(&bar_empty[s]);
-                            umma_commit(&bar_acc_full[b]);
-                        }
-                        __syncwarp();
-                        ++u;
+        // one elected lane issues each group of tcgen05.mma / tcgen05.commit.
+        const uint32_t ring = smem_u32(sRing);
+        const uint32_t t_ahi = tmem_base + kColAhi, t_alo = tmem_base + kColAlo;
+        uint32_t u = 0, it = 0, xr = 0, ar = 0;
+        // wait for n_slots consecutive ring slots starting at stream position `it`: lane l polls slot l (one wait latency)
+        auto wait_slots = [&](int n_slots) {
+            if (lane < n_slots) {
+                const uint32_t itl = it + (uint32_t)lane;
+                mbar_wait(&bar_full[itl % kSlots], (itl / kSlots) & 1u);
+            }
+            __syncwarp();
+            tc_fence_after_sync();
+        };
+        for (int step = 0; step < p.T; ++step) {
+            unsigned long long *ds = (dbg_cta && lane == 0) ? p.dbg + ((size_t)p.T + step) * 16 : nullptr;
+            unsigned long long w_full = 0, w_a = 0, w_acc = 0, tq = 0, w_issue = 0;
+            if (ds) ds[0] = clock64();
+            // ---- layer 0: h1_pre = x . P1^T   (K = 16; x pieces x1,x2,x3 at A_hi[0,8),[8,16),[16,24); P1 hi|lo per unit)
+            mbar_wait(&bar_x_ready, xr & 1u);
+            ++xr;
+            if (ds) ds[1] = clock64();
+            {
+                wait_slots(1);
+                const uint32_t s = it % kSlots;
+                for (int half = 0; half < 2; ++half) {
+                    const uint32_t b = u & 1u, n = u >> 1;
+                    mbar_wait(&bar_acc_empty[b], (n & 1u) ^ 1u);
+                    tc_fence_after_sync();
+                    const uint32_t d = tmem_base + kColD + b * 128u;
+                    const uint64_t bhi = make_smem_desc(ring + s * kSlotBytes + (uint32_t)half * 8192u, kLboB, kSbo);
+                    const uint64_t blo = make_smem_desc(ring + s * kSlotBytes + (uint32_t)half * 8192u + 4096u, kLboB, kSbo);
+                    if (elect_one_sync()) {
+                        umma_bf16_ts(d, t_ahi + 0u, bhi, idesc128, false);
+                        umma_bf16_ts(d, t_ahi + 8u, bhi, idesc128, true);
+                        umma_bf16_ts(d, t_ahi + 16u, bhi, idesc128, true);
+                        umma_bf16_ts(d, t_ahi + 0u, blo, idesc128, true);
+                        umma_bf16_ts(d, t_ahi + 8u, blo, idesc128, true);
+                        if (half == 1) umma_commit(&bar_empty[s]);
+                        umma_commit(&bar_acc_full[b]);
                     }
-                    ++it;
+                    __syncwarp();
+                    ++u;
                 }
-                // ---- layers 1..4: P2, head rot_x, head rot_y, head trans   (K = 256, two N = 128 units each)
-                for (int layer = 1; layer <= 4; ++layer) {
-                    if (ds) tq = clock64();
-                    if (layer <= 2) {
-                        mbar_wait(&bar_a_ready, ar & 1u);
-                        ++ar;
-                    }
-                    if (ds) {
-                        w_a += clock64() - tq;
-                        ds[2 + layer] = clock64();
-                    }
-                    for (int half = 0; half < 2; ++half) {
-                        const uint32_t b = u & 1u, n = u >> 1;
-                        if (ds) tq = clock64();
-                        mbar_wait(&bar_acc_empty[b], (n & 1u) ^ 1u);
-                        if (ds) w_acc += clock64() - tq;
-                        const uint32_t d = tmem_base + kColD + b * 128u;
-                        // all 8 weight slots of the unit: lanes 0-7 wait on one mbarrier each (one wait latency instead of 8)
-                        if (ds) tq = clock64();
-                        if (lane < 8) {
-                            const uint32_t itl = it + (uint32_t)lane;
-                            mbar_wait(&bar_full[itl % kSlots], (itl / kSlots) & 1u);
-                        }
-                        __syncwarp();
-                        if (ds) { w_full += clock64() - tq; tq = clock64(); }
-                        tc_fence_after_sync();
-                        if (ds) { w_fence += clock64() - tq; tq = clock64(); }
-                        const uint32_t s_first = it % kSlots;
-                        if (elect_one_sync()) {       // one issue group per unit: 48 MMAs, 8 slot releases, accumulator-ready
-#pragma unroll
-                            for (int kc = 0; kc < 8; ++kc) {
-                                uint32_t s = s_first + (uint32_t)kc;
-                                s = s >= (uint32_t)kSlots ? s - (uint32_t)kSlots : s;
-                                const uint32_t sb = ring + s * kSlotBytes;
-#pragma unroll
-                                for (int j = 0; j < 2; ++j) {
-                                    const uint64_t b_hi = make_smem_desc(sb + 2u * j * kLboB, kLboB, kSbo);
-                                    const uint64_t b_lo = make_smem_desc(sb + 8192u + 2u * j * kLboB, kLboB, kSbo);
-                                    const uint32_t ac = (uint32_t)kc * 16u + 8u * j;      // K index / 2
-                                    umma_bf16_ts(d, t_ahi + ac, b_hi, idesc, (kc | j) != 0);
-                                    umma_bf16_ts(d, t_alo + ac, b_hi, idesc, true);
-                                    umma_bf16_ts(d, t_ahi + ac, b_lo, idesc, true);
-                                }
-                                umma_commit(&bar_empty[s]);
-                            }
-                            umma_commit(&bar_acc_full[b]);
-                        }
-                        __syncwarp();
-                        if (ds) w_issue += clock64() - tq;
-                        it += 8;
-                        ++u;
-                    }
+                ++it;
+            }
+            // ---- units with K = 256: layer 1 (P2: two 128-column units) and this rank's head slice (128 + 64 columns) ----
+            for (int unit = 0; unit < 4; ++unit) {
+                if (ds) tq = clock64();
+                if (unit == 0 || unit == 2) {      // h1 / pf complete in tensor memory
+                    mbar_wait(&bar_a_ready, ar & 1u);
+                    ++ar;
                 }
                 if (ds) {
-                    ds[7] = clock64();
-                    ds[8] = w_full;
-                    ds[9] = w_a;
-                    ds[10] = w_acc;
-                    ds[11] = w_issue;
-                    ds[12] = w_fence;
+                    w_a += clock64() - tq;
+                    if (unit == 0) ds[3] = clock64();
+                    if (unit == 2) ds[4] = clock64();
+                    tq = clock64();
                 }
+                const uint32_t b = u & 1u, n = u >> 1;
+                mbar_wait(&bar_acc_empty[b], (n & 1u) ^ 1u);
+                if (ds) { w_acc += clock64() - tq; tq = clock64(); }
+                const uint32_t d = tmem_base + kColD + b * 128u;
+                const bool small = unit == 3;                      // the 64-column unit: 2 K-chunks per slot
+                const int n_slots = small ? 4 : 8;
+                wait_slots(n_slots);
+                if (ds) { w_full += clock64() - tq; tq = clock64(); }
+                const uint32_t s_first = it % kSlots;
+                if (elect_one_sync()) {       // one issue group per unit: 48 MMAs, slot releases, accumulator-ready
+                    if (!small) {
+#pragma unroll
+                        for (int kc = 0; kc < 8; ++kc) {
+                            uint32_t s = s_first + (uint32_t)kc;
+                            s = s >= (uint32_t)kSlots ? s - (uint32_t)kSlots : s;
+                            const uint32_t sb = ring + s * kSlotBytes;
+#pragma unroll
+                            for (int j = 0; j < 2; ++j) {
+                                const uint64_t b_hi = make_smem_desc(sb + 2u * j * kLboB, kLboB, kSbo);
+                                const uint64_t b_lo = make_smem_desc(sb + 8192u + 2u * j * kLboB, kLboB, kSbo);
+                                const uint32_t ac = (uint32_t)kc * 16u + 8u * j;      // K index / 2
+                                umma_bf16_ts(d, t_ahi + ac, b_hi, idesc128, (kc | j) != 0);
+                                umma_bf16_ts(d, t_alo + ac, b_hi, idesc128, true);
+                                umma_bf16_ts(d, t_ahi + ac, b_lo, idesc128, true);
+                            }
+                            umma_commit(&bar_empty[s]);
+                        }
+                    } else {
+#pragma unroll
+                        for (int sl = 0; sl < 4; ++sl) {
+                            uint32_t s = s_first + (uint32_t)sl;
+                            s = s >= (uint32_t)kSlots ? s - (uint32_t)kSlots : s;
+#pragma unroll
+                            for (int c = 0; c < 2; ++c) {                  // K-chunk 2*sl + c: [hi 4 KiB | lo 4 KiB] at c * 8 KiB
+                                const uint32_t sb = ring + s * kSlotBytes + (uint32_t)c * 8192u;
+#pragma unroll
+                                for (int j = 0; j < 2; ++j) {
+                                    const uint64_t b_hi = make_smem_desc(sb + 2u * j * kLboB64, kLboB64, kSbo);
+                                    const uint64_t b_lo = make_smem_desc(sb + 4096u + 2u * j * kLboB64, kLboB64, kSbo);
+                                    const uint32_t ac = (uint32_t)(2 * sl + c) * 16u + 8u * j;
+                                    umma_bf16_ts(d, t_ahi + ac, b_hi, idesc64, (sl | c | j) != 0);
+                                    umma_bf16_ts(d, t_alo + ac, b_hi, idesc64, true);
+                                    umma_bf16_ts(d, t_ahi + ac, b_lo, idesc64, true);
+                                }
+                            }
+                            umma_commit(&bar_empty[s]);
+                        }
+                    }
+                    umma_commit(&bar_acc_full[b]);
+                }
+                __syncwarp();
+                if (ds) w_issue += clock64() - tq;
+                it += (uint32_t)n_slots;
+                ++u;
+            }
+            if (ds) {
+                ds[7] = clock64();
+                ds[8] = w_full;
+                ds[9] = w_a;
+                ds[10] = w_acc;
+                ds[11] = w_issue;
             }
         }
     } else {
@@ -241,9 +282,13 @@ tc_pc_sampler_kernel(TcPcParams tp) {
         const int r = q * 32 + lane;              // row of the tile == TMEM lane
         const int row = row0 + r;                 // global candidate row
         const bool valid = row < p.R;
+        const bool leader = rank == 0;
         const uint32_t tm_row = tmem_base + ((uint32_t)(q * 32) << 16);
         const float *obt_row = sObt + (size_t)((valid ? row : p.R - 1) / p.K - obj_lo) * 768;
         const bool dbg = dbg_cta && tid == 0;
+        float *xf = tp.xch_f + (size_t)tile * 3 * 128 * 9;
+        float *xx = tp.xch_x + (size_t)tile * 128 * 9;
+        unsigned *cnt_f = tp.xch_cnt + 2 * tile, *cnt_x = tp.xch_cnt + 2 * tile + 1;
 
         float x[9];
 #pragma unroll
@@ -281,6 +326,26 @@ tc_pc_sampler_kernel(TcPcParams tp) {
         const float snr_norm = (float)((double)p.snr * 3.0);
         uint32_t u = 0;
         unsigned bar_target = 0;
+
+        // relu(acc + obj_bias + t_bias) . O over one 32-column block whose first stacked hidden unit is n (one head per block)
+        auto head_block = [&](const uint32_t (&v)[32], int n, float &o0, float &o1, float &o2) {
+            const float *ob = obt_row + n;
+            const float *w0 = sOw + (size_t)(3 * (n >> 8)) * 256 + (n & 255);
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+                const float4 o4 = *reinterpret_cast<const float4 *>(ob + 4 * j4);
+                const float4 wa = *reinterpret_cast<const float4 *>(w0 + 4 * j4);
+                const float4 wb = *reinterpret_cast<const float4 *>(w0 + 256 + 4 * j4);
+                const float4 wc = *reinterpret_cast<const float4 *>(w0 + 512 + 4 * j4);
+                const float h0 = fmaxf(__uint_as_float(v[4 * j4 + 0]) + o4.x, 0.f);
+                const float h1 = fmaxf(__uint_as_float(v[4 * j4 + 1]) + o4.y, 0.f);
+                const float h2 = fmaxf(__uint_as_float(v[4 * j4 + 2]) + o4.z, 0.f);
+                const float h3 = fmaxf(__uint_as_float(v[4 * j4 + 3]) + o4.w, 0.f);
+                o0 = fmaf(h3, wa.w, fmaf(h2, wa.z, fmaf(h1, wa.y, fmaf(h0, wa.x, o0))));
+                o1 = fmaf(h3, wb.w, fmaf(h2, wb.z, fmaf(h1, wb.y, fmaf(h0, wb.x, o1))));
+                o2 = fmaf(h3, wc.w, fmaf(h2, wc.z, fmaf(h1, wc.y, fmaf(h0, wc.x, o2))));
+            }
+        };
 
         for (int step = 0; step < p.T; ++step) {
             unsigned long long *ds = dbg ? p.dbg + (size_t)step * 16 : nullptr;
@@ -340,66 +405,64 @@ tc_pc_sampler_kernel(TcPcParams tp) {
                 }
                 if (ds) ds[2 + 2 * layer] = clock64();
             }
-            // noise of this step, generated while the tensor core runs the heads (warps 0-3 own the rows)
+            // noise of this step, generated while the tensor core runs the head slice (the leader's warps 0-3 own the rows)
             float z1[9], z2[9];
-            if (cs == 0 && valid) {
+            if (leader && cs == 0 && valid) {
                 row_noise(p, step, 0, row, z1);
                 row_noise(p, step, 1, row, z2);
             }
             named_bar_sync(3, kTcRowWarps * 32);      // sObt holds obj_bias + t_bias of THIS step (written by warps 4-7)
-            // ---- heads: relu(acc + obj_bias + t_bias) . O   -> 3 score components per head ----
-            float f[9];
+            // ---- head slice: relu(acc + obj_bias + t_bias) . O, partial sums per touched head (oA: head hA, oB: head hB) ----
+            float oA[3] = {0.f, 0.f, 0.f}, oB[3] = {0.f, 0.f, 0.f};
+            {   // 128-column unit: this thread's columns [cs*64, +64) of the slice
+                const uint32_t b = u & 1u, n = u >> 1;
+                mbar_wait(&bar_acc_full[b], n & 1u);
+                if (ds) ds[5] = clock64();
+                tc_fence_after_sync();
 #pragma unroll 1
-            for (int h = 0; h < 3; ++h) {
-                float o0 = 0.f, o1 = 0.f, o2 = 0.f;
-#pragma unroll 1
-                for (int half = 0; half < 2; ++half) {
-                    const uint32_t b = u & 1u, n = u >> 1;
-                    mbar_wait(&bar_acc_full[b], n & 1u);
-                    if (ds && half == 0) ds[5 + 2 * h] = clock64();
-                    tc_fence_after_sync();
-                    uint32_t v0[32], v1[32];
-                    tmem_ld32(tm_row + kColD + b * 128u + (uint32_t)cs * 64u, v0);
-                    tmem_ld32(tm_row + kColD + b * 128u + (uint32_t)cs * 64u + 32u, v1);
+                for (int blk = 0; blk < 2; ++blk) {
+                    uint32_t v[32];
+                    tmem_ld32(tm_row + kColD + b * 128u + (uint32_t)(cs * 64 + blk * 32), v);
                     tmem_ld_wait();
-                    tc_fence_before_sync();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&bar_acc_empty[b]);
-                    const int n0 = h * 256 + half * 128 + cs * 64;                 // first stacked hidden unit of this slice
-                    const float *ob = obt_row + n0;
-                    const float *w0 = sOw + (size_t)(3 * h) * 256 + half * 128 + cs * 64;
+                    const int nn = n_lo + cs * 64 + blk * 32;
+                    if ((nn >> 8) == hA) head_block(v, nn, oA[0], oA[1], oA[2]);
+                    else head_block(v, nn, oB[0], oB[1], oB[2]);
+                }
+                tc_fence_before_sync();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar_acc_empty[b]);
+                ++u;
+                if (ds) ds[6] = clock64();
+            }
+            {   // 64-column unit: this thread's columns [128 + cs*32, +32) of the slice
+                const uint32_t b = u & 1u, n = u >> 1;
+                mbar_wait(&bar_acc_full[b], n & 1u);
+                if (ds) ds[7] = clock64();
+                tc_fence_after_sync();
+                uint32_t v[32];
+                tmem_ld32(tm_row + kColD + b * 128u + (uint32_t)(cs * 32), v);
+                tmem_ld_wait();
+                tc_fence_before_sync();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar_acc_empty[b]);
+                const int nn = n_lo + 128 + cs * 32;
+                if ((nn >> 8) == hA) head_block(v, nn, oA[0], oA[1], oA[2]);
+                else head_block(v, nn, oB[0], oB[1], oB[2]);
+                ++u;
+                if (ds) ds[8] = clock64();
+            }
+            // this thread's 9 partial score components (zero outside the touched heads)
+            float f[9];
 #pragma unroll
-                    for (int j4 = 0; j4 < 16; ++j4) {
-                        const float4 o4 = *reinterpret_cast<const float4 *>(ob + 4 * j4);
-                        const float4 wa = *reinterpret_cast<const float4 *>(w0 + 4 * j4);
-                        const float4 wb = *reinterpret_cast<const float4 *>(w0 + 256 + 4 * j4);
-                        const float4 wc = *reinterpret_cast<const float4 *>(w0 + 512 + 4 * j4);
-                        const uint32_t *vv = j4 < 8 ? &v0[4 * j4] : &v1[4 * j4 - 32];
-                        const float h0 = fmaxf(__uint_as_float(vv[0]) + o4.x, 0.f);
-                        const float h1 = fmaxf(__uint_as_float(vv[1]) + o4.y, 0.f);
-                        const float h2 = fmaxf(__uint_as_float(vv[2]) + o4.z, 0.f);
-                        const float h3 = fmaxf(__uint_as_float(vv[3]) + o4.w, 0.f);
-                        o0 = fmaf(h3, wa.w, fmaf(h2, wa.z, fmaf(h1, wa.y, fmaf(h0, wa.x, o0))));
-                        o1 = fmaf(h3, wb.w, fmaf(h2, wb.z, fmaf(h1, wb.y, fmaf(h0, wb.x, o1))));
-                        o2 = fmaf(h3, wc.w, fmaf(h2, wc.z, fmaf(h1, wc.y, fmaf(h0, wc.x, o2))));
-                    }
-                    ++u;
-                }
-                if (ds) ds[6 + 2 * h] = clock64();
-                if (cs == 1) {
-                    sFpart[r * 12 + 3 * h + 0] = o0;
-                    sFpart[r * 12 + 3 * h + 1] = o1;
-                    sFpart[r * 12 + 3 * h + 2] = o2;
-                } else {
-                    f[3 * h + 0] = o0;
-                    f[3 * h + 1] = o1;
-                    f[3 * h + 2] = o2;
-                }
+            for (int c = 0; c < 9; ++c) f[c] = ((c / 3) == hA ? oA[c % 3] : 0.f) + (((c / 3) == hB && hB != hA) ? oB[c % 3] : 0.f);
+            if (cs == 1) {
+#pragma unroll
+                for (int c = 0; c < 9; ++c) sFpart[r * 12 + c] = f[c];
             }
             named_bar_sync(1, kTcRowWarps * 32);      // sub-half 1 partials are in sFpart; everyone is done with sObt
-            if (ds) ds[11] = clock64();
+            if (ds) ds[9] = clock64();
             if (cs == 1) {
-                // warps 4-7: table of (object bias + time bias) for the NEXT step, while warps 0-3 reduce and update
+                // warps 4-7: table of (object bias + time bias) for the NEXT step, while warps 0-3 exchange / reduce / update
                 if (step + 1 < p.T) {
                     const float *tbn = p.tb_table + (size_t)(step + 1) * 768;
                     for (int i = tid - 128; i < n_obj * 768; i += 128)
@@ -407,21 +470,53 @@ tc_pc_sampler_kernel(TcPcParams tp) {
                 }
                 continue;
             }
+#pragma unroll
+            for (int c = 0; c < 9; ++c) f[c] += sFpart[r * 12 + c];
 
-            // ---- score, batch-mean gradient norm, update (warps 0-3: one thread per row) ----
+            if (!leader) {
+                // ---- peers: mail the partial sums to the leader, then wait for the new pose rows ----
+                float *dst = xf + ((size_t)(rank - 1) * 128 + r) * 9;
+#pragma unroll
+                for (int c = 0; c < 9; ++c) __stcg(dst + c, f[c]);
+                named_bar_sync(2, 128);
+                if (tid == 0) {
+                    red_release_add(cnt_f, 1u);
+                    while (ld_acquire_u32(cnt_x) < (unsigned)(step + 1)) {
+                    }
+                }
+                named_bar_sync(2, 128);
+#pragma unroll
+                for (int c = 0; c < 9; ++c) x[c] = __ldcg(xx + (size_t)r * 9 + c);
+                publish_x();
+                continue;
+            }
+
+            // ---- leader: gather the team's partials (fixed order), score, batch-mean gradient norm, update ----
+            if (tid == 0) {
+                while (ld_acquire_u32(cnt_f) < (unsigned)(3 * (step + 1))) {
+                }
+            }
+            named_bar_sync(2, 128);
+            if (ds) ds[10] = clock64();
+#pragma unroll
+            for (int pr = 0; pr < 3; ++pr) {
+                const float *src = xf + ((size_t)pr * 128 + r) * 9;
+#pragma unroll
+                for (int c = 0; c < 9; ++c) f[c] += __ldcg(src + c);
+            }
             float gr[9], n2 = 0.f;
 #pragma unroll
             for (int c = 0; c < 9; ++c) {
-                gr[c] = ((f[c] + sFpart[r * 12 + c]) + sOw[9 * 256 + c]) / stdv;
+                gr[c] = (f[c] + sOw[9 * 256 + c]) / stdv;
                 n2 = fmaf(gr[c], gr[c], n2);
             }
             const float wsum = warp_sum(valid ? sqrtf(n2) : 0.f);
             if (lane == 0) s_red[q] = wsum;
             named_bar_sync(2, 128);
-            bar_target += gridDim.x;
+            bar_target += (unsigned)n_tiles;
             if (tid == 0) {
                 if (ds) ds[14] = clock64();
-                p.partial[(step & 1) * gridDim.x + blockIdx.x] = (s_red[0] + s_red[1]) + (s_red[2] + s_red[3]);
+                p.partial[(step & 1) * n_tiles + tile] = (s_red[0] + s_red[1]) + (s_red[2] + s_red[3]);
                 red_release_add(p.barrier, 1u);
                 while (ld_acquire_u32(p.barrier) < bar_target) {
                 }
@@ -429,8 +524,8 @@ tc_pc_sampler_kernel(TcPcParams tp) {
             }
             named_bar_sync(2, 128);
             if (ds) ds[12] = clock64();
-            float tot = 0.f;   // every warp: lanes fetch the per-CTA partials in parallel, fixed-shape shuffle tree => identical everywhere
-            for (int i = lane; i < (int)gridDim.x; i += 32) tot += __ldcg(p.partial + (step & 1) * gridDim.x + i);
+            float tot = 0.f;   // every warp: lanes fetch the per-tile partials in parallel, fixed-shape shuffle tree => identical everywhere
+            for (int i = lane; i < n_tiles; i += 32) tot += __ldcg(p.partial + (step & 1) * n_tiles + i);
             tot = warp_sum(tot);
             const float grad_norm = tot / (float)p.R;
             const PcStepConsts sc = pc_step_consts(grad_norm, snr_norm, sigma, step_size, sqrt_step);
@@ -463,6 +558,11 @@ tc_pc_sampler_kernel(TcPcParams tp) {
                     for (int c = 0; c < 9; ++c) p.mean_x[(size_t)row * 9 + c] = m[c];
                 }
             }
+            // mail the new pose rows to the peers, then publish them locally
+#pragma unroll
+            for (int c = 0; c < 9; ++c) __stcg(xx + (size_t)r * 9 + c, x[c]);
+            named_bar_sync(2, 128);
+            if (tid == 0) red_release_add(cnt_x, 1u);
             publish_x();
             if (ds) ds[13] = clock64();
         }
@@ -498,7 +598,8 @@ extern "C" int gpb_sample_pc_tc_dbg(const float *x0, int R, int K, int num_steps
     int dev = 0, sms = 0;
     GPB_CUDA(cudaGetDevice(&dev));
     GPB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    const int grid = (R + kTcRows - 1) / kTcRows;
+    const int n_tiles = (R + kTcRows - 1) / kTcRows;
+    const int grid = n_tiles * kTeam;
     GPB_REQUIRE(grid <= sms, "sample_pc_tc: R=%d needs %d co-resident CTAs but the device has %d SMs; split the batch", R, grid, sms);
 
     SamplerWs w = carve_sampler(workspace, R, num_steps);
@@ -513,6 +614,10 @@ extern "C" int gpb_sample_pc_tc_dbg(const float *x0, int R, int K, int num_steps
     p.ts = time_grid; p.tb_table = w.tb_table; p.partial = w.partial; p.barrier = w.barrier;
     p.mean_x = mean_x; p.process = process; p.tiles_per_cta = 1; p.dbg = dbg;
     tp.wstream = reinterpret_cast<const uint8_t *>(tc_stream);
+    tp.xch_cnt = reinterpret_cast<unsigned *>(w.xch);
+    tp.xch_x = reinterpret_cast<float *>(reinterpret_cast<char *>(w.xch) + 4096);
+    tp.xch_f = tp.xch_x + (size_t)n_tiles * 128 * 9;
+    GPB_CUDA(cudaMemsetAsync(w.xch, 0, 4096, st));
     GPB_CUDA(cudaFuncSetAttribute(tc_pc_sampler_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes));
     void *args[] = {&tp};
     GPB_CUDA(cudaLaunchCooperativeKernel((void *)tc_pc_sampler_kernel, dim3(grid), dim3(kTcThreads), args, kTcSmemBytes, st));

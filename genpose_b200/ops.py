@@ -135,9 +135,9 @@ class Engine:
     # ---- a9: PC sampler -------------------------------------------------------------------------------
     @staticmethod
     def tc_supported(R: int, K: int) -> bool:
-        """tcgen05 sampler constraints: a 128-row tile spans <= 4 objects, one CTA per tile co-resident."""
+        """tcgen05 sampler constraints: a 128-row tile spans <= 4 objects, four co-resident CTAs per tile."""
         sms = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
-        return 127 // K + 2 <= 4 and (R + 127) // 128 <= sms
+        return 127 // K + 2 <= 4 and 4 * ((R + 127) // 128) <= sms
 
     def sample_pc(self, obj_bias: torch.Tensor, pts_center: torch.Tensor, x0: torch.Tensor, K: int, num_steps: int,
                   step_noise: Optional[torch.Tensor] = None, seed: int = 0, snr: float = arch.SNR,

@@ -132,12 +132,15 @@ def umma_image(w_bf16: torch.Tensor, variant: int = 0) -> torch.Tensor:
 
 
 def pack_trunk_tc(sd: Dict[str, torch.Tensor], prefix: str = "pose_score_net") -> torch.Tensor:
-    """The per-step weight stream of tc_pc_sampler_kernel: 65 slots of 16 KiB (int16 words).  Operand images are 128-row
-    [K/8][128][8] blocks of one N = 128 "unit" (output neurons [0,128) = unit a, [128,256) = unit b):
-         slot 0        : P1 (K padded 9 -> 16): unit a hi (4 KiB) | lo (4 KiB) | unit b hi | lo
-         slots 1..64   : for layer in (P2, head rot_x, head rot_y, head trans): for unit in (a, b):
-                             for K-chunk kc in 0..7 (32 input columns): hi image chunk (8 KiB) | lo image chunk (8 KiB)
-    Head matrices are the pose-feature column block [:, 1152:1408] of fusion_tail_*.0.weight (scorenet.py:204)."""
+    """The weight stream of tc_pc_sampler_kernel: 65 slots of 16 KiB (int16 words), each a pair `hi image | lo image` of
+    K-major no-swizzle operand blocks [K/8][rows][8]:
+         slot 0         : P1 (K padded 9 -> 16), output neurons [0,128): hi (4 KiB) | lo (4 KiB), then [128,256): hi | lo
+         slots 1..16    : P2: for unit in ([0,128), [128,256)): for K-chunk kc in 0..7 (32 inputs): 128-row hi (8 KiB) | lo (8 KiB)
+         slots 17+12r.. : head slice of team rank r = stacked hidden units [192r, 192r+192) of the three heads
+                          (rows h*256 + j of fusion_tail_{rot_x,rot_y,trans}.0.weight[:, 1152:1408], scorenet.py:204):
+                            8 slots : units [192r, 192r+128), K-chunk kc: 128-row hi (8 KiB) | lo (8 KiB)
+                            4 slots : units [192r+128, 192r+192), two K-chunks per slot: 64-row hi (4 KiB) | lo (4 KiB), twice
+    Every CTA streams slots 0..16 plus its rank's 12 slots each step."""
     g = lambda k: sd[f"{prefix}.{k}"].float()
     slots = []
     p1 = torch.zeros(256, 16)
@@ -147,14 +150,26 @@ def pack_trunk_tc(sd: Dict[str, torch.Tensor], prefix: str = "pose_score_net") -
         hi, lo = split_bf16(p1[128 * unit: 128 * unit + 128])
         parts += [umma_image(hi), umma_image(lo)]
     slots.append(torch.cat(parts))
+
+    def unit_slots(w_rows, chunks_per_slot):
+        rows = w_rows.shape[0]
+        hi, lo = split_bf16(w_rows)
+        ih, il = umma_image(hi).reshape(32, rows * 8), umma_image(lo).reshape(32, rows * 8)
+        out = []
+        for s0 in range(0, 8, chunks_per_slot):
+            pieces = []
+            for kc in range(s0, s0 + chunks_per_slot):
+                pieces += [ih[4 * kc: 4 * kc + 4].reshape(-1), il[4 * kc: 4 * kc + 4].reshape(-1)]
+            out.append(torch.cat(pieces))
+        return out
+
+    p2 = g("pose_encoder.2.weight")
+    for unit in range(2):
+        slots += unit_slots(p2[128 * unit: 128 * unit + 128], 1)
     off = arch.PTS_FEAT_DIM + arch.T_EMBED_DIM
-    layers = [g("pose_encoder.2.weight")] + [g(f"fusion_tail_{h}.0.weight")[:, off:] for h in arch.HEADS]
-    for w in layers:
-        assert tuple(w.shape) == (256, 256)
-        for unit in range(2):
-            hi, lo = split_bf16(w[128 * unit: 128 * unit + 128])
-            ih, il = umma_image(hi).reshape(32, 128 * 8), umma_image(lo).reshape(32, 128 * 8)
-            for kc in range(8):
-                slots.append(torch.cat([ih[4 * kc: 4 * kc + 4].reshape(-1), il[4 * kc: 4 * kc + 4].reshape(-1)]))
-    assert all(sl.numel() * 2 == 16384 for sl in slots) and len(slots) == 65
+    stacked = torch.cat([g(f"fusion_tail_{h}.0.weight")[:, off:] for h in arch.HEADS], dim=0)      # [768, 256]
+    for r in range(4):
+        slots += unit_slots(stacked[192 * r: 192 * r + 128], 1)
+        slots += unit_slots(stacked[192 * r + 128: 192 * r + 192], 2)
+    assert all(sl.numel() * 2 == 16384 for sl in slots) and len(slots) == 65, (len(slots), {sl.numel() for sl in slots})
     return torch.cat(slots).contiguous()

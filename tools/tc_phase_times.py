@@ -29,22 +29,23 @@ for _ in range(2):
 torch.cuda.synchronize()
 d = dbg.cpu().numpy().astype(np.float64)
 row, mma = d[0, 5:-1], d[1, 5:-1]
-names = ["wait acc0", "epi0", "wait acc1", "epi1", "wait h0", "epi h0", "wait h1", "epi h1", "wait h2", "epi h2", "halves sync",
-         "norm+grid barrier", "update+x pieces"]
-idx = [0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13]
-print("row thread 0 (cycles, mean over steps):")
-for n, a, b in zip(names, idx[:-1], idx[1:]):
-    print(f"  {n:22s} {np.mean(row[:, b] - row[:, a]):9.0f}")
-print(f"  step total             {np.mean(row[1:, 0] - row[:-1, 0]):9.0f}")
-print(f"  (of the barrier phase: score+norm+named barrier {np.mean(row[:, 14] - row[:, 11]):7.0f}, publish+poll {np.mean(row[:, 15] - row[:, 14]):7.0f}, release named barrier {np.mean(row[:, 12] - row[:, 15]):7.0f})")
-print("MMA thread:")
-print(f"  wait x_ready           {np.mean(mma[:, 1] - mma[:, 0]):9.0f}")
-for l in range(1, 5):
-    nxt = mma[:, 3 + l] if l < 4 else mma[:, 7]
-    print(f"  layer {l} issue span     {np.mean(nxt - mma[:, 2 + l]):9.0f}")
-print(f"  waiting on weights     {np.mean(mma[:, 8]):9.0f}   (sum over the step)")
-print(f"  waiting on A operand   {np.mean(mma[:, 9]):9.0f}")
-print(f"  waiting on acc buffers {np.mean(mma[:, 10]):9.0f}")
-print(f"  inside issue groups    {np.mean(mma[:, 11]):9.0f}   (32 groups of 12 MMAs per step)")
-print(f"  tcgen05 fences         {np.mean(mma[:, 12]):9.0f}")
-print(f"  step total             {np.mean(mma[1:, 0] - mma[:-1, 0]):9.0f}")
+# stamps of CTA 0 (team leader of tile 0), row thread 0 — see tc_sampler.cu
+seq = [("wait layer-0 accumulator", 0, 1), ("epilogue layer 0 (2 units)", 1, 2), ("wait layer-1 accumulator", 2, 3),
+       ("epilogue layer 1 (2 units)", 3, 4), ("wait head 128-col unit", 4, 5), ("epilogue head 128-col unit", 5, 6),
+       ("wait head 64-col unit", 6, 7), ("epilogue head 64-col unit", 7, 8), ("column-half sync", 8, 9),
+       ("wait peers' partials", 9, 10), ("score + norm + CTA barrier", 10, 14), ("publish + poll grid barrier", 14, 15),
+       ("release CTA barrier", 15, 12), ("sum partials, update, mail x, publish x", 12, 13)]
+print("leader row thread 0 (cycles, mean over steps):")
+for n, a, b in seq:
+    print(f"  {n:42s} {np.mean(row[:, b] - row[:, a]):9.0f}")
+print(f"  {'step total':42s} {np.mean(row[1:, 0] - row[:-1, 0]):9.0f}")
+print("MMA warp:")
+print(f"  {'wait x_ready':42s} {np.mean(mma[:, 1] - mma[:, 0]):9.0f}")
+print(f"  {'layer 0 issue':42s} {np.mean(mma[:, 3] - mma[:, 1]):9.0f}")
+print(f"  {'layer 1 (2 units) span':42s} {np.mean(mma[:, 4] - mma[:, 3]):9.0f}")
+print(f"  {'head slice (128 + 64 columns) span':42s} {np.mean(mma[:, 7] - mma[:, 4]):9.0f}")
+print(f"  {'  of which: inside issue groups':42s} {np.mean(mma[:, 11]):9.0f}")
+print(f"  {'            waiting on weight slots':42s} {np.mean(mma[:, 8]):9.0f}")
+print(f"  {'            waiting on the A operand':42s} {np.mean(mma[:, 9]):9.0f}")
+print(f"  {'            waiting on accumulator slots':42s} {np.mean(mma[:, 10]):9.0f}")
+print(f"  {'step total':42s} {np.mean(mma[1:, 0] - mma[:-1, 0]):9.0f}")
