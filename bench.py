@@ -92,11 +92,17 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def best_cpu_threads():
+    """torch's intra-op pool stops scaling on these tiny matmuls well below the core count (measured on the 128-core GPU
+    box: 16 threads 1175 cand/s, 32: 626, 64: 300, 128: 1.4 at T=100 — profiles/cpu_threads_probe.txt), so the CPU arm uses 16."""
+    return min(os.cpu_count() or 1, 16)
+
+
 def cpu_oracle_rate(n_objects, K, T, config, seed=0, threads=None):
     """Times the oracle port (reference algorithm on the CPU) on a bounded sample; returns (cands/s, seconds, detail)."""
     from genpose_b200 import synth
     from oracle import genpose_oracle as O
-    threads = threads or os.cpu_count() or 1
+    threads = threads or best_cpu_threads()
     torch.set_num_threads(threads)
     sd = synth.make_state_dict(seed, kappa=-0.3)
     clouds = synth.make_clouds(n_objects, seed)
@@ -124,7 +130,7 @@ def run_reference_arm(args, rank, world):
     Python + a CUDA-only extension and cannot travel to this box) on all host threads; rank 0 only."""
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
+    cores = best_cpu_threads()
     n_obj = args.ref_objects
     for _ in range(args.warmup):
         cpu_oracle_rate(1, K_CAND, 20, args.config, threads=cores)
@@ -141,7 +147,7 @@ def run_reference_arm(args, rank, world):
         "warmup": args.warmup, "ms_per_step": 1000.0 * sum(secs) / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args, world),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "host_cores": os.cpu_count(), "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -309,11 +315,11 @@ def main():
             ffma_peak = 148 * 128 * 2 * clock_info["sm_mhz"] * 1e6 / 1e12
             line["roofline"]["frac_ffma"] = ach / ffma_peak
         if not args.no_cpu_baseline:
-            cores = os.cpu_count() or 1
+            cores = best_cpu_threads()
             cpu_oracle_rate(1, K_CAND, 10, args.config, threads=cores)      # page in
             v, secs, detail = cpu_oracle_rate(args.ref_objects, K_CAND, T_STEPS, args.config, threads=cores)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": f"{args.ref_objects} of {B_PER_GPU} objects x K={K_CAND} x T={T_STEPS} ({secs:.1f} s), "
+                                    "host_cores": os.cpu_count(), "sample": f"{args.ref_objects} of {B_PER_GPU} objects x K={K_CAND} x T={T_STEPS} ({secs:.1f} s), "
                                               f"oracle port of the reference on torch CPU fp32", **detail}
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -99,7 +99,7 @@ struct SamplerWs {
     float *partial;      // [2*1024] floats (PC)  /  doubles [4*1024] (ODE) share the slot
     unsigned *barrier;   // [64] (256 B)
     double *y, *ynew, *Kst;
-    void *xch;           // tile-team mailboxes of the tcgen05 sampler: counters (4 KiB) | poses [tiles][128][9] | partials [tiles][3][128][9]
+    void *xch;           // tile-team mailboxes of the tcgen05 sampler: counters (4 KiB) | partials [tiles][2][4][128][9]
     size_t bytes;
 };
 inline SamplerWs carve_sampler(void *base, int R, int T) {
@@ -117,7 +117,7 @@ inline SamplerWs carve_sampler(void *base, int R, int T) {
     w.y = reinterpret_cast<double *>(take((size_t)R * 9 * sizeof(double)));
     w.ynew = reinterpret_cast<double *>(take((size_t)R * 9 * sizeof(double)));
     w.Kst = reinterpret_cast<double *>(take((size_t)7 * R * 9 * sizeof(double)));
-    w.xch = take(4096 + (size_t)((R + 127) / 128) * 4 * 128 * 9 * sizeof(float));
+    w.xch = take(4096 + (size_t)((R + 127) / 128) * 2 * 4 * 128 * 9 * sizeof(float));
     w.bytes = off;
     return w;
 }

@@ -11,10 +11,10 @@
 // FOUR CTAs share a 128-row tile of candidates for all T steps ("tile team", rank = blockIdx.x & 3): every rank runs
 // layers 0 and 1 (P1, P2) redundantly — they are the sequential prefix — and then only ITS 192-column slice of the
 // 768 stacked head units (N = 128 + N = 64 MMAs), so the head phase costs one quarter of the tensor time.  The ranks'
-// partial score components are summed by rank 0 (the leader, which alone owns the pose state, the noise, the grid-wide
-// gradient-norm reduction and the update); the exchange uses global-memory mailboxes with release/acquire counters
-// (peers -> leader: 9 partial sums per row; leader -> peers: the new pose rows).  Inside a CTA nothing of the per-step
-// state leaves the SM:
+// partial score components (9 per row) are exchanged all-to-all through L2-resident mailboxes with one release/acquire
+// counter per tile and summed in a fixed rank order; every rank then applies the update redundantly and bit-identically
+// (same noise stream, same batch-mean norm, which rank 0 of every tile publishes to the grid-wide reduction), so the new
+// pose never has to be sent back.  Inside a CTA nothing of the per-step state leaves the SM:
 //   * activations never touch shared memory: the A operand of every layer lives in TENSOR MEMORY (written by the
 //     epilogue with tcgen05.st, lane = row, two bf16 per 32-bit column; consumed by the TS form of tcgen05.mma),
 //     TMEM map: D0 [0,128) D1 [128,256) accumulators (N = 128 "units", ping-pong), A_hi [256,384), A_lo [384,512);
@@ -68,9 +68,8 @@ static_assert(kTcSmemBytes <= 227 * 1024 - 768, "tc sampler shared memory budget
 struct TcPcParams {
     PcParams pc;
     const uint8_t *wstream;   // kSlotsPerStep x 16 KiB of bf16 operand images (genpose_b200/weights.py::pack_trunk_tc)
-    float *xch_f;             // [tiles][3 peers][128][9]  partial head sums, peers -> leader
-    float *xch_x;             // [tiles][128][9]           new pose rows, leader -> peers
-    unsigned *xch_cnt;        // [tiles][2]                monotonic counters: [0] peers' partials published, [1] poses published
+    float *xch_f;             // [tiles][2 parities][4 ranks][128][9]  partial head sums, all-to-all inside a tile team
+    unsigned *xch_cnt;        // [tiles]                               monotonic counter: partials published
 };
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
@@ -286,13 +285,12 @@ tc_pc_sampler_kernel(TcPcParams tp) {
         const uint32_t tm_row = tmem_base + ((uint32_t)(q * 32) << 16);
         const float *obt_row = sObt + (size_t)((valid ? row : p.R - 1) / p.K - obj_lo) * 768;
         const bool dbg = dbg_cta && tid == 0;
-        float *xf = tp.xch_f + (size_t)tile * 3 * 128 * 9;
-        float *xx = tp.xch_x + (size_t)tile * 128 * 9;
-        unsigned *cnt_f = tp.xch_cnt + 2 * tile, *cnt_x = tp.xch_cnt + 2 * tile + 1;
+        float *xf = tp.xch_f + (size_t)tile * 2 * kTeam * 128 * 9;       // [parity][rank][row][9]
+        unsigned *cnt_f = tp.xch_cnt + tile;
 
         float x[9];
 #pragma unroll
-        for (int c = 0; c < 9; ++c) x[c] = (valid && cs == 0) ? p.x0[(size_t)row * 9 + c] : 0.f;
+        for (int c = 0; c < 9; ++c) x[c] = (valid && cs == 0) ? p.x0[(size_t)row * 9 + c] : 0.f;   // every rank keeps its own (identical) copy
         auto publish_x = [&]() {   // three bf16 pieces of the pose row -> A_hi[0,24)
             uint32_t pc[3][8];
 #pragma unroll
@@ -407,7 +405,7 @@ tc_pc_sampler_kernel(TcPcParams tp) {
             }
             // noise of this step, generated while the tensor core runs the head slice (the leader's warps 0-3 own the rows)
             float z1[9], z2[9];
-            if (leader && cs == 0 && valid) {
+            if (cs == 0 && valid) {
                 row_noise(p, step, 0, row, z1);
                 row_noise(p, step, 1, row, z2);
             }
@@ -473,51 +471,48 @@ tc_pc_sampler_kernel(TcPcParams tp) {
 #pragma unroll
             for (int c = 0; c < 9; ++c) f[c] += sFpart[r * 12 + c];
 
-            if (!leader) {
-                // ---- peers: mail the partial sums to the leader, then wait for the new pose rows ----
-                float *dst = xf + ((size_t)(rank - 1) * 128 + r) * 9;
+            // ---- all-to-all inside the tile team: mail this rank's partial sums, gather the other three (fixed rank order) ----
+            {
+                float *mine = xf + (((size_t)(step & 1) * kTeam + rank) * 128 + r) * 9;
 #pragma unroll
-                for (int c = 0; c < 9; ++c) __stcg(dst + c, f[c]);
+                for (int c = 0; c < 9; ++c) __stcg(mine + c, f[c]);
                 named_bar_sync(2, 128);
                 if (tid == 0) {
                     red_release_add(cnt_f, 1u);
-                    while (ld_acquire_u32(cnt_x) < (unsigned)(step + 1)) {
+                    while (ld_acquire_u32(cnt_f) < (unsigned)(kTeam * (step + 1))) {
                     }
                 }
                 named_bar_sync(2, 128);
+                if (ds) ds[10] = clock64();
+                float g4[kTeam][9];
 #pragma unroll
-                for (int c = 0; c < 9; ++c) x[c] = __ldcg(xx + (size_t)r * 9 + c);
-                publish_x();
-                continue;
-            }
-
-            // ---- leader: gather the team's partials (fixed order), score, batch-mean gradient norm, update ----
-            if (tid == 0) {
-                while (ld_acquire_u32(cnt_f) < (unsigned)(3 * (step + 1))) {
+                for (int pr = 0; pr < kTeam; ++pr) {
+                    const float *src = xf + (((size_t)(step & 1) * kTeam + pr) * 128 + r) * 9;
+#pragma unroll
+                    for (int c = 0; c < 9; ++c) g4[pr][c] = __ldcg(src + c);
                 }
-            }
-            named_bar_sync(2, 128);
-            if (ds) ds[10] = clock64();
 #pragma unroll
-            for (int pr = 0; pr < 3; ++pr) {
-                const float *src = xf + ((size_t)pr * 128 + r) * 9;
-#pragma unroll
-                for (int c = 0; c < 9; ++c) f[c] += __ldcg(src + c);
+                for (int c = 0; c < 9; ++c) f[c] = ((g4[0][c] + g4[1][c]) + g4[2][c]) + g4[3][c];
             }
+            // ---- every rank: score, batch-mean gradient norm (published by the leaders), update — redundantly, bit-identically ----
             float gr[9], n2 = 0.f;
 #pragma unroll
             for (int c = 0; c < 9; ++c) {
                 gr[c] = (f[c] + sOw[9 * 256 + c]) / stdv;
                 n2 = fmaf(gr[c], gr[c], n2);
             }
-            const float wsum = warp_sum(valid ? sqrtf(n2) : 0.f);
-            if (lane == 0) s_red[q] = wsum;
-            named_bar_sync(2, 128);
             bar_target += (unsigned)n_tiles;
+            if (leader) {
+                const float wsum = warp_sum(valid ? sqrtf(n2) : 0.f);
+                if (lane == 0) s_red[q] = wsum;
+                named_bar_sync(2, 128);
+                if (tid == 0) {
+                    if (ds) ds[14] = clock64();
+                    p.partial[(step & 1) * n_tiles + tile] = (s_red[0] + s_red[1]) + (s_red[2] + s_red[3]);
+                    red_release_add(p.barrier, 1u);
+                }
+            }
             if (tid == 0) {
-                if (ds) ds[14] = clock64();
-                p.partial[(step & 1) * n_tiles + tile] = (s_red[0] + s_red[1]) + (s_red[2] + s_red[3]);
-                red_release_add(p.barrier, 1u);
                 while (ld_acquire_u32(p.barrier) < bar_target) {
                 }
                 if (ds) ds[15] = clock64();
@@ -544,25 +539,22 @@ tc_pc_sampler_kernel(TcPcParams tp) {
 #pragma unroll
                 for (int c = 0; c < 9; ++c) x[c] = m[c] + (sc.g * sc.sqrt_step) * z2[c];                // (:149)
                 gram_schmidt6(x);                                                                        // (:152)
-                const float *ctr = p.pts_center + (size_t)(row / p.K) * 3;
-                if (p.process) {
-                    float *dst = p.process + ((size_t)row * p.T + step) * 9;
+                if (leader) {
+                    const float *ctr = p.pts_center + (size_t)(row / p.K) * 3;
+                    if (p.process) {
+                        float *dst = p.process + ((size_t)row * p.T + step) * 9;
 #pragma unroll
-                    for (int c = 0; c < 9; ++c) dst[c] = x[c] + (c >= 6 ? ctr[c - 6] : 0.f);
-                }
-                if (step == p.T - 1) {
+                        for (int c = 0; c < 9; ++c) dst[c] = x[c] + (c >= 6 ? ctr[c - 6] : 0.f);
+                    }
+                    if (step == p.T - 1) {
 #pragma unroll
-                    for (int c = 6; c < 9; ++c) m[c] += ctr[c - 6];
-                    gram_schmidt6(m);
+                        for (int c = 6; c < 9; ++c) m[c] += ctr[c - 6];
+                        gram_schmidt6(m);
 #pragma unroll
-                    for (int c = 0; c < 9; ++c) p.mean_x[(size_t)row * 9 + c] = m[c];
+                        for (int c = 0; c < 9; ++c) p.mean_x[(size_t)row * 9 + c] = m[c];
+                    }
                 }
             }
-            // mail the new pose rows to the peers, then publish them locally
-#pragma unroll
-            for (int c = 0; c < 9; ++c) __stcg(xx + (size_t)r * 9 + c, x[c]);
-            named_bar_sync(2, 128);
-            if (tid == 0) red_release_add(cnt_x, 1u);
             publish_x();
             if (ds) ds[13] = clock64();
         }
@@ -615,8 +607,7 @@ extern "C" int gpb_sample_pc_tc_dbg(const float *x0, int R, int K, int num_steps
     p.mean_x = mean_x; p.process = process; p.tiles_per_cta = 1; p.dbg = dbg;
     tp.wstream = reinterpret_cast<const uint8_t *>(tc_stream);
     tp.xch_cnt = reinterpret_cast<unsigned *>(w.xch);
-    tp.xch_x = reinterpret_cast<float *>(reinterpret_cast<char *>(w.xch) + 4096);
-    tp.xch_f = tp.xch_x + (size_t)n_tiles * 128 * 9;
+    tp.xch_f = reinterpret_cast<float *>(reinterpret_cast<char *>(w.xch) + 4096);
     GPB_CUDA(cudaMemsetAsync(w.xch, 0, 4096, st));
     GPB_CUDA(cudaFuncSetAttribute(tc_pc_sampler_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes));
     void *args[] = {&tp};
