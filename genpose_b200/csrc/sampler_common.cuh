@@ -33,7 +33,8 @@ struct PcParams {
     float *mean_x;            // [R,9] out
     float *process;           // [R,T,9] out or null
     int tiles_per_cta;
-    unsigned long long *dbg;  // optional [2][T][16] cycle stamps of CTA 0 (profiling aid; NULL in production)
+    unsigned long long *dbg;  // optional [2][T][16] cycle stamps of CTA `dbg_cta` (profiling aid; NULL in production)
+    int dbg_cta;
 };
 
 __device__ __forceinline__ void row_noise(const PcParams &p, int step, int which, int row, float *z) {

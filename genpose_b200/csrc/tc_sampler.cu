@@ -11,15 +11,15 @@
 // FOUR CTAs share a 128-row tile of candidates for all T steps ("tile team", rank = blockIdx.x & 3): every rank runs
 // layers 0 and 1 (P1, P2) redundantly — they are the sequential prefix — and then only ITS 192-column slice of the
 // 768 stacked head units (N = 128 + N = 64 MMAs), so the head phase costs one quarter of the tensor time.  The ranks'
-// partial score components (9 per row) are exchanged all-to-all through L2-resident mailboxes with one release/acquire
-// counter per tile and summed in a fixed rank order; every rank then applies the update redundantly and bit-identically
+// partial score components (9 per row) are exchanged all-to-all through DISTRIBUTED SHARED MEMORY (the team is a thread-block
+// cluster: st.shared::cluster into every rank's mailbox + remote mbarrier arrival) and summed in a fixed rank order; every rank then applies the update redundantly and bit-identically
 // (same noise stream, same batch-mean norm, which rank 0 of every tile publishes to the grid-wide reduction), so the new
 // pose never has to be sent back.  Inside a CTA nothing of the per-step state leaves the SM:
 //   * activations never touch shared memory: the A operand of every layer lives in TENSOR MEMORY (written by the
 //     epilogue with tcgen05.st, lane = row, two bf16 per 32-bit column; consumed by the TS form of tcgen05.mma),
 //     TMEM map: D0 [0,128) D1 [128,256) accumulators (N = 128 "units", ping-pong), A_hi [256,384), A_lo [384,512);
-//   * the whole 227 KB of shared memory is therefore free for the weight stream: 12 slots x 16 KiB of pre-tiled bf16
-//     operand images (hi | lo; 1,040 KiB per step, L2-resident) fetched with cp.async.bulk on mbarriers, 12 K-chunks ahead;
+//   * the whole 227 KB of shared memory is therefore free for the weight stream: 9 slots x 16 KiB of pre-tiled bf16
+//     operand images (hi | lo; 1,040 KiB per step, L2-resident) fetched with cp.async.bulk on mbarriers, up to 9 K-chunks ahead;
 //   * pose state, noise and score of a row live in the registers of "its" thread.
 // Roles (warp-specialised, 320 threads):
 //   warps 0-7  row warps: warp w owns TMEM lanes 32*(w%4).. (rows) and the column sub-half w/4 of every unit.
@@ -44,7 +44,7 @@ constexpr int kTcRows = 128;
 constexpr int kTcRowWarps = 8;
 constexpr int kTcThreads = (kTcRowWarps + 2) * 32;
 constexpr uint32_t kSlotBytes = 16384;
-constexpr int kSlots = 12;
+constexpr int kSlots = 9;
 constexpr int kTeam = 4;                           // CTAs per tile
 constexpr int kCommonSlots = 1 + 16;               // P1 (both units) + P2 (2 units x 8 K-chunks); slot = hi image | lo image
 constexpr int kHeadSlots = 8 + 4;                  // head slice: 128-row unit (8 K-chunks) + 64-row unit (2 K-chunks per slot)
@@ -62,14 +62,13 @@ constexpr uint32_t kOffObt = kOffRing + kSlots * kSlotBytes;          // [4][768
 constexpr uint32_t kOffOw = kOffObt + kMaxObjPerTile * 768 * 4;       // [9][256] fp32 output layer + [16] bias
 constexpr uint32_t kOffBias = kOffOw + (9 * 256 + 16) * 4;            // p1_b [256] | p2_b [256]
 constexpr uint32_t kOffFpart = kOffBias + 512 * 4;                    // [128][12] fp32 partial scores of column sub-half 1
-constexpr uint32_t kTcSmemBytes = kOffFpart + 128 * 12 * 4;
+constexpr uint32_t kOffMail = kOffFpart + 128 * 12 * 4;               // [2 parities][4 ranks][128][8] fp32: the team's partial sums (DSMEM)
+constexpr uint32_t kTcSmemBytes = kOffMail + 2 * 4 * 128 * 8 * 4;
 static_assert(kTcSmemBytes <= 227 * 1024 - 768, "tc sampler shared memory budget");
 
 struct TcPcParams {
     PcParams pc;
     const uint8_t *wstream;   // kSlotsPerStep x 16 KiB of bf16 operand images (genpose_b200/weights.py::pack_trunk_tc)
-    float *xch_f;             // [tiles][2 parities][4 ranks][128][9]  partial head sums, all-to-all inside a tile team
-    unsigned *xch_cnt;        // [tiles]                               monotonic counter: partials published
 };
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
@@ -97,12 +96,14 @@ tc_pc_sampler_kernel(TcPcParams tp) {
     float *sOw = reinterpret_cast<float *>(smem + kOffOw);
     float *sBias = reinterpret_cast<float *>(smem + kOffBias);
     float *sFpart = reinterpret_cast<float *>(smem + kOffFpart);
-    __shared__ __align__(8) uint64_t bar_full[kSlots], bar_empty[kSlots], bar_acc_full[2], bar_acc_empty[2], bar_x_ready, bar_a_ready;
+    float *sMail = reinterpret_cast<float *>(smem + kOffMail);
+    __shared__ __align__(8) uint64_t bar_full[kSlots], bar_empty[kSlots], bar_acc_full[2], bar_acc_empty[2], bar_x_ready, bar_a_ready,
+        bar_mail[2];
     __shared__ uint32_t s_tmem_base;
     __shared__ float s_red[4];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int tile = blockIdx.x / kTeam, rank = blockIdx.x % kTeam;   // rank 0 = leader of the tile team
+    const int tile = blockIdx.x / kTeam, rank = (int)cluster_ctarank();   // cluster = tile team (launch: cluster dims 4x1x1); rank 0 leads
     const int n_tiles = gridDim.x / kTeam;
     const int row0 = tile * kTcRows;
     const int obj_lo = row0 / p.K;
@@ -122,6 +123,8 @@ tc_pc_sampler_kernel(TcPcParams tp) {
         }
         mbar_init(&bar_x_ready, 4);
         mbar_init(&bar_a_ready, kTcRowWarps);
+        mbar_init(&bar_mail[0], kTeam * 4);        // one arrival per row warp (0-3) of every rank per use
+        mbar_init(&bar_mail[1], kTeam * 4);
         fence_mbar_init();
     }
     if (warp == kTcRowWarps) tmem_alloc(&s_tmem_base, 512);
@@ -134,9 +137,10 @@ tc_pc_sampler_kernel(TcPcParams tp) {
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
+    cluster_sync_all();          // the team's mailbox barriers are initialised before anyone arrives remotely
     const uint32_t tmem_base = s_tmem_base;
     const uint32_t idesc128 = make_idesc_bf16_f32(128, 128), idesc64 = make_idesc_bf16_f32(128, 64);
-    const bool dbg_cta = p.dbg != nullptr && blockIdx.x == 0;
+    const bool dbg_cta = p.dbg != nullptr && (int)blockIdx.x == p.dbg_cta;
 
     if (warp == kTcRowWarps + 1) {
         // =============================== weight producer ===============================
@@ -285,8 +289,6 @@ tc_pc_sampler_kernel(TcPcParams tp) {
         const uint32_t tm_row = tmem_base + ((uint32_t)(q * 32) << 16);
         const float *obt_row = sObt + (size_t)((valid ? row : p.R - 1) / p.K - obj_lo) * 768;
         const bool dbg = dbg_cta && tid == 0;
-        float *xf = tp.xch_f + (size_t)tile * 2 * kTeam * 128 * 9;       // [parity][rank][row][9]
-        unsigned *cnt_f = tp.xch_cnt + tile;
 
         float x[9];
 #pragma unroll
@@ -449,13 +451,10 @@ tc_pc_sampler_kernel(TcPcParams tp) {
                 ++u;
                 if (ds) ds[8] = clock64();
             }
-            // this thread's 9 partial score components (zero outside the touched heads)
-            float f[9];
-#pragma unroll
-            for (int c = 0; c < 9; ++c) f[c] = ((c / 3) == hA ? oA[c % 3] : 0.f) + (((c / 3) == hB && hB != hA) ? oB[c % 3] : 0.f);
+            // column sub-half 1 hands its partial sums (oA: head hA, oB: head hB) to sub-half 0
             if (cs == 1) {
-#pragma unroll
-                for (int c = 0; c < 9; ++c) sFpart[r * 12 + c] = f[c];
+                sFpart[r * 12 + 0] = oA[0]; sFpart[r * 12 + 1] = oA[1]; sFpart[r * 12 + 2] = oA[2];
+                sFpart[r * 12 + 3] = oB[0]; sFpart[r * 12 + 4] = oB[1]; sFpart[r * 12 + 5] = oB[2];
             }
             named_bar_sync(1, kTcRowWarps * 32);      // sub-half 1 partials are in sFpart; everyone is done with sObt
             if (ds) ds[9] = clock64();
@@ -469,30 +468,47 @@ tc_pc_sampler_kernel(TcPcParams tp) {
                 continue;
             }
 #pragma unroll
-            for (int c = 0; c < 9; ++c) f[c] += sFpart[r * 12 + c];
-
-            // ---- all-to-all inside the tile team: mail this rank's partial sums, gather the other three (fixed rank order) ----
+            for (int c = 0; c < 3; ++c) {
+                oA[c] += sFpart[r * 12 + c];
+                oB[c] += sFpart[r * 12 + 3 + c];
+            }
+            // ---- all-to-all inside the tile team through distributed shared memory: 6 floats per row and rank (its two heads),
+            //      summed by every rank in the same fixed rank order ----
+            float f[9];
             {
-                float *mine = xf + (((size_t)(step & 1) * kTeam + rank) * 128 + r) * 9;
+                const uint32_t par = (uint32_t)step & 1u;
+                float *my_slot = sMail + (((size_t)par * kTeam + rank) * 128 + r) * 8;
+                const uint32_t mail_off = smem_u32(my_slot);
+                const uint32_t bar_off = smem_u32(&bar_mail[par]);
+                *reinterpret_cast<float4 *>(my_slot) = make_float4(oA[0], oA[1], oA[2], oB[0]);
+                *reinterpret_cast<float2 *>(my_slot + 4) = make_float2(oB[1], oB[2]);
 #pragma unroll
-                for (int c = 0; c < 9; ++c) __stcg(mine + c, f[c]);
-                named_bar_sync(2, 128);
-                if (tid == 0) {
-                    red_release_add(cnt_f, 1u);
-                    while (ld_acquire_u32(cnt_f) < (unsigned)(kTeam * (step + 1))) {
-                    }
+                for (uint32_t d = 1; d < (uint32_t)kTeam; ++d) {
+                    const uint32_t dst = ((uint32_t)rank + d) & (uint32_t)(kTeam - 1);
+                    const uint32_t ra = mapa_shared(mail_off, dst);
+                    st_cluster_f4(ra, oA[0], oA[1], oA[2], oB[0]);
+                    st_cluster_f2(ra + 16u, oB[1], oB[2]);
                 }
-                named_bar_sync(2, 128);
+                __syncwarp();                      // the warp's 32 rows are written; one release-arrival per warp and destination
+                if (lane == 0) {                   // one cluster-scope release for the batch, then four cheap arrivals
+                    fence_acq_rel_cluster();
+#pragma unroll
+                    for (uint32_t dst = 0; dst < (uint32_t)kTeam; ++dst) mbar_arrive_cluster_relaxed(mapa_shared(bar_off, dst));
+                }
+                if (ds) ds[11] = clock64();
+                mbar_wait_cluster(&bar_mail[par], ((uint32_t)step >> 1) & 1u);
                 if (ds) ds[10] = clock64();
-                float g4[kTeam][9];
+                const float *mb = sMail + ((size_t)(par * kTeam) * 128 + r) * 8;
 #pragma unroll
-                for (int pr = 0; pr < kTeam; ++pr) {
-                    const float *src = xf + (((size_t)(step & 1) * kTeam + pr) * 128 + r) * 9;
+                for (int c = 0; c < 9; ++c) f[c] = 0.f;
 #pragma unroll
-                    for (int c = 0; c < 9; ++c) g4[pr][c] = __ldcg(src + c);
+                for (int pr = 0; pr < kTeam; ++pr) {     // rank pr covers stacked units [192 pr, 192 pr + 192): heads (192 pr)/256 and (192 pr + 191)/256
+                    const float4 a = *reinterpret_cast<const float4 *>(mb + (size_t)pr * 128 * 8);
+                    const float2 b = *reinterpret_cast<const float2 *>(mb + (size_t)pr * 128 * 8 + 4);
+                    const int ha = (192 * pr) / 256, hb = (192 * pr + 191) / 256;
+                    f[3 * ha + 0] += a.x; f[3 * ha + 1] += a.y; f[3 * ha + 2] += a.z;
+                    if (hb != ha) { f[3 * hb + 0] += a.w; f[3 * hb + 1] += b.x; f[3 * hb + 2] += b.y; }
                 }
-#pragma unroll
-                for (int c = 0; c < 9; ++c) f[c] = ((g4[0][c] + g4[1][c]) + g4[2][c]) + g4[3][c];
             }
             // ---- every rank: score, batch-mean gradient norm (published by the leaders), update — redundantly, bit-identically ----
             float gr[9], n2 = 0.f;
@@ -561,6 +577,7 @@ tc_pc_sampler_kernel(TcPcParams tp) {
     }
     tc_fence_before_sync();
     __syncthreads();
+    cluster_sync_all();          // nobody leaves while a team mate may still write into its mailbox
     if (warp == kTcRowWarps) tmem_dealloc(tmem_base, 512);
 }
 
@@ -574,6 +591,7 @@ extern "C" int gpb_sample_pc_tc_dbg(const float *x0, int R, int K, int num_steps
                                     const void *tc_stream, const float *pts_center, const float *step_noise, uint64_t seed,
                                     const float *time_grid, float *mean_x, float *process, void *workspace, size_t workspace_bytes,
                                     unsigned long long *dbg, void *stream) {
+    const int dbg_cta_sel = (int)(seed >> 56);   // profiling aid: the top byte of the seed selects the recording CTA when dbg != NULL
     GPB_REQUIRE(R >= 0 && K >= 1 && num_steps >= 2, "sample_pc_tc: need R >= 0, K >= 1, num_steps >= 2");
     if (R == 0) return GPB_OK;
     GPB_REQUIRE(x0 && obj_bias && W && tc_stream && pts_center && time_grid && mean_x && workspace, "sample_pc_tc: NULL buffer");
@@ -604,14 +622,29 @@ extern "C" int gpb_sample_pc_tc_dbg(const float *x0, int R, int K, int num_steps
     p.x0 = x0; p.R = R; p.K = K; p.T = num_steps; p.snr = snr;
     p.obj_bias = obj_bias; p.W = W; p.pts_center = pts_center; p.noise = step_noise; p.seed = seed;
     p.ts = time_grid; p.tb_table = w.tb_table; p.partial = w.partial; p.barrier = w.barrier;
-    p.mean_x = mean_x; p.process = process; p.tiles_per_cta = 1; p.dbg = dbg;
+    p.mean_x = mean_x; p.process = process; p.tiles_per_cta = 1; p.dbg = dbg; p.dbg_cta = dbg ? dbg_cta_sel : 0;
     tp.wstream = reinterpret_cast<const uint8_t *>(tc_stream);
-    tp.xch_cnt = reinterpret_cast<unsigned *>(w.xch);
-    tp.xch_f = reinterpret_cast<float *>(reinterpret_cast<char *>(w.xch) + 4096);
-    GPB_CUDA(cudaMemsetAsync(w.xch, 0, 4096, st));
+
     GPB_CUDA(cudaFuncSetAttribute(tc_pc_sampler_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes));
-    void *args[] = {&tp};
-    GPB_CUDA(cudaLaunchCooperativeKernel((void *)tc_pc_sampler_kernel, dim3(grid), dim3(kTcThreads), args, kTcSmemBytes, st));
+    // cluster (4 CTAs = one tile team, DSMEM) + cooperative (grid barrier => all CTAs must be co-resident)
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kTcThreads);
+    cfg.dynamicSmemBytes = kTcSmemBytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attrs[2];
+    attrs[0].id = cudaLaunchAttributeClusterDimension;
+    attrs[0].val.clusterDim.x = kTeam;
+    attrs[0].val.clusterDim.y = 1;
+    attrs[0].val.clusterDim.z = 1;
+    attrs[1].id = cudaLaunchAttributeCooperative;
+    attrs[1].val.cooperative = 1;
+    cfg.attrs = attrs;
+    cfg.numAttrs = 2;
+    int max_clusters = 0;
+    GPB_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, tc_pc_sampler_kernel, &cfg));
+    GPB_REQUIRE(max_clusters >= n_tiles, "sample_pc_tc: only %d co-resident 4-CTA clusters fit, %d needed; split the batch", max_clusters, n_tiles);
+    GPB_CUDA(cudaLaunchKernelEx(&cfg, tc_pc_sampler_kernel, tp));
     g_launches.fetch_add(1);
     return GPB_OK;
 }

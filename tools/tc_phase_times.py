@@ -9,6 +9,7 @@ sys.path.insert(0, ".")
 from genpose_b200 import lib, ops, synth  # noqa: E402
 
 T = int(sys.argv[1]) if len(sys.argv) > 1 else 100
+CTAS = [int(c) for c in sys.argv[2].split(",")] if len(sys.argv) > 2 else [0]
 B, K = 64, 50
 sd = synth.make_state_dict(0, kappa=synth.stable_kappa(T))
 eng = ops.Engine(sd)
@@ -22,12 +23,29 @@ ws = torch.empty(L.gpb_sampler_workspace_bytes(R, T), dtype=torch.uint8, device=
 ts = ops.time_grid(T, "cuda")
 out = torch.empty(R, 9, device="cuda")
 dbg = torch.zeros(2, T, 16, dtype=torch.int64, device="cuda")
-for _ in range(2):
-    lib.check(L.gpb_sample_pc_tc_dbg(x0.data_ptr(), R, K, T, 0.16, ob.data_ptr(), eng.trunk_w.data_ptr(), eng.trunk_tc.data_ptr(),
-                                     center.data_ptr(), 0, 1, ts.data_ptr(), out.data_ptr(), 0, ws.data_ptr(), ws.numel(), dbg.data_ptr(),
-                                     torch.cuda.current_stream().cuda_stream), "dbg")
-torch.cuda.synchronize()
-d = dbg.cpu().numpy().astype(np.float64)
+
+
+def record(cta):
+    for _ in range(2):
+        lib.check(L.gpb_sample_pc_tc_dbg(x0.data_ptr(), R, K, T, 0.16, ob.data_ptr(), eng.trunk_w.data_ptr(), eng.trunk_tc.data_ptr(),
+                                         center.data_ptr(), 0, (cta << 56) | 1, ts.data_ptr(), out.data_ptr(), 0, ws.data_ptr(), ws.numel(),
+                                         dbg.data_ptr(), torch.cuda.current_stream().cuda_stream), "dbg")
+    torch.cuda.synchronize()
+    return dbg.cpu().numpy().astype(np.float64)
+
+
+if len(CTAS) > 1:
+    print("per-CTA comparison (cycles, mean over steps): cta | gather wait | grid wait (publish->release) | heads epi | L1 epi | step")
+    for c in CTAS:
+        dd = record(c)[0, 5:-1]
+        # non-leaders have no ds[14]: use ds[10]->ds[12] for them
+        lead = c % 4 == 0
+        grid = np.mean(dd[:, 12] - (dd[:, 14] if lead else dd[:, 10]))
+        print(f"  cta {c:3d} (rank {c % 4}): send {np.mean(dd[:, 11] - dd[:, 9]):6.0f} wait {np.mean(dd[:, 10] - dd[:, 11]):6.0f}  {'grid' if lead else 'score+grid'} {grid:7.0f}  "
+              f"heads {np.mean(dd[:, 8] - dd[:, 4]):7.0f}  L1 {np.mean(dd[:, 4] - dd[:, 2]):7.0f}  L0 {np.mean(dd[:, 2] - dd[:, 0]):7.0f}  "
+              f"tail {np.mean(dd[:, 13] - dd[:, 12]):7.0f}  step {np.mean(dd[1:, 0] - dd[:-1, 0]):7.0f}")
+    sys.exit(0)
+d = record(CTAS[0])
 row, mma = d[0, 5:-1], d[1, 5:-1]
 # stamps of CTA 0 (team leader of tile 0), row thread 0 — see tc_sampler.cu
 seq = [("wait layer-0 accumulator", 0, 1), ("epilogue layer 0 (2 units)", 1, 2), ("wait layer-1 accumulator", 2, 3),
