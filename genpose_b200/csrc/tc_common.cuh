@@ -65,6 +65,18 @@ __device__ __forceinline__ void st_cluster_f2(uint32_t cluster_addr, float a, fl
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar_addr) {   // release at cluster scope: prior DSMEM stores visible
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar_addr) : "memory");
 }
+// asynchronous DSMEM store that completes `bytes` on the DESTINATION CTA's mbarrier (transaction count): producer/consumer
+// hand-off without any cluster-scope fence
+__device__ __forceinline__ void st_async_f4(uint32_t cluster_addr, float a, float b, float c, float d, uint32_t cluster_bar_addr) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(cluster_addr),
+                 "f"(a), "f"(b), "f"(c), "f"(d), "r"(cluster_bar_addr)
+                 : "memory");
+}
+__device__ __forceinline__ void st_async_f2(uint32_t cluster_addr, float a, float b, uint32_t cluster_bar_addr) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f32 [%0], {%1, %2}, [%3];" ::"r"(cluster_addr), "f"(a),
+                 "f"(b), "r"(cluster_bar_addr)
+                 : "memory");
+}
 __device__ __forceinline__ void fence_acq_rel_cluster() { asm volatile("fence.acq_rel.cluster;" ::: "memory"); }
 __device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_bar_addr) {   // pair with ONE fence_acq_rel_cluster() before a batch
     asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar_addr) : "memory");

@@ -123,8 +123,8 @@ tc_pc_sampler_kernel(TcPcParams tp) {
         }
         mbar_init(&bar_x_ready, 4);
         mbar_init(&bar_a_ready, kTcRowWarps);
-        mbar_init(&bar_mail[0], kTeam * 4);        // one arrival per row warp (0-3) of every rank per use
-        mbar_init(&bar_mail[1], kTeam * 4);
+        mbar_init(&bar_mail[0], 1);                // one local arrive.expect_tx per use; the peers' st.async complete the bytes
+        mbar_init(&bar_mail[1], 1);
         fence_mbar_init();
     }
     if (warp == kTcRowWarps) tmem_alloc(&s_tmem_base, 512);
@@ -480,20 +480,15 @@ tc_pc_sampler_kernel(TcPcParams tp) {
                 float *my_slot = sMail + (((size_t)par * kTeam + rank) * 128 + r) * 8;
                 const uint32_t mail_off = smem_u32(my_slot);
                 const uint32_t bar_off = smem_u32(&bar_mail[par]);
-                *reinterpret_cast<float4 *>(my_slot) = make_float4(oA[0], oA[1], oA[2], oB[0]);
+                if (tid == 0) mbar_arrive_expect_tx(&bar_mail[par], (uint32_t)(kTeam - 1) * 128u * 24u);   // 3 peers x 128 rows x 24 B
+                *reinterpret_cast<float4 *>(my_slot) = make_float4(oA[0], oA[1], oA[2], oB[0]);   // own slot: read back by this same thread
                 *reinterpret_cast<float2 *>(my_slot + 4) = make_float2(oB[1], oB[2]);
 #pragma unroll
                 for (uint32_t d = 1; d < (uint32_t)kTeam; ++d) {
                     const uint32_t dst = ((uint32_t)rank + d) & (uint32_t)(kTeam - 1);
-                    const uint32_t ra = mapa_shared(mail_off, dst);
-                    st_cluster_f4(ra, oA[0], oA[1], oA[2], oB[0]);
-                    st_cluster_f2(ra + 16u, oB[1], oB[2]);
-                }
-                __syncwarp();                      // the warp's 32 rows are written; one release-arrival per warp and destination
-                if (lane == 0) {                   // one cluster-scope release for the batch, then four cheap arrivals
-                    fence_acq_rel_cluster();
-#pragma unroll
-                    for (uint32_t dst = 0; dst < (uint32_t)kTeam; ++dst) mbar_arrive_cluster_relaxed(mapa_shared(bar_off, dst));
+                    const uint32_t ra = mapa_shared(mail_off, dst), rb = mapa_shared(bar_off, dst);
+                    st_async_f4(ra, oA[0], oA[1], oA[2], oB[0], rb);
+                    st_async_f2(ra + 16u, oB[1], oB[2], rb);
                 }
                 if (ds) ds[11] = clock64();
                 mbar_wait_cluster(&bar_mail[par], ((uint32_t)step >> 1) & 1u);
