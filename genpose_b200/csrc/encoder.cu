@@ -566,8 +566,21 @@ extern "C" size_t gpb_encoder_weights_floats(void) { return kEncoderFloats; }
 
 extern "C" size_t gpb_encode_workspace_bytes(int B) { return B > 0 ? carve(nullptr, B).bytes : 0; }
 
-extern "C" int gpb_encode(const float *pts, int B, const float *enc_w, float *pts_feat, void *workspace,
-                          size_t workspace_bytes, int *fps_idx1, int *fps_idx2, int *fps_idx3, void *stream) {
+namespace gpb {
+int launch_sa3_tc(const float *xyz_in, const float *new_xyz, const float *U, const float *consts, const void *wstream, int scale,
+                  float *feat_out, int B, cudaStream_t st);   // sa_tc.cu
+constexpr size_t kEncTcConstBytes = 8192;                     // 2 x 992 floats, padded
+constexpr size_t kEncTcScaleBytes = (size_t)22 * 16384;
+int launch_sa2_tc(const float *xyz_in, const float *new_xyz, const float *U, const float *consts, const void *wimg, int scale,
+                  float *feat_out, int B, cudaStream_t st);   // sa_tc.cu
+// level-2 block, appended: [consts s0 2 KiB | image s0 48 KiB | consts s1 2 KiB | image s1 72 KiB]
+constexpr size_t kEncTcL2Off = kEncTcConstBytes + 2 * kEncTcScaleBytes;
+constexpr size_t kEncTcL2Const = 2048, kEncTcL2Img0 = (64 * 64 + 64 * 128) * 4, kEncTcL2Img1 = (64 * 96 + 96 * 128) * 4;
+constexpr size_t kEncTcBytes = kEncTcL2Off + 2 * kEncTcL2Const + kEncTcL2Img0 + kEncTcL2Img1;
+}  // namespace gpb
+
+static int encode_impl(const float *pts, int B, const float *enc_w, const uint8_t *enc_tc, float *pts_feat, void *workspace,
+                       size_t workspace_bytes, int *fps_idx1, int *fps_idx2, int *fps_idx3, void *stream) {
     GPB_REQUIRE(B >= 0, "encode: B < 0");
     if (B == 0) return GPB_OK;
     GPB_REQUIRE(pts && enc_w && pts_feat && workspace, "encode: NULL buffer");
@@ -593,16 +606,29 @@ extern "C" int gpb_encode(const float *pts, int B, const float *enc_w, float *pt
         constexpr MlpSpec m0 = enc_spec(1, 0), m1 = enc_spec(1, 1);
         if ((rc = launch_point_gemm<96, 64, 4, 8, 128>(w.feat1, 96, enc_w + spec_offset(1, 0) + off_wf(m0), w.u[0], (size_t)B * 512, st))) return rc;
         if ((rc = launch_point_gemm<96, 64, 4, 8, 128>(w.feat1, 96, enc_w + spec_offset(1, 1) + off_wf(m1), w.u[1], (size_t)B * 512, st))) return rc;
-        if ((rc = launch_sa<1, 0>(w.nx1, w.nx2, w.u[0], enc_w, w.feat2, B, st))) return rc;
-        if ((rc = launch_sa<1, 1>(w.nx1, w.nx2, w.u[1], enc_w, w.feat2, B, st))) return rc;
+        if (enc_tc) {
+            const uint8_t *l2 = enc_tc + kEncTcL2Off;
+            if ((rc = launch_sa2_tc(w.nx1, w.nx2, w.u[0], reinterpret_cast<const float *>(l2), l2 + kEncTcL2Const, 0, w.feat2, B, st))) return rc;
+            l2 += kEncTcL2Const + kEncTcL2Img0;
+            if ((rc = launch_sa2_tc(w.nx1, w.nx2, w.u[1], reinterpret_cast<const float *>(l2), l2 + kEncTcL2Const, 1, w.feat2, B, st))) return rc;
+        } else {
+            if ((rc = launch_sa<1, 0>(w.nx1, w.nx2, w.u[0], enc_w, w.feat2, B, st))) return rc;
+            if ((rc = launch_sa<1, 1>(w.nx1, w.nx2, w.u[1], enc_w, w.feat2, B, st))) return rc;
+        }
     }
     // level 3
     {
         constexpr MlpSpec m0 = enc_spec(2, 0), m1 = enc_spec(2, 1);
         if ((rc = launch_point_gemm<256, 128, 8, 4, 256>(w.feat2, 256, enc_w + spec_offset(2, 0) + off_wf(m0), w.u[0], (size_t)B * 256, st))) return rc;
         if ((rc = launch_point_gemm<256, 128, 8, 4, 256>(w.feat2, 256, enc_w + spec_offset(2, 1) + off_wf(m1), w.u[1], (size_t)B * 256, st))) return rc;
-        if ((rc = launch_sa<2, 0>(w.nx2, w.nx3, w.u[0], enc_w, w.feat3, B, st))) return rc;
-        if ((rc = launch_sa<2, 1>(w.nx2, w.nx3, w.u[1], enc_w, w.feat3, B, st))) return rc;
+        if (enc_tc) {
+            const float *consts = reinterpret_cast<const float *>(enc_tc);
+            if ((rc = launch_sa3_tc(w.nx2, w.nx3, w.u[0], consts, enc_tc + kEncTcConstBytes, 0, w.feat3, B, st))) return rc;
+            if ((rc = launch_sa3_tc(w.nx2, w.nx3, w.u[1], consts + 992, enc_tc + kEncTcConstBytes + kEncTcScaleBytes, 1, w.feat3, B, st))) return rc;
+        } else {
+            if ((rc = launch_sa<2, 0>(w.nx2, w.nx3, w.u[0], enc_w, w.feat3, B, st))) return rc;
+            if ((rc = launch_sa<2, 1>(w.nx2, w.nx3, w.u[1], enc_w, w.feat3, B, st))) return rc;
+        }
     }
     // level 4 (GroupAll)
     GPB_CUDA(cudaMemsetAsync(pts_feat, 0, (size_t)B * 1024 * sizeof(float), st));
@@ -613,4 +639,19 @@ extern "C" int gpb_encode(const float *pts, int B, const float *enc_w, float *pt
     groupall_kernel<1><<<dim3(4, B), kGaThreads, GaSmem<1>::bytes, st>>>(w.nx3, w.feat3, enc_w + spec_offset(3, 1), pts_feat);
     GPB_LAUNCHED();
     return GPB_OK;
+}
+
+extern "C" int gpb_encode(const float *pts, int B, const float *enc_w, float *pts_feat, void *workspace,
+                          size_t workspace_bytes, int *fps_idx1, int *fps_idx2, int *fps_idx3, void *stream) {
+    return encode_impl(pts, B, enc_w, nullptr, pts_feat, workspace, workspace_bytes, fps_idx1, fps_idx2, fps_idx3, stream);
+}
+
+extern "C" size_t gpb_encoder_tc_bytes(void) { return kEncTcBytes; }
+
+extern "C" int gpb_encode_tc(const float *pts, int B, const float *enc_w, const void *enc_tc, float *pts_feat, void *workspace,
+                             size_t workspace_bytes, int *fps_idx1, int *fps_idx2, int *fps_idx3, void *stream) {
+    GPB_REQUIRE(enc_tc != nullptr, "encode_tc: NULL tensor-core weight image");
+    GPB_REQUIRE((reinterpret_cast<uintptr_t>(enc_tc) & 127) == 0, "encode_tc: weight image must be 128-byte aligned");
+    return encode_impl(pts, B, enc_w, reinterpret_cast<const uint8_t *>(enc_tc), pts_feat, workspace, workspace_bytes, fps_idx1, fps_idx2,
+                       fps_idx3, stream);
 }

@@ -211,35 +211,40 @@ __device__ __forceinline__ void trunk_tile(const TrunkSmem &s, const float *__re
 // ---------------------------------------------------------------------------------------------------
 // object bias: obj_bias[b, n] = sum_k pts_feat[b,k] * A_pts[k][n] + a_b[n]; 8 objects per CTA
 // ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 object_bias_kernel(const float *__restrict__ pts_feat, int B, const float *__restrict__ W, float *__restrict__ out) {
+    // grid (ceil(B/8), 3): 8 objects x 256 of the 768 columns per CTA; the K = 1024 reduction is split over 4 thread groups
+    // and combined in fixed order (deterministic)
     __shared__ float sf[8][1024];
-    const int b0 = blockIdx.x * 8, tid = threadIdx.x;
-    for (int i = tid; i < 8 * 1024; i += 256) {
+    float (*sred)[8][256] = reinterpret_cast<float (*)[8][256]>(&sf[0][0]);      // aliases sf after the main loop
+    const int b0 = blockIdx.x * 8, tid = threadIdx.x, col = tid & 255, kg = tid >> 8;
+    for (int i = tid; i < 8 * 1024; i += 1024) {
         const int bi = b0 + (i >> 10);
         sf[i >> 10][i & 1023] = bi < B ? pts_feat[(size_t)bi * 1024 + (i & 1023)] : 0.f;
     }
     __syncthreads();
-    float acc[8][3];
+    float acc[8];
 #pragma unroll
-    for (int o = 0; o < 8; ++o) acc[o][0] = acc[o][1] = acc[o][2] = 0.f;
-    const float *w = W + TL::a_pts + tid;
-    for (int k = 0; k < 1024; ++k) {
-        const float w0 = __ldg(w + (size_t)k * 768), w1 = __ldg(w + (size_t)k * 768 + 256), w2 = __ldg(w + (size_t)k * 768 + 512);
+    for (int o = 0; o < 8; ++o) acc[o] = 0.f;
+    const int n = blockIdx.y * 256 + col;
+    const float *w = W + TL::a_pts + n;
+#pragma unroll 8
+    for (int k = kg * 256; k < kg * 256 + 256; ++k) {
+        const float wv = __ldg(w + (size_t)k * 768);
 #pragma unroll
-        for (int o = 0; o < 8; ++o) {
-            const float f = sf[o][k];
-            acc[o][0] = fmaf(f, w0, acc[o][0]);
-            acc[o][1] = fmaf(f, w1, acc[o][1]);
-            acc[o][2] = fmaf(f, w2, acc[o][2]);
-        }
+        for (int o = 0; o < 8; ++o) acc[o] = fmaf(sf[o][k], wv, acc[o]);
     }
+    __syncthreads();
+    if (kg > 0) {
 #pragma unroll
-    for (int o = 0; o < 8; ++o) {
-        if (b0 + o < B) {
+        for (int o = 0; o < 8; ++o) sred[kg - 1][o][col] = acc[o];
+    }
+    __syncthreads();
+    if (kg == 0) {
+        const float bias = W[TL::a_b + n];
 #pragma unroll
-            for (int j = 0; j < 3; ++j) out[(size_t)(b0 + o) * 768 + tid + 256 * j] = acc[o][j] + W[TL::a_b + tid + 256 * j];
-        }
+        for (int o = 0; o < 8; ++o)
+            if (b0 + o < B) out[(size_t)(b0 + o) * 768 + n] = ((acc[o] + sred[0][o][col]) + sred[1][o][col]) + sred[2][o][col] + bias;
     }
 }
 
@@ -735,7 +740,7 @@ extern "C" int gpb_object_bias(const float *pts_feat, int B, const float *W, flo
     GPB_REQUIRE(B >= 0, "object_bias: B < 0");
     if (B == 0) return GPB_OK;
     GPB_REQUIRE(pts_feat && W && obj_bias, "object_bias: NULL buffer");
-    object_bias_kernel<<<(B + 7) / 8, 256, 0, (cudaStream_t)stream>>>(pts_feat, B, W, obj_bias);
+    object_bias_kernel<<<dim3((B + 7) / 8, 3), 1024, 0, (cudaStream_t)stream>>>(pts_feat, B, W, obj_bias);
     GPB_LAUNCHED();
     return GPB_OK;
 }

@@ -28,6 +28,8 @@ SIGNATURES = {
     "gpb_sampler_workspace_bytes": (_sz, [_i, _i]),
     "gpb_sample_pc": (_i, [_vp, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _u64, _vp, _vp, _vp, _vp, _sz, _vp]),
     "gpb_trunk_tc_stream_bytes": (_sz, []),
+    "gpb_encoder_tc_bytes": (_sz, []),
+    "gpb_encode_tc": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _sz, _vp, _vp, _vp, _vp]),
     "gpb_sample_pc_tc": (_i, [_vp, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _u64, _vp, _vp, _vp, _vp, _sz, _vp]),
     "gpb_sample_pc_tc_dbg": (_i, [_vp, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _u64, _vp, _vp, _vp, _vp, _sz, _vp, _vp]),
     "gpb_sample_ode": (_i, [_vp, _i, _i, _f, _f, _f, _i, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),

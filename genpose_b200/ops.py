@@ -91,6 +91,10 @@ class Engine:
         if tc.numel() * 2 != L.gpb_trunk_tc_stream_bytes():
             raise lib.GenPoseB200Error("tensor-core weight stream size disagrees with the library")
         self.trunk_tc = tc.to(self.device)
+        etc = weights.pack_encoder_tc(state_dict)
+        if etc.numel() != L.gpb_encoder_tc_bytes():
+            raise lib.GenPoseB200Error("tensor-core encoder image size disagrees with the library")
+        self.enc_tc = etc.to(self.device)
         self._ws: Dict[Tuple[str, int], torch.Tensor] = {}
 
     def _workspace(self, kind: str, nbytes: int) -> torch.Tensor:
@@ -101,8 +105,11 @@ class Engine:
         return ws
 
     # ---- a7: encoder ------------------------------------------------------------------------------
-    def encode(self, pts: torch.Tensor, return_fps: bool = False):
-        """Pointnet2ClsMSG.forward: pts [B,1024,3] (raw camera frame) -> pts_feat [B,1024]."""
+    def encode(self, pts: torch.Tensor, return_fps: bool = False, precision: str = "auto"):
+        """Pointnet2ClsMSG.forward: pts [B,1024,3] (raw camera frame) -> pts_feat [B,1024].
+        precision 'fp32' = every level on FFMA; 'bf16x3' / 'auto' = set-abstraction level 3 on tcgen05 (bf16x3 split)."""
+        if precision not in ("auto", "bf16x3", "fp32"):
+            raise lib.GenPoseB200Error(f"encode: unknown precision {precision!r}")
         B, N, C = pts.shape
         if N != arch.NUM_POINTS or C != 3:
             raise lib.GenPoseB200Error(f"encode: expected [B,1024,3], got {tuple(pts.shape)}")
@@ -112,8 +119,12 @@ class Engine:
         fps = [None, None, None]
         if return_fps:
             fps = [torch.empty(B, n, dtype=torch.int32, device=self.device) for n in (512, 256, 128)]
-        lib.check(L.gpb_encode(_chk(pts, torch.float32, "pts"), B, self.enc_w.data_ptr(), feat.data_ptr(), ws.data_ptr(),
-                               ws.numel(), *[0 if f is None else f.data_ptr() for f in fps], _stream()), "encode")
+        tail = (feat.data_ptr(), ws.data_ptr(), ws.numel(), *[0 if f is None else f.data_ptr() for f in fps], _stream())
+        if precision == "fp32":
+            lib.check(L.gpb_encode(_chk(pts, torch.float32, "pts"), B, self.enc_w.data_ptr(), *tail), "encode")
+        else:
+            lib.check(L.gpb_encode_tc(_chk(pts, torch.float32, "pts"), B, self.enc_w.data_ptr(), self.enc_tc.data_ptr(), *tail),
+                      "encode_tc")
         return (feat, fps) if return_fps else feat
 
     def object_bias(self, pts_feat: torch.Tensor) -> torch.Tensor:

@@ -93,7 +93,7 @@ class GFObjectPose:
     # ---- modes ------------------------------------------------------------------------------------------
     def extract_pts_feature(self, data):
         """posenet.py:71-91 — uses data['pts'] (raw camera frame)."""
-        return self._eng().encode(data["pts"].float().contiguous())
+        return self._eng().encode(data["pts"].float().contiguous(), precision=self.precision)
 
     def _step_noise(self, num_steps, rows, device):
         if self.noise_mode == "torch":

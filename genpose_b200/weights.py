@@ -131,6 +131,59 @@ def umma_image(w_bf16: torch.Tensor, variant: int = 0) -> torch.Tensor:
     return x.reshape(rows // 8, 8, K // 8, 8).permute(0, 2, 1, 3).contiguous().reshape(-1)
 
 
+def pack_encoder_tc(sd: Dict[str, torch.Tensor], prefix: str = "pts_encoder") -> torch.Tensor:
+    """Tensor-core operand image of set-abstraction level 3 (csrc/sa_tc.cu), uint8:
+       [8192 B: per scale  wx[3][128] | b1[128] | b2[224] | b3[256]  fp32]
+       then per scale 22 slots of 16 KiB: 8 x (W2 K-step: hi [2][224][8] bf16 | lo)  and  14 x (W3 K-step: hi [2][256][8] | lo)
+    with hi = rn_bf16(w), lo = rn_bf16(w - hi); 196 -> 224 zero padded (rows of W2 / columns of W3);
+    followed by the level-2 block (see below)."""
+    consts = torch.zeros(2048, dtype=torch.float32)
+    streams = []
+    for s in range(2):
+        base = f"{prefix}.SA_modules.2.mlps.{s}"
+        w1, b1 = _fold(sd, f"{base}.layer0")
+        w2, b2 = _fold(sd, f"{base}.layer1")
+        w3, b3 = _fold(sd, f"{base}.layer2")
+        assert w1.shape == (128, 259) and w2.shape == (196, 128) and w3.shape == (256, 196)
+        c = consts[s * 992:(s + 1) * 992]
+        c[0:384] = w1[:, :3].t().reshape(-1).float()
+        c[384:512] = b1.float()
+        c[512:512 + 196] = b2.float()
+        c[736:992] = b3.float()
+        pw2 = torch.zeros(224, 128, dtype=torch.float32)
+        pw2[:196] = w2.float()
+        pw3 = torch.zeros(256, 224, dtype=torch.float32)
+        pw3[:, :196] = w3.float()
+        slots = torch.zeros(22, 8192, dtype=torch.int16)
+        h2, l2 = split_bf16(pw2)
+        for k in range(8):
+            slots[k, 0:3584] = umma_image(h2[:, 16 * k:16 * k + 16].contiguous())
+            slots[k, 3584:7168] = umma_image(l2[:, 16 * k:16 * k + 16].contiguous())
+        h3, l3 = split_bf16(pw3)
+        for k in range(14):
+            slots[8 + k, 0:4096] = umma_image(h3[:, 16 * k:16 * k + 16].contiguous())
+            slots[8 + k, 4096:8192] = umma_image(l3[:, 16 * k:16 * k + 16].contiguous())
+        streams.append(slots.reshape(-1).view(torch.uint8))
+    # level 2 (resident image of csrc/sa_tc.cu::sa2_tc_kernel): per scale
+    #   [512 fp32: wx[3][64] | b1[64] | b2[C2] | b3[128]] [W2 hi [8][C2][8] | W2 lo | W3 hi [C2/8][128][8] | W3 lo]
+    for s, c2 in ((0, 64), (1, 96)):
+        base = f"{prefix}.SA_modules.1.mlps.{s}"
+        w1, b1 = _fold(sd, f"{base}.layer0")
+        w2, b2 = _fold(sd, f"{base}.layer1")
+        w3, b3 = _fold(sd, f"{base}.layer2")
+        assert w1.shape == (64, 99) and w2.shape == (c2, 64) and w3.shape == (128, c2)
+        c = torch.zeros(512, dtype=torch.float32)
+        c[0:192] = w1[:, :3].t().reshape(-1).float()
+        c[192:256] = b1.float()
+        c[256:256 + c2] = b2.float()
+        c[256 + c2:384 + c2] = b3.float()
+        h2, l2 = split_bf16(w2.float())
+        h3, l3 = split_bf16(w3.float())
+        img = torch.cat([umma_image(h2), umma_image(l2), umma_image(h3), umma_image(l3)])
+        streams += [c.view(torch.uint8), img.view(torch.uint8)]
+    return torch.cat([consts.view(torch.uint8)] + streams).contiguous()
+
+
 def pack_trunk_tc(sd: Dict[str, torch.Tensor], prefix: str = "pose_score_net") -> torch.Tensor:
     """The weight stream of tc_pc_sampler_kernel: 65 slots of 16 KiB (int16 words), each a pair `hi image | lo image` of
     K-major no-swizzle operand blocks [K/8][rows][8]:

@@ -114,18 +114,23 @@ def test_fused_path_matches_reference_golden(ops, name):
 # ------------------------------------------------------------------------------------------------------
 # fused path against the oracle on fresh seeds / awkward sizes
 # ------------------------------------------------------------------------------------------------------
-def test_encoder_levels_against_oracle(ops):
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
+def test_encoder_levels_against_oracle(ops, precision):
     seed, B = 21, 5
     sd = synth.make_state_dict(seed, kappa=-0.3)
     clouds = synth.make_clouds(B, seed)
     clouds[1] = clouds[1, 0]                              # degenerate: every point identical
     trace = O.encoder_levels(sd, torch.from_numpy(clouds))
     eng = ops.Engine(sd)
-    feat, fps = eng.encode(_dev(clouds), return_fps=True)
+    feat, fps = eng.encode(_dev(clouds), return_fps=True, precision=precision)
     for l in range(3):
         assert np.array_equal(fps[l].cpu().numpy(), trace["fps_idx"][l].numpy())
     ref = trace["pts_feat"].numpy()
     np.testing.assert_allclose(feat.cpu().numpy(), ref, rtol=1e-4, atol=1e-4 * max(1.0, np.abs(ref).max()))
+    if precision == "bf16x3":      # tensor-core level 3 against the FFMA level 3: the bf16x3 split keeps ~fp32 accuracy
+        f32 = eng.encode(_dev(clouds), precision="fp32")
+        err = (feat - f32).abs().max().item() / max(1.0, f32.abs().max().item())
+        assert err < 5e-5, err
 
 
 @pytest.mark.parametrize("B,K,T", [(1, 1, 10), (3, 7, 40), (7, 50, 30), (2, 30, 500)])
