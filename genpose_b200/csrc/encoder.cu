@@ -509,10 +509,13 @@ groupall_kernel(const float *__restrict__ xyz3,    // [B,128,3]  absolute coordi
 // ---------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------
+size_t ga_tc_scratch_bytes(int B);   // ga_tc.cu
+
 struct EncWorkspace {
     float *nx1, *nx2, *nx3;   // [B,512,3] [B,256,3] [B,128,3]
     float *feat1, *feat2, *feat3;   // [B,512,96] [B,256,256] [B,128,512]
     float *u[2];   // scratch for U (max over levels): [B,512,64] / [B,256,128]
+    uint8_t *ga;   // tensor-core GroupAll operand images (ga_tc.cu)
     size_t bytes;
 };
 
@@ -532,6 +535,7 @@ static EncWorkspace carve(void *base, int B) {
     w.feat3 = take((size_t)B * 128 * 512);
     w.u[0] = take((size_t)B * 512 * 64);   // >= B*256*128
     w.u[1] = take((size_t)B * 512 * 64);
+    w.ga = reinterpret_cast<uint8_t *>(take(ga_tc_scratch_bytes(B) / sizeof(float)));
     w.bytes = off;
     return w;
 }
@@ -568,7 +572,10 @@ extern "C" size_t gpb_encode_workspace_bytes(int B) { return B > 0 ? carve(nullp
 
 namespace gpb {
 int launch_sa3_tc(const float *xyz_in, const float *new_xyz, const float *U, const float *consts, const void *wstream, int scale,
-                  float *feat_out, int B, cudaStream_t st);   // sa_tc.cu
+                  float *feat_out, uint8_t *a0_hi, uint8_t *a0_lo, int B, cudaStream_t st);   // sa_tc.cu
+size_t ga_tc_blob_bytes();                                                                    // ga_tc.cu
+size_t ga_tc_scratch_bytes(int B);
+int launch_groupall_tc(const uint8_t *blob, uint8_t *scratch, const float *xyz3, float *pts_feat, int B, cudaStream_t st);
 constexpr size_t kEncTcConstBytes = 8192;                     // 2 x 992 floats, padded
 constexpr size_t kEncTcScaleBytes = (size_t)22 * 16384;
 int launch_sa2_tc(const float *xyz_in, const float *new_xyz, const float *U, const float *consts, const void *wimg, int scale,
@@ -576,7 +583,7 @@ int launch_sa2_tc(const float *xyz_in, const float *new_xyz, const float *U, con
 // level-2 block, appended: [consts s0 2 KiB | image s0 48 KiB | consts s1 2 KiB | image s1 72 KiB]
 constexpr size_t kEncTcL2Off = kEncTcConstBytes + 2 * kEncTcScaleBytes;
 constexpr size_t kEncTcL2Const = 2048, kEncTcL2Img0 = (64 * 64 + 64 * 128) * 4, kEncTcL2Img1 = (64 * 96 + 96 * 128) * 4;
-constexpr size_t kEncTcBytes = kEncTcL2Off + 2 * kEncTcL2Const + kEncTcL2Img0 + kEncTcL2Img1;
+constexpr size_t kEncTcGaOff = kEncTcL2Off + 2 * kEncTcL2Const + kEncTcL2Img0 + kEncTcL2Img1;   // GroupAll block (ga_tc.cu) last
 }  // namespace gpb
 
 static int encode_impl(const float *pts, int B, const float *enc_w, const uint8_t *enc_tc, float *pts_feat, void *workspace,
@@ -623,14 +630,18 @@ static int encode_impl(const float *pts, int B, const float *enc_w, const uint8_
         if ((rc = launch_point_gemm<256, 128, 8, 4, 256>(w.feat2, 256, enc_w + spec_offset(2, 1) + off_wf(m1), w.u[1], (size_t)B * 256, st))) return rc;
         if (enc_tc) {
             const float *consts = reinterpret_cast<const float *>(enc_tc);
-            if ((rc = launch_sa3_tc(w.nx2, w.nx3, w.u[0], consts, enc_tc + kEncTcConstBytes, 0, w.feat3, B, st))) return rc;
-            if ((rc = launch_sa3_tc(w.nx2, w.nx3, w.u[1], consts + 992, enc_tc + kEncTcConstBytes + kEncTcScaleBytes, 1, w.feat3, B, st))) return rc;
+            uint8_t *a0_hi = w.ga, *a0_lo = w.ga + (size_t)B * 131072;
+            if ((rc = launch_sa3_tc(w.nx2, w.nx3, w.u[0], consts, enc_tc + kEncTcConstBytes, 0, w.feat3, a0_hi, a0_lo, B, st))) return rc;
+            if ((rc = launch_sa3_tc(w.nx2, w.nx3, w.u[1], consts + 992, enc_tc + kEncTcConstBytes + kEncTcScaleBytes, 1, w.feat3, a0_hi, a0_lo, B,
+                                    st)))
+                return rc;
         } else {
             if ((rc = launch_sa<2, 0>(w.nx2, w.nx3, w.u[0], enc_w, w.feat3, B, st))) return rc;
             if ((rc = launch_sa<2, 1>(w.nx2, w.nx3, w.u[1], enc_w, w.feat3, B, st))) return rc;
         }
     }
     // level 4 (GroupAll)
+    if (enc_tc) return launch_groupall_tc(enc_tc + kEncTcGaOff, w.ga, w.nx3, pts_feat, B, st);
     GPB_CUDA(cudaMemsetAsync(pts_feat, 0, (size_t)B * 1024 * sizeof(float), st));
     GPB_CUDA(cudaFuncSetAttribute(groupall_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GaSmem<0>::bytes));
     GPB_CUDA(cudaFuncSetAttribute(groupall_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GaSmem<1>::bytes));
@@ -646,7 +657,7 @@ extern "C" int gpb_encode(const float *pts, int B, const float *enc_w, float *pt
     return encode_impl(pts, B, enc_w, nullptr, pts_feat, workspace, workspace_bytes, fps_idx1, fps_idx2, fps_idx3, stream);
 }
 
-extern "C" size_t gpb_encoder_tc_bytes(void) { return kEncTcBytes; }
+extern "C" size_t gpb_encoder_tc_bytes(void) { return kEncTcGaOff + ga_tc_blob_bytes(); }
 
 extern "C" int gpb_encode_tc(const float *pts, int B, const float *enc_w, const void *enc_tc, float *pts_feat, void *workspace,
                              size_t workspace_bytes, int *fps_idx1, int *fps_idx2, int *fps_idx3, void *stream) {

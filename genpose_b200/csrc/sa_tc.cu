@@ -53,7 +53,8 @@ sa3_tc_kernel(const float *__restrict__ xyz_in,    // [B,256,3]   level-2 centre
               const float *__restrict__ U,         // [B,256,128] W1_feat . f
               const float *__restrict__ consts,    // kSaConstFloats
               const uint8_t *__restrict__ wstream, // kSaSlotsPerTile x 16 KiB
-              float radius, int ch_off, float *__restrict__ feat_out /* [B,128,512] */) {
+              float radius, int ch_off, float *__restrict__ feat_out /* [B,128,512] */,
+              uint8_t *__restrict__ a0_hi, uint8_t *__restrict__ a0_lo /* GroupAll A-operand images [B][64][128][8] bf16, or null */) {
     constexpr int TC = kSaRows / NS;
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t *sRing = smem + kSaOffRing;
@@ -287,6 +288,20 @@ sa3_tc_kernel(const float *__restrict__ xyz_in,    // [B,256,3]   level-2 centre
         for (int i = tid; i < TC * 256; i += kSaRowWarps * 32) {
             const int tc = i >> 8, c = i & 255;
             feat_out[((size_t)b * kSaNPoint + c_base + tc) * kSaCTotal + ch_off + c] = __int_as_float(sOut[i]);
+        }
+        if (a0_hi) {   // the same values as the bf16 hi/lo A operand of GroupAll layer 1 (ga_tc.cu): [K/8][128 rows][8]
+            for (int i = tid; i < TC * 32; i += kSaRowWarps * 32) {
+                const int tc = i >> 5, g = i & 31;
+                const float4 v0 = *reinterpret_cast<const float4 *>(sOut + tc * 256 + g * 8), v1 = *reinterpret_cast<const float4 *>(sOut + tc * 256 + g * 8 + 4);
+                uint32_t hi[4], lo[4];
+                split_bf16x2(v0.x, v0.y, hi[0], lo[0]);
+                split_bf16x2(v0.z, v0.w, hi[1], lo[1]);
+                split_bf16x2(v1.x, v1.y, hi[2], lo[2]);
+                split_bf16x2(v1.z, v1.w, hi[3], lo[3]);
+                const size_t off = (size_t)b * 131072 + (size_t)((ch_off >> 3) + g) * 2048 + (size_t)(c_base + tc) * 16;
+                *reinterpret_cast<uint4 *>(a0_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                *reinterpret_cast<uint4 *>(a0_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            }
         }
     }
     tc_fence_before_sync();
@@ -569,15 +584,17 @@ int launch_sa2_tc(const float *xyz_in, const float *new_xyz, const float *U, con
 }
 
 int launch_sa3_tc(const float *xyz_in, const float *new_xyz, const float *U, const float *consts, const void *wstream, int scale,
-                  float *feat_out, int B, cudaStream_t st) {
+                  float *feat_out, uint8_t *a0_hi, uint8_t *a0_lo, int B, cudaStream_t st) {
     if (scale == 0) {
         GPB_CUDA(cudaFuncSetAttribute(sa3_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSaSmemBytes));
         sa3_tc_kernel<16><<<dim3(kSaNPoint / 8, B), kSaThreads, kSaSmemBytes, st>>>(xyz_in, new_xyz, U, consts,
-                                                                                   reinterpret_cast<const uint8_t *>(wstream), 0.08f, 0, feat_out);
+                                                                                   reinterpret_cast<const uint8_t *>(wstream), 0.08f, 0, feat_out,
+                                                                                   a0_hi, a0_lo);
     } else {
         GPB_CUDA(cudaFuncSetAttribute(sa3_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSaSmemBytes));
         sa3_tc_kernel<32><<<dim3(kSaNPoint / 4, B), kSaThreads, kSaSmemBytes, st>>>(xyz_in, new_xyz, U, consts,
-                                                                                   reinterpret_cast<const uint8_t *>(wstream), 0.16f, 256, feat_out);
+                                                                                   reinterpret_cast<const uint8_t *>(wstream), 0.16f, 256, feat_out,
+                                                                                   a0_hi, a0_lo);
     }
     GPB_LAUNCHED();
     return GPB_OK;

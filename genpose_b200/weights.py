@@ -181,6 +181,36 @@ def pack_encoder_tc(sd: Dict[str, torch.Tensor], prefix: str = "pts_encoder") ->
         h3, l3 = split_bf16(w3.float())
         img = torch.cat([umma_image(h2), umma_image(l2), umma_image(h3), umma_image(l3)])
         streams += [c.view(torch.uint8), img.view(torch.uint8)]
+    # GroupAll (csrc/ga_tc.cu): [16 KiB fp32: per scale wx[3][256] | b1[256] | b2[384] | b3[512]] then 8 KiB slots
+    # (one 128-row tile of W, one K=16 step: hi [2][128][8] | lo), ordered layer-major, scale, tile, K-step.
+    gconst = torch.zeros(4096, dtype=torch.float32)
+    folded = []
+    for s, c2 in ((0, 256), (1, 384)):
+        base = f"{prefix}.SA_modules.3.mlps.{s}"
+        w1, b1 = _fold(sd, f"{base}.layer0")
+        w2, b2 = _fold(sd, f"{base}.layer1")
+        w3, b3 = _fold(sd, f"{base}.layer2")
+        assert w1.shape == (256, 515) and w2.shape == (c2, 256) and w3.shape == (512, c2)
+        c = gconst[s * 1920:(s + 1) * 1920]
+        c[0:768] = w1[:, :3].t().reshape(-1).float()
+        c[768:1024] = b1.float()
+        c[1024:1024 + c2] = b2.float()
+        c[1408:1920] = b3.float()
+        folded.append((w1[:, 3:].float().contiguous(), w2.float(), w3.float()))
+
+    def tile_slots(w):                      # w [N, K] -> per 128-row tile, per K-step: hi | lo  (int16 words)
+        out = []
+        hi, lo = split_bf16(w)
+        for n0 in range(0, w.shape[0], 128):
+            for k in range(0, w.shape[1], 16):
+                out += [umma_image(hi[n0:n0 + 128, k:k + 16].contiguous()), umma_image(lo[n0:n0 + 128, k:k + 16].contiguous())]
+        return out
+
+    gslots = []
+    for layer in range(3):
+        for s in range(2):
+            gslots += tile_slots(folded[s][layer])
+    streams += [gconst.view(torch.uint8), torch.cat(gslots).view(torch.uint8)]
     return torch.cat([consts.view(torch.uint8)] + streams).contiguous()
 
 
