@@ -100,7 +100,7 @@ tc_pc_sampler_kernel(TcPcParams tp) {
     __shared__ __align__(8) uint64_t bar_full[kSlots], bar_empty[kSlots], bar_acc_full[2], bar_acc_empty[2], bar_x_ready, bar_a_ready,
         bar_mail[2];
     __shared__ uint32_t s_tmem_base;
-    __shared__ float s_red[4];
+    __shared__ float s_red[8];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int tile = blockIdx.x / kTeam, rank = (int)cluster_ctarank();   // cluster = tile team (launch: cluster dims 4x1x1); rank 0 leads
@@ -206,7 +206,11 @@ tc_pc_sampler_kernel(TcPcParams tp) {
             // ---- units with K = 256: layer 1 (P2: two 128-column units) and this rank's head slice (128 + 64 columns) ----
             for (int unit = 0; unit < 4; ++unit) {
                 if (ds) tq = clock64();
-                if (unit == 0 || unit == 2) {      // h1 / pf complete in tensor memory
+                // Units 0 and 2 are the first consumers of a freshly written A operand (h1 / pf).  The row warps publish it in
+                // two halves (K columns [0,128) as soon as the first accumulator unit is converted, [128,256) after the second),
+                // so the first 8 K-steps are issued while the second half is still in the epilogue.
+                const bool split = unit == 0 || unit == 2;
+                if (split) {
                     mbar_wait(&bar_a_ready, ar & 1u);
                     ++ar;
                 }
@@ -221,29 +225,49 @@ tc_pc_sampler_kernel(TcPcParams tp) {
                 if (ds) { w_acc += clock64() - tq; tq = clock64(); }
                 const uint32_t d = tmem_base + kColD + b * 128u;
                 const bool small = unit == 3;                      // the 64-column unit: 2 K-chunks per slot
-                const int n_slots = small ? 4 : 8;
-                wait_slots(n_slots);
-                if (ds) { w_full += clock64() - tq; tq = clock64(); }
-                const uint32_t s_first = it % kSlots;
-                if (elect_one_sync()) {       // one issue group per unit: 48 MMAs, slot releases, accumulator-ready
-                    if (!small) {
-#pragma unroll
-                        for (int kc = 0; kc < 8; ++kc) {
-                            uint32_t s = s_first + (uint32_t)kc;
-                            s = s >= (uint32_t)kSlots ? s - (uint32_t)kSlots : s;
-                            const uint32_t sb = ring + s * kSlotBytes;
-#pragma unroll
-                            for (int j = 0; j < 2; ++j) {
-                                const uint64_t b_hi = make_smem_desc(sb + 2u * j * kLboB, kLboB, kSbo);
-                                const uint64_t b_lo = make_smem_desc(sb + 8192u + 2u * j * kLboB, kLboB, kSbo);
-                                const uint32_t ac = (uint32_t)kc * 16u + 8u * j;      // K index / 2
-                                umma_bf16_ts(d, t_ahi + ac, b_hi, idesc128, (kc | j) != 0);
-                                umma_bf16_ts(d, t_alo + ac, b_hi, idesc128, true);
-                                umma_bf16_ts(d, t_ahi + ac, b_lo, idesc128, true);
-                            }
-                            umma_commit(&bar_empty[s]);
+                if (!small) {
+                    // 8 slots = 16 K-steps, issued as one group (unit 1) or two groups of 4 slots (units 0, 2)
+                    const int groups = split ? 2 : 1, per = split ? 4 : 8;
+                    for (int g = 0; g < groups; ++g) {
+                        if (g == 1) {
+                            if (ds) tq = clock64();
+                            mbar_wait(&bar_a_ready, ar & 1u);
+                            ++ar;
+                            if (ds) { w_a += clock64() - tq; tq = clock64(); }
                         }
-                    } else {
+                        wait_slots(per);
+                        if (ds) { w_full += clock64() - tq; tq = clock64(); }
+                        const uint32_t s_first = it % kSlots;
+                        const int kc0 = g * per;
+                        if (elect_one_sync()) {
+#pragma unroll 4
+                            for (int kk = 0; kk < per; ++kk) {
+                                const int kc = kc0 + kk;
+                                uint32_t s = s_first + (uint32_t)kk;
+                                s = s >= (uint32_t)kSlots ? s - (uint32_t)kSlots : s;
+                                const uint32_t sb = ring + s * kSlotBytes;
+#pragma unroll
+                                for (int j = 0; j < 2; ++j) {
+                                    const uint64_t b_hi = make_smem_desc(sb + 2u * j * kLboB, kLboB, kSbo);
+                                    const uint64_t b_lo = make_smem_desc(sb + 8192u + 2u * j * kLboB, kLboB, kSbo);
+                                    const uint32_t ac = (uint32_t)kc * 16u + 8u * j;      // K index / 2
+                                    umma_bf16_ts(d, t_ahi + ac, b_hi, idesc128, (kc | j) != 0);
+                                    umma_bf16_ts(d, t_alo + ac, b_hi, idesc128, true);
+                                    umma_bf16_ts(d, t_ahi + ac, b_lo, idesc128, true);
+                                }
+                                umma_commit(&bar_empty[s]);
+                            }
+                            if (g == groups - 1) umma_commit(&bar_acc_full[b]);
+                        }
+                        __syncwarp();
+                        if (ds) { w_issue += clock64() - tq; tq = clock64(); }
+                        it += (uint32_t)per;
+                    }
+                } else {
+                    wait_slots(4);
+                    if (ds) { w_full += clock64() - tq; tq = clock64(); }
+                    const uint32_t s_first = it % kSlots;
+                    if (elect_one_sync()) {
 #pragma unroll
                         for (int sl = 0; sl < 4; ++sl) {
                             uint32_t s = s_first + (uint32_t)sl;
@@ -263,12 +287,12 @@ tc_pc_sampler_kernel(TcPcParams tp) {
                             }
                             umma_commit(&bar_empty[s]);
                         }
+                        umma_commit(&bar_acc_full[b]);
                     }
-                    umma_commit(&bar_acc_full[b]);
+                    __syncwarp();
+                    if (ds) w_issue += clock64() - tq;
+                    it += 4u;
                 }
-                __syncwarp();
-                if (ds) w_issue += clock64() - tq;
-                it += (uint32_t)n_slots;
                 ++u;
             }
             if (ds) {
@@ -387,6 +411,11 @@ tc_pc_sampler_kernel(TcPcParams tp) {
                         uint32_t v[32];
                         tmem_ld32(tm_row + kColD + b * 128u + (uint32_t)cs * 64u, v);
                         tmem_ld_wait();
+                        // first half of the new A operand (K columns [0,128)) is in tensor memory: let the MMA warp start on it
+                        tmem_st_wait();
+                        tc_fence_before_sync();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&bar_a_ready);
                         relu_split32(v, bias + 128, hi, lo);
                         tmem_ld32(tm_row + kColD + b * 128u + (uint32_t)cs * 64u + 32u, v);
                         tmem_ld_wait();
@@ -512,6 +541,10 @@ tc_pc_sampler_kernel(TcPcParams tp) {
                 gr[c] = (f[c] + sOw[9 * 256 + c]) / stdv;
                 n2 = fmaf(gr[c], gr[c], n2);
             }
+            // ---- batch-mean gradient norm: leaders publish the tile partial + one RED on the counter; thread 0 of every CTA polls
+            //      the counter, then every warp fetches the partials.  (Measured alternatives, both slower: per-warp partials as
+            //      tagged 64-bit words polled by every warp, 8.2 k cycles instead of 2.8 k — the pollers starve the writers;
+            //      tagged tile sums polled by one warp per CTA, 4.4 k.)
             bar_target += (unsigned)n_tiles;
             if (leader) {
                 const float wsum = warp_sum(valid ? sqrtf(n2) : 0.f);
