@@ -575,6 +575,8 @@ int launch_sa3_tc(const float *xyz_in, const float *new_xyz, const float *U, con
                   float *feat_out, uint8_t *a0_hi, uint8_t *a0_lo, int B, cudaStream_t st);   // sa_tc.cu
 size_t ga_tc_blob_bytes();                                                                    // ga_tc.cu
 size_t ga_tc_scratch_bytes(int B);
+int launch_sa1_tc(const float *pts, const float *new_xyz, const float *consts, const void *wimg, float *feat_out, int B, cudaStream_t st);
+constexpr size_t kEncTcL1Bytes = 2048 + (32 * 32 + 32 * 64) * 4;   // level 1 scale 1: [consts 2 KiB | image 12 KiB], after the GroupAll block
 int launch_groupall_tc(const uint8_t *blob, uint8_t *scratch, const float *xyz3, float *pts_feat, int B, cudaStream_t st);
 constexpr size_t kEncTcConstBytes = 8192;                     // 2 x 992 floats, padded
 constexpr size_t kEncTcScaleBytes = (size_t)22 * 16384;
@@ -606,7 +608,12 @@ static int encode_impl(const float *pts, int B, const float *enc_w, const uint8_
 
     // level 1 (no input features)
     if ((rc = launch_sa<0, 0>(pts, w.nx1, nullptr, enc_w, w.feat1, B, st))) return rc;
-    if ((rc = launch_sa<0, 1>(pts, w.nx1, nullptr, enc_w, w.feat1, B, st))) return rc;
+    if (enc_tc) {
+        const uint8_t *l1 = enc_tc + kEncTcGaOff + ga_tc_blob_bytes();
+        if ((rc = launch_sa1_tc(pts, w.nx1, reinterpret_cast<const float *>(l1), l1 + 2048, w.feat1, B, st))) return rc;
+    } else {
+        if ((rc = launch_sa<0, 1>(pts, w.nx1, nullptr, enc_w, w.feat1, B, st))) return rc;
+    }
 
     // level 2: U = W1_feat . feat1 per source point, then the grouped part
     {
@@ -657,7 +664,7 @@ extern "C" int gpb_encode(const float *pts, int B, const float *enc_w, float *pt
     return encode_impl(pts, B, enc_w, nullptr, pts_feat, workspace, workspace_bytes, fps_idx1, fps_idx2, fps_idx3, stream);
 }
 
-extern "C" size_t gpb_encoder_tc_bytes(void) { return kEncTcGaOff + ga_tc_blob_bytes(); }
+extern "C" size_t gpb_encoder_tc_bytes(void) { return kEncTcGaOff + ga_tc_blob_bytes() + kEncTcL1Bytes; }
 
 extern "C" int gpb_encode_tc(const float *pts, int B, const float *enc_w, const void *enc_tc, float *pts_feat, void *workspace,
                              size_t workspace_bytes, int *fps_idx1, int *fps_idx2, int *fps_idx3, void *stream) {

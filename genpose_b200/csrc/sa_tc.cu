@@ -310,61 +310,78 @@ sa3_tc_kernel(const float *__restrict__ xyz_in,    // [B,256,3]   level-2 centre
 }
 
 // ===================================================================================================================
-// Set-abstraction level 2 (512 -> 256 centres, MLP [99,64,C2,128], C2 = 64 / 96) on the tensor cores, PERSISTENT:
-// the whole bf16 hi/lo operand image of W2 and W3 (48 / 72 KiB) stays in shared memory, two CTAs per SM (256 TMEM
-// columns each) loop over 128-row tiles so that one CTA's row phases overlap the other's MMAs.
+// Small-width set abstraction (level 1 scale 1: MLP [3,32,32,64]; level 2: [99,64,64|96,128]) on the tensor cores,
+// PERSISTENT: the whole bf16 hi/lo operand image of W2 and W3 (<= 72 KiB) stays in shared memory, two CTAs per SM
+// (256 TMEM columns each) loop over 128-row tiles so that one CTA's row phases overlap the other's MMAs.
 //   TMEM (per CTA): D [0,128) | A_hi [128,176) | A_lo [192,240)
-//   weight image:   W2 hi [8][C2][8] | W2 lo | W3 hi [C2/8][128][8] | W3 lo      (bf16, canonical K-major)
-//   fp32 constants: wx[3][64] | b1[64] | b2[C2] | b3[128]   (padded to 512 floats)
+//   weight image:   W2 hi [C1/8][C2][8] | W2 lo | W3 hi [C2/8][C3][8] | W3 lo      (bf16, canonical K-major)
+//   fp32 constants: wx[3][C1] | b1[C1] | b2[C2] | b3[C3]   (padded to 512 floats)
 // ===================================================================================================================
 constexpr int kS2Threads = (kSaRowWarps + 1) * 32;
-constexpr int kS2NIn = 512, kS2NPoint = 256, kS2CTotal = 256, kS2C1 = 64, kS2C3 = 128;
 constexpr int kS2ConstFloats = 512;
 constexpr uint32_t kS2ColD = 0, kS2ColAhi = 128, kS2ColAlo = 192;
-__host__ __device__ constexpr uint32_t s2_w_bytes(int c2) { return (uint32_t)(kS2C1 * c2 + c2 * kS2C3) * 4u; }
 
-template <int NS, int C2>
-struct S2Smem {
+template <int NS_, int C1_, int C2_, int C3_, int NIN_, int NPOINT_, int CTOTAL_, bool HAS_U_>
+struct SmallCfg {
+    static constexpr int NS = NS_, C1 = C1_, C2 = C2_, C3 = C3_, NIN = NIN_, NPOINT = NPOINT_, CTOTAL = CTOTAL_;
+    static constexpr bool HAS_U = HAS_U_;
     static constexpr int TC = kSaRows / NS;
+    static constexpr int H = kSaRowWarps / TC;        // warps sharing one centre's ball query (1 or 2)
+    static constexpr uint32_t w_bytes = (uint32_t)(C1 * C2 + C2 * C3) * 4u;
     static constexpr uint32_t off_w = 0;
-    static constexpr uint32_t off_const = off_w + s2_w_bytes(C2);
-    static constexpr uint32_t off_xyz = off_const + kS2ConstFloats * 4;         // [2][512*3]
-    static constexpr uint32_t off_ctr = off_xyz + 2 * kS2NIn * 12;              // [2][32]
-    static constexpr uint32_t off_nbr = off_ctr + 2 * 32 * 4;
-    static constexpr uint32_t off_out = off_nbr + kSaRows * 4;                  // [TC][128]
-    static constexpr uint32_t bytes = off_out + TC * 128 * 4;
+    static constexpr uint32_t off_const = off_w + w_bytes;
+    static constexpr uint32_t off_xyz = off_const + kS2ConstFloats * 4;          // [2][NIN*3]
+    static constexpr uint32_t off_ctr = off_xyz + 2 * NIN * 12;                  // [2][32]
+    static constexpr uint32_t off_hit = off_ctr + 2 * 32 * 4;                    // [TC][H][NS] candidate lists
+    static constexpr uint32_t off_cnt = off_hit + kSaRows * H * 4;               // [TC][H]
+    static constexpr uint32_t off_out = off_cnt + 16 * 4;                        // [TC][C3]
+    static constexpr uint32_t bytes = off_out + TC * C3 * 4;
+    static_assert(H == 1 || H == 2, "ball query split");
+    static_assert(C1 % 32 == 0 && C2 % 32 == 0 && C3 % 64 == 0 && C1 <= 96 && C2 <= 96 && C3 <= 128, "widths");
 };
 
-template <int NS, int C2>
+template <int NCOLS>
+__device__ __forceinline__ void tmem_st_cols(uint32_t taddr, const uint32_t *r) {
+    static_assert(NCOLS == 8 || NCOLS == 16, "store width");
+    if constexpr (NCOLS == 16) {
+        tmem_st16(taddr, r);
+    } else {
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]),
+                     "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+                     : "memory");
+    }
+}
+
+template <class C>
 __global__ void __maxnreg__(80)
-sa2_tc_kernel(const float *__restrict__ xyz_in,    // [B,512,3]   level-1 centres
-              const float *__restrict__ new_xyz,   // [B,256,3]   level-2 centres
-              const float *__restrict__ U,         // [B,512,64]  W1_feat . f
-              const float *__restrict__ consts,    // kS2ConstFloats
-              const uint8_t *__restrict__ wimg,    // s2_w_bytes(C2)
-              float radius, int ch_off, int n_tiles, float *__restrict__ feat_out /* [B,256,256] */) {
-    using S = S2Smem<NS, C2>;
-    constexpr int TC = S::TC;
-    constexpr int kTilesPerObj = kS2NPoint / TC;
-    constexpr uint32_t kLboW2 = C2 * 16, kLboW3 = 2048;
-    constexpr uint32_t kW2Bytes = kS2C1 * C2 * 2, kW3Bytes = C2 * kS2C3 * 2;
+sa_small_tc_kernel(const float *__restrict__ xyz_in,    // [B,NIN,3]      source points
+                   const float *__restrict__ new_xyz,   // [B,NPOINT,3]   centres
+                   const float *__restrict__ U,         // [B,NIN,C1]     W1_feat . f   (HAS_U) or nullptr
+                   const float *__restrict__ consts,    // kS2ConstFloats
+                   const uint8_t *__restrict__ wimg,    // C::w_bytes
+                   float radius, int ch_off, int n_tiles, float *__restrict__ feat_out /* [B,NPOINT,CTOTAL] */) {
+    constexpr int NS = C::NS, TC = C::TC, H = C::H, C1 = C::C1, C2 = C::C2, C3 = C::C3, NIN = C::NIN;
+    constexpr int kTilesPerObj = C::NPOINT / TC;
+    constexpr uint32_t kLboW2 = C2 * 16, kLboW3 = C3 * 16;
+    constexpr uint32_t kW2Bytes = C1 * C2 * 2, kW3Bytes = C2 * C3 * 2;
     extern __shared__ __align__(1024) uint8_t smem[];
-    float *sConst = reinterpret_cast<float *>(smem + S::off_const);
-    float *sXyz = reinterpret_cast<float *>(smem + S::off_xyz);
-    float *sCtr = reinterpret_cast<float *>(smem + S::off_ctr);
-    int *sNbr = reinterpret_cast<int *>(smem + S::off_nbr);
-    int *sOut = reinterpret_cast<int *>(smem + S::off_out);
+    float *sConst = reinterpret_cast<float *>(smem + C::off_const);
+    float *sXyz = reinterpret_cast<float *>(smem + C::off_xyz);
+    float *sCtr = reinterpret_cast<float *>(smem + C::off_ctr);
+    int *sHit = reinterpret_cast<int *>(smem + C::off_hit);
+    int *sCnt = reinterpret_cast<int *>(smem + C::off_cnt);
+    int *sOut = reinterpret_cast<int *>(smem + C::off_out);
     __shared__ __align__(8) uint64_t bar_w, bar_in[2], bar_acc_full, bar_a_ready;
     __shared__ uint32_t s_tmem_base;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const float *sWx = sConst, *sB1 = sConst + 192, *sB2 = sConst + 256, *sB3 = sConst + 256 + C2;
+    const float *sWx = sConst, *sB1 = sConst + 3 * C1, *sB2 = sConst + 4 * C1, *sB3 = sConst + 4 * C1 + C2;
 
-    auto prefetch = [&](int tile, int buf) {   // one thread: the object's level-1 centres and this tile's level-2 centres
+    auto prefetch = [&](int tile, int buf) {   // one thread: the object's source points and this tile's centres
         const int b = tile / kTilesPerObj, c_base = (tile % kTilesPerObj) * TC;
-        mbar_arrive_expect_tx(&bar_in[buf], (uint32_t)(kS2NIn * 12 + TC * 12));
-        bulk_g2s(sXyz + buf * kS2NIn * 3, xyz_in + (size_t)b * kS2NIn * 3, kS2NIn * 12, &bar_in[buf]);
-        bulk_g2s(sCtr + buf * 32, new_xyz + ((size_t)b * kS2NPoint + c_base) * 3, TC * 12, &bar_in[buf]);
+        mbar_arrive_expect_tx(&bar_in[buf], (uint32_t)(NIN * 12 + TC * 12));
+        bulk_g2s(sXyz + buf * NIN * 3, xyz_in + (size_t)b * NIN * 3, NIN * 12, &bar_in[buf]);
+        bulk_g2s(sCtr + buf * 32, new_xyz + ((size_t)b * C::NPOINT + c_base) * 3, TC * 12, &bar_in[buf]);
     };
 
     if (tid == 0) {
@@ -374,8 +391,8 @@ sa2_tc_kernel(const float *__restrict__ xyz_in,    // [B,512,3]   level-1 centre
         mbar_init(&bar_acc_full, 1);
         mbar_init(&bar_a_ready, kSaRowWarps);
         fence_mbar_init();
-        mbar_arrive_expect_tx(&bar_w, s2_w_bytes(C2) + kS2ConstFloats * 4);
-        bulk_g2s(smem + S::off_w, wimg, s2_w_bytes(C2), &bar_w);
+        mbar_arrive_expect_tx(&bar_w, C::w_bytes + kS2ConstFloats * 4);
+        bulk_g2s(smem + C::off_w, wimg, C::w_bytes, &bar_w);
         bulk_g2s(sConst, consts, kS2ConstFloats * 4, &bar_w);
         if ((int)blockIdx.x < n_tiles) prefetch(blockIdx.x, 0);
     }
@@ -387,10 +404,10 @@ sa2_tc_kernel(const float *__restrict__ xyz_in,    // [B,512,3]   level-1 centre
 
     if (warp == kSaRowWarps) {
         // =============================== MMA issuer ===============================
-        const uint32_t wbase = smem_u32(smem + S::off_w);
+        const uint32_t wbase = smem_u32(smem + C::off_w);
         const uint32_t w2_hi = wbase, w2_lo = wbase + kW2Bytes, w3_hi = wbase + 2 * kW2Bytes, w3_lo = w3_hi + kW3Bytes;
         const uint32_t t_ahi = tmem_base + kS2ColAhi, t_alo = tmem_base + kS2ColAlo, d = tmem_base + kS2ColD;
-        const uint32_t idesc2 = make_idesc_bf16_f32(128, C2), idesc3 = make_idesc_bf16_f32(128, kS2C3);
+        const uint32_t idesc2 = make_idesc_bf16_f32(128, C2), idesc3 = make_idesc_bf16_f32(128, C3);
         mbar_wait(&bar_w, 0);
         int it = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
@@ -400,7 +417,7 @@ sa2_tc_kernel(const float *__restrict__ xyz_in,    // [B,512,3]   level-1 centre
                 // the other side-input buffer was last read in the previous tile, which every row warp has left
                 if (tile + (int)gridDim.x < n_tiles) prefetch(tile + gridDim.x, (it + 1) & 1);
 #pragma unroll
-                for (int k = 0; k < kS2C1 / 16; ++k) {
+                for (int k = 0; k < C1 / 16; ++k) {
                     const uint64_t b_hi = make_smem_desc(w2_hi + (uint32_t)k * 2u * kLboW2, kLboW2, kSaSbo);
                     const uint64_t b_lo = make_smem_desc(w2_lo + (uint32_t)k * 2u * kLboW2, kLboW2, kSaSbo);
                     umma_bf16_ts(d, t_ahi + 8u * k, b_hi, idesc2, k != 0);
@@ -437,44 +454,62 @@ sa2_tc_kernel(const float *__restrict__ xyz_in,    // [B,512,3]   level-1 centre
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
             const int b = tile / kTilesPerObj, c_base = (tile % kTilesPerObj) * TC;
             const int buf = it & 1;
-            const float *xyz = sXyz + buf * kS2NIn * 3, *ctr = sCtr + buf * 32;
+            const float *xyz = sXyz + buf * NIN * 3, *ctr = sCtr + buf * 32;
             mbar_wait(&bar_in[buf], (uint32_t)(it >> 1) & 1u);
-            // ---- ball query: one warp per centre, ascending k, pad with the first hit ----
-            for (int tc = warp; tc < TC; tc += kSaRowWarps) {
+            // ---- ball query: H warps per centre, each over its ascending slice of the source points; the row threads below
+            //      concatenate the slices in order (== the first NS hits in ascending index) and pad with the first hit ----
+            {
+                const int tc = warp / H, h = warp % H;
                 const float cx = ctr[tc * 3 + 0], cy = ctr[tc * 3 + 1], cz = ctr[tc * 3 + 2];
-                int cnt = 0, first = 0;
-                for (int base = 0; base < kS2NIn && cnt < NS; base += 32) {
+                int *hit = sHit + (tc * H + h) * NS;
+                int cnt = 0;
+                for (int base = h * (NIN / H); base < (h + 1) * (NIN / H) && cnt < NS; base += 32) {
                     const int k = base + lane;
-                    const bool hit = dist2_ref(cx, cy, cz, xyz[k * 3], xyz[k * 3 + 1], xyz[k * 3 + 2]) < r2;
-                    const unsigned mask = __ballot_sync(0xffffffffu, hit);
-                    if (mask) {
-                        if (cnt == 0) first = base + __ffs(mask) - 1;
-                        const int slot = cnt + __popc(mask & ((1u << lane) - 1u));
-                        if (hit && slot < NS) sNbr[tc * NS + slot] = k;
-                        cnt += __popc(mask);
-                    }
+                    const bool in = dist2_ref(cx, cy, cz, xyz[k * 3], xyz[k * 3 + 1], xyz[k * 3 + 2]) < r2;
+                    const unsigned mask = __ballot_sync(0xffffffffu, in);
+                    const int slot = cnt + __popc(mask & ((1u << lane) - 1u));
+                    if (in && slot < NS) hit[slot] = k;
+                    cnt += __popc(mask);
                 }
-                cnt = cnt < NS ? cnt : NS;
-                for (int sl = cnt + lane; sl < NS; sl += 32) sNbr[tc * NS + sl] = first;
+                if (lane == 0) sCnt[tc * H + h] = cnt < NS ? cnt : NS;
             }
             asm volatile("bar.sync 1, 256;" ::: "memory");
-            // ---- layer 1 -> A operand: row r, channels [cs*32, +32) ----
+            // ---- layer 1 -> A operand: row r, channels [cs*C1/2, +C1/2) ----
             {
-                const int j = sNbr[r], tc = r / NS;
+                constexpr int CH = C1 / 2;
+                const int tc = r / NS, sl = r % NS;
+                int j;
+                {
+                    const int c0 = sCnt[tc * H];
+                    const int *h0 = sHit + (tc * H) * NS;
+                    if constexpr (H == 1) {
+                        j = sl < c0 ? h0[sl] : h0[0];          // the centre itself is a source point: c0 >= 1
+                    } else {
+                        const int c1 = sCnt[tc * H + 1];
+                        const int *h1 = h0 + NS;
+                        const int first = c0 > 0 ? h0[0] : h1[0];
+                        j = sl < c0 ? h0[sl] : (sl - c0 < c1 ? h1[sl - c0] : first);
+                    }
+                }
                 const float dx = xyz[j * 3 + 0] - ctr[tc * 3 + 0];
                 const float dy = xyz[j * 3 + 1] - ctr[tc * 3 + 1];
                 const float dz = xyz[j * 3 + 2] - ctr[tc * 3 + 2];
-                const float4 *urow = reinterpret_cast<const float4 *>(U + ((size_t)b * kS2NIn + j) * kS2C1 + cs * 32);
-                float4 u[8];
+                float4 u[CH / 4];
+                if constexpr (C::HAS_U) {
+                    const float4 *urow = reinterpret_cast<const float4 *>(U + ((size_t)b * NIN + j) * C1 + cs * CH);
 #pragma unroll
-                for (int c4 = 0; c4 < 8; ++c4) u[c4] = __ldg(urow + c4);
-                uint32_t hi[16], lo[16];
+                    for (int c4 = 0; c4 < CH / 4; ++c4) u[c4] = __ldg(urow + c4);
+                } else {
 #pragma unroll
-                for (int c4 = 0; c4 < 8; ++c4) {
-                    const int c = cs * 32 + c4 * 4;
+                    for (int c4 = 0; c4 < CH / 4; ++c4) u[c4] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                uint32_t hi[CH / 2], lo[CH / 2];
+#pragma unroll
+                for (int c4 = 0; c4 < CH / 4; ++c4) {
+                    const int c = cs * CH + c4 * 4;
                     float4 v = u[c4];
-                    const float4 w0 = *reinterpret_cast<const float4 *>(sWx + c), w1 = *reinterpret_cast<const float4 *>(sWx + 64 + c),
-                                 w2 = *reinterpret_cast<const float4 *>(sWx + 128 + c), bb = *reinterpret_cast<const float4 *>(sB1 + c);
+                    const float4 w0 = *reinterpret_cast<const float4 *>(sWx + c), w1 = *reinterpret_cast<const float4 *>(sWx + C1 + c),
+                                 w2 = *reinterpret_cast<const float4 *>(sWx + 2 * C1 + c), bb = *reinterpret_cast<const float4 *>(sB1 + c);
                     v.x = fmaxf(fmaf(dz, w2.x, fmaf(dy, w1.x, fmaf(dx, w0.x, v.x + bb.x))), 0.f);
                     v.y = fmaxf(fmaf(dz, w2.y, fmaf(dy, w1.y, fmaf(dx, w0.y, v.y + bb.y))), 0.f);
                     v.z = fmaxf(fmaf(dz, w2.z, fmaf(dy, w1.z, fmaf(dx, w0.z, v.z + bb.z))), 0.f);
@@ -482,8 +517,8 @@ sa2_tc_kernel(const float *__restrict__ xyz_in,    // [B,512,3]   level-1 centre
                     split_bf16x2(v.x, v.y, hi[2 * c4], lo[2 * c4]);
                     split_bf16x2(v.z, v.w, hi[2 * c4 + 1], lo[2 * c4 + 1]);
                 }
-                tmem_st16(tm_row + kS2ColAhi + (uint32_t)(cs * 16), hi);
-                tmem_st16(tm_row + kS2ColAlo + (uint32_t)(cs * 16), lo);
+                tmem_st_cols<CH / 2>(tm_row + kS2ColAhi + (uint32_t)(cs * (CH / 2)), hi);
+                tmem_st_cols<CH / 2>(tm_row + kS2ColAlo + (uint32_t)(cs * (CH / 2)), lo);
                 tmem_st_wait();
                 tc_fence_before_sync();
                 __syncwarp();
@@ -513,13 +548,13 @@ sa2_tc_kernel(const float *__restrict__ xyz_in,    // [B,512,3]   level-1 centre
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&bar_a_ready);
             }
-            // ---- epilogue layer 3: relu(acc + b3), max over the NS rows of a centre; columns [cs*64, +64) ----
+            // ---- epilogue layer 3: relu(acc + b3), max over the NS rows of a centre; columns [cs*C3/2, +C3/2) ----
             {
                 mbar_wait(&bar_acc_full, 1);
                 tc_fence_after_sync();
 #pragma unroll 1
-                for (int blk = 0; blk < 2; ++blk) {
-                    const int c0 = cs * 64 + blk * 32;
+                for (int blk = 0; blk < C3 / 64; ++blk) {
+                    const int c0 = cs * (C3 / 2) + blk * 32;
                     uint32_t v[32];
                     tmem_ld32(tm_row + kS2ColD + (uint32_t)c0, v);
                     tmem_ld_wait();
@@ -531,7 +566,7 @@ sa2_tc_kernel(const float *__restrict__ xyz_in,    // [B,512,3]   level-1 centre
                             const int m = __reduce_max_sync(0xffffffffu, __float_as_int(h));
                             keep = lane == jj ? m : keep;
                         }
-                        sOut[q * 128 + c0 + lane] = keep;
+                        sOut[q * C3 + c0 + lane] = keep;
                     } else {
                         int keep0 = 0, keep1 = 0;
 #pragma unroll
@@ -542,18 +577,18 @@ sa2_tc_kernel(const float *__restrict__ xyz_in,    // [B,512,3]   level-1 centre
                             keep0 = lane == jj ? m0 : keep0;
                             keep1 = lane == jj ? m1 : keep1;
                         }
-                        sOut[(q * 2) * 128 + c0 + lane] = keep0;
-                        sOut[(q * 2 + 1) * 128 + c0 + lane] = keep1;
+                        sOut[(q * 2) * C3 + c0 + lane] = keep0;
+                        sOut[(q * 2 + 1) * C3 + c0 + lane] = keep1;
                     }
                 }
                 tc_fence_before_sync();
             }
             asm volatile("bar.sync 1, 256;" ::: "memory");
-            for (int i = tid; i < TC * 128; i += kSaRowWarps * 32) {
-                const int tc = i >> 7, c = i & 127;
-                feat_out[((size_t)b * kS2NPoint + c_base + tc) * kS2CTotal + ch_off + c] = __int_as_float(sOut[i]);
+            for (int i = tid; i < TC * C3; i += kSaRowWarps * 32) {
+                const int tc = i / C3, c = i % C3;
+                feat_out[((size_t)b * C::NPOINT + c_base + tc) * C::CTOTAL + ch_off + c] = __int_as_float(sOut[i]);
             }
-            asm volatile("bar.sync 1, 256;" ::: "memory");     // sOut / sNbr are reused by the next tile
+            asm volatile("bar.sync 1, 256;" ::: "memory");     // sOut / sHit are reused by the next tile
         }
     }
     tc_fence_before_sync();
@@ -561,26 +596,33 @@ sa2_tc_kernel(const float *__restrict__ xyz_in,    // [B,512,3]   level-1 centre
     if (warp == kSaRowWarps) tmem_dealloc(tmem_base, 256);
 }
 
-template <int NS, int C2>
-static int launch_sa2_one(const float *xyz_in, const float *new_xyz, const float *U, const float *consts, const void *wimg, float radius,
-                          int ch_off, float *feat_out, int B, int sms, cudaStream_t st) {
-    using S = S2Smem<NS, C2>;
-    GPB_CUDA(cudaFuncSetAttribute(sa2_tc_kernel<NS, C2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::bytes));
-    const int n_tiles = B * (kS2NPoint / S::TC);
+template <class C>
+static int launch_sa_small(const float *xyz_in, const float *new_xyz, const float *U, const float *consts, const void *wimg, float radius,
+                           int ch_off, float *feat_out, int B, cudaStream_t st) {
+    int dev = 0, sms = 0;
+    GPB_CUDA(cudaGetDevice(&dev));
+    GPB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    GPB_CUDA(cudaFuncSetAttribute(sa_small_tc_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::bytes));
+    const int n_tiles = B * (C::NPOINT / C::TC);
     const int grid = n_tiles < 2 * sms ? n_tiles : 2 * sms;
-    sa2_tc_kernel<NS, C2><<<grid, kS2Threads, S::bytes, st>>>(xyz_in, new_xyz, U, consts, reinterpret_cast<const uint8_t *>(wimg), radius,
-                                                            ch_off, n_tiles, feat_out);
+    sa_small_tc_kernel<C><<<grid, kS2Threads, C::bytes, st>>>(xyz_in, new_xyz, U, consts, reinterpret_cast<const uint8_t *>(wimg), radius, ch_off,
+                                                             n_tiles, feat_out);
     GPB_LAUNCHED();
     return GPB_OK;
 }
 
+using CfgL1S1 = SmallCfg<32, 32, 32, 64, 1024, 512, 96, false>;
+using CfgL2S0 = SmallCfg<16, 64, 64, 128, 512, 256, 256, true>;
+using CfgL2S1 = SmallCfg<32, 64, 96, 128, 512, 256, 256, true>;
+
+int launch_sa1_tc(const float *pts, const float *new_xyz, const float *consts, const void *wimg, float *feat_out, int B, cudaStream_t st) {
+    return launch_sa_small<CfgL1S1>(pts, new_xyz, nullptr, consts, wimg, 0.04f, 32, feat_out, B, st);
+}
+
 int launch_sa2_tc(const float *xyz_in, const float *new_xyz, const float *U, const float *consts, const void *wimg, int scale,
                   float *feat_out, int B, cudaStream_t st) {
-    int dev = 0, sms = 0;
-    GPB_CUDA(cudaGetDevice(&dev));
-    GPB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    return scale == 0 ? launch_sa2_one<16, 64>(xyz_in, new_xyz, U, consts, wimg, 0.04f, 0, feat_out, B, sms, st)
-                      : launch_sa2_one<32, 96>(xyz_in, new_xyz, U, consts, wimg, 0.08f, 128, feat_out, B, sms, st);
+    return scale == 0 ? launch_sa_small<CfgL2S0>(xyz_in, new_xyz, U, consts, wimg, 0.04f, 0, feat_out, B, st)
+                      : launch_sa_small<CfgL2S1>(xyz_in, new_xyz, U, consts, wimg, 0.08f, 128, feat_out, B, st);
 }
 
 int launch_sa3_tc(const float *xyz_in, const float *new_xyz, const float *U, const float *consts, const void *wstream, int scale,

@@ -211,6 +211,20 @@ def pack_encoder_tc(sd: Dict[str, torch.Tensor], prefix: str = "pts_encoder") ->
         for s in range(2):
             gslots += tile_slots(folded[s][layer])
     streams += [gconst.view(torch.uint8), torch.cat(gslots).view(torch.uint8)]
+    # level 1, scale 1 (MLP [3,32,32,64]; same resident-image kernel as level 2): [512 fp32: wx[3][32] | b1 | b2 | b3][W2 hi|lo|W3 hi|lo]
+    base = f"{prefix}.SA_modules.0.mlps.1"
+    w1, b1 = _fold(sd, f"{base}.layer0")
+    w2, b2 = _fold(sd, f"{base}.layer1")
+    w3, b3 = _fold(sd, f"{base}.layer2")
+    assert w1.shape == (32, 3) and w2.shape == (32, 32) and w3.shape == (64, 32)
+    c = torch.zeros(512, dtype=torch.float32)
+    c[0:96] = w1.t().reshape(-1).float()
+    c[96:128] = b1.float()
+    c[128:160] = b2.float()
+    c[160:224] = b3.float()
+    h2, l2 = split_bf16(w2.float())
+    h3, l3 = split_bf16(w3.float())
+    streams += [c.view(torch.uint8), torch.cat([umma_image(h2), umma_image(l2), umma_image(h3), umma_image(l3)]).view(torch.uint8)]
     return torch.cat([consts.view(torch.uint8)] + streams).contiguous()
 
 

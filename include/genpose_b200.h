@@ -90,10 +90,10 @@ GPB_API size_t gpb_encode_workspace_bytes(int B);
 GPB_API int gpb_encode(const float *pts, int B, const float *enc_weights, float *pts_feat, void *workspace,
                size_t workspace_bytes, int *fps_idx1, int *fps_idx2, int *fps_idx3, void *stream);
 
-/* Same function with set-abstraction levels 2, 3 and 4 (GroupAll) on the tensor cores
+/* Same function with the MLPs of set-abstraction level 1 (wide scale), 2, 3 and 4 (GroupAll) on the tensor cores
  * (tcgen05, bf16x3 error-compensated split, fp32 accumulation; pts_feat within 1e-5 relative of gpb_encode).
  * enc_tc = the operand image made by genpose_b200/weights.py::pack_encoder_tc, gpb_encoder_tc_bytes() long,
- * 128-byte aligned.  Level 1 and the FPS / ball-query stages run the same kernels as gpb_encode. */
+ * 128-byte aligned.  FPS, ball query (same index semantics) and the narrow scale of level 1 stay on the CUDA cores. */
 GPB_API size_t gpb_encoder_tc_bytes(void);
 GPB_API int gpb_encode_tc(const float *pts, int B, const float *enc_weights, const void *enc_tc, float *pts_feat,
                   void *workspace, size_t workspace_bytes, int *fps_idx1, int *fps_idx2, int *fps_idx3, void *stream);
