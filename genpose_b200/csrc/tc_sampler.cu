@@ -33,6 +33,8 @@
 // Per step and CTA: layer 0 (10 MMAs), layer 1 (2 x 48 MMAs of 128x128x16), head slice (48 of 128x128x16 + 48 of 128x64x16).
 // History (3200 rows x 500 steps, one B200): A in shared memory + 2-deep weight ring 18.2 ms; A in TMEM, deep ring,
 // warp-uniform issue, one issue group per unit 12.6 ms (one CTA per tile, all three heads); this version: see DESIGN.md §5.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "sampler_common.cuh"
 #include "tc_common.cuh"
@@ -668,7 +670,11 @@ extern "C" int gpb_sample_pc_tc_dbg(const float *x0, int R, int K, int num_steps
     attrs[1].id = cudaLaunchAttributeCooperative;
     attrs[1].val.cooperative = 1;
     cfg.attrs = attrs;
-    cfg.numAttrs = 2;
+    // Nsight Compute cannot launch a kernel that is both clustered and cooperative (every replay mode ends in LaunchFailed,
+    // profiles/README): GPB_PROFILE_NO_COOP=1 drops the cooperative attribute for profiling runs only.  Co-residency, which the
+    // grid barrier needs, is still established by the occupancy check below (1 CTA per SM, grid <= #SMs, idle device).
+    const char *no_coop = getenv("GPB_PROFILE_NO_COOP");
+    cfg.numAttrs = (no_coop && no_coop[0] == '1') ? 1 : 2;
     int max_clusters = 0;
     GPB_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, tc_pc_sampler_kernel, &cfg));
     GPB_REQUIRE(max_clusters >= n_tiles, "sample_pc_tc: only %d co-resident 4-CTA clusters fit, %d needed; split the batch", max_clusters, n_tiles);

@@ -84,7 +84,8 @@ def test_tc_sampler_against_oracle_and_fp32_kernel(B, K, T):
     assert d_kernels <= 1e-3
     if B * K <= 400:   # the CPU oracle finishes in seconds
         ref_pose, _ = O.pred_func_pc(sd, data, K, T, torch.from_numpy(x0), torch.from_numpy(sn))
-        np.testing.assert_allclose(p_tc.cpu().numpy().reshape(B, K, 9), ref_pose.numpy(), rtol=0, atol=1e-3)
+        # relative term: the T = 30 chain ends with translations of O(100) (see test_gpu_parity.py)
+        np.testing.assert_allclose(p_tc.cpu().numpy().reshape(B, K, 9), ref_pose.numpy(), rtol=5e-5, atol=1e-3)
 
 
 def test_tc_sampler_philox_deterministic():

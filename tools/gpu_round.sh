@@ -15,9 +15,9 @@ echo "== ncu launch list"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $OUT/${TAG}_launches.csv \
     python bench.py --steps 1 --warmup 1 --no-cpu-baseline > $OUT/${TAG}_launches_bench.log 2>&1
 echo "== ncu full: sampler"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:pc_sampler -s 1 -c 1 -o $OUT/${TAG}_prof_sampler \
-    python tools/profile_target.py sampler > $OUT/${TAG}_prof_sampler.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:tc_pc_sampler -s 1 -c 1 -o $OUT/${TAG}_prof_tc_sampler \
+    python tools/profile_target.py tc_sampler > $OUT/${TAG}_prof_tc_sampler.log 2>&1
 echo "== ncu full: encoder"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:'sa_kernel|groupall|fps3|point_gemm' -s 11 -c 11 -o $OUT/${TAG}_prof_encoder \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:'sa_kernel|sa_small_tc|sa3_tc|ga_gemm|fps3|point_gemm|object_bias' -s 15 -c 15 -o $OUT/${TAG}_prof_encoder \
     python tools/profile_target.py encoder > $OUT/${TAG}_prof_encoder.log 2>&1
 ls -la $OUT | tail -20
