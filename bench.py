@@ -92,10 +92,26 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def best_cpu_threads():
-    """torch's intra-op pool stops scaling on these tiny matmuls well below the core count (measured on the 128-core GPU
-    box: 16 threads 1175 cand/s, 32: 626, 64: 300, 128: 1.4 at T=100 — profiles/cpu_threads_probe.txt), so the CPU arm uses 16."""
-    return min(os.cpu_count() or 1, 16)
+_BEST_THREADS = {}
+
+
+def best_cpu_threads(n_objects=None):
+    """torch's intra-op pool stops scaling on these small matmuls well below the core count (measured on the 128-core GPU
+    box at 200 rows: 16 threads 1175 cand/s, 32: 626, 64: 300, 128: 1.4 — profiles/cpu_threads_probe.txt).  So the CPU arm
+    is given the thread count that is actually fastest for its batch: a 10-step probe at 16 / 32 / 64 threads."""
+    cores = os.cpu_count() or 1
+    if os.environ.get("GPB_CPU_THREADS"):
+        return max(1, min(cores, int(os.environ["GPB_CPU_THREADS"])))
+    cands = [t for t in (16, 32, 64) if t <= cores]
+    if n_objects is None or len(cands) <= 1:
+        return min(cores, 16)
+    if n_objects not in _BEST_THREADS:
+        rates = {}
+        for t in cands:
+            cpu_oracle_rate(1, K_CAND, 4, 2, threads=t)                      # page in at this pool size
+            rates[t] = cpu_oracle_rate(n_objects, K_CAND, 10, 2, threads=t)[0]
+        _BEST_THREADS[n_objects] = max(rates, key=rates.get)
+    return _BEST_THREADS[n_objects]
 
 
 def cpu_oracle_rate(n_objects, K, T, config, seed=0, threads=None):
@@ -130,8 +146,10 @@ def run_reference_arm(args, rank, world):
     Python + a CUDA-only extension and cannot travel to this box) on all host threads; rank 0 only."""
     if rank != 0:
         return
-    cores = best_cpu_threads()
-    n_obj = args.ref_objects
+    # bounded sample: as many objects of the batch per step as keep the whole arm near two minutes
+    r_probe = cpu_oracle_rate(4, K_CAND, T_STEPS, args.config, threads=best_cpu_threads())[0]
+    n_obj = min(args.ref_objects, max(4, int(120.0 * r_probe / (K_CAND * max(1, args.steps)))))
+    cores = best_cpu_threads(n_obj)
     for _ in range(args.warmup):
         cpu_oracle_rate(1, K_CAND, 20, args.config, threads=cores)
     rates, secs = [], []
@@ -169,7 +187,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", type=int, default=2, choices=[2, 3])
-    ap.add_argument("--ref-objects", type=int, default=8, help="objects per step of the CPU reference arm / cpu_baseline sample")
+    ap.add_argument("--ref-objects", type=int, default=64, help="objects per step of the CPU reference arm / cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--precision", default="auto", choices=["auto", "bf16x3", "fp32"],
                     help="dense layers of the sampler: tcgen05 bf16x3 (auto when the shape allows) or the fp32 FFMA parity kernel")
@@ -318,7 +336,7 @@ def main():
             ffma_peak = 148 * 128 * 2 * clock_info["sm_mhz"] * 1e6 / 1e12
             line["roofline"]["frac_ffma"] = ach / ffma_peak
         if not args.no_cpu_baseline:
-            cores = best_cpu_threads()
+            cores = best_cpu_threads(args.ref_objects)
             cpu_oracle_rate(1, K_CAND, 10, args.config, threads=cores)      # page in
             v, secs, detail = cpu_oracle_rate(args.ref_objects, K_CAND, T_STEPS, args.config, threads=cores)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
