@@ -30,6 +30,7 @@ struct PcParams {
     const float *tb_table;    // [T,768]
     float *partial;           // [2][gridDim] per-CTA sums of row norms
     unsigned *barrier;        // monotonic arrival counter (zeroed before launch)
+    unsigned long long *acc;  // [T] zeroed before launch; tcgen05 sampler only (see tc_sampler.cu, "batch-mean gradient norm")
     float *mean_x;            // [R,9] out
     float *process;           // [R,T,9] out or null
     int tiles_per_cta;
@@ -100,7 +101,7 @@ struct SamplerWs {
     float *partial;      // [2*1024] floats (PC)  /  doubles [4*1024] (ODE) share the slot
     unsigned *barrier;   // [64] (256 B)
     double *y, *ynew, *Kst;
-    void *xch;           // tile-team mailboxes of the tcgen05 sampler: counters (4 KiB) | partials [tiles][2][4][128][9]
+    unsigned long long *acc;   // [T] per-step (arrival count | fixed-point norm sum) words of the tcgen05 sampler's grid reduction
     size_t bytes;
 };
 inline SamplerWs carve_sampler(void *base, int R, int T) {
@@ -118,7 +119,7 @@ inline SamplerWs carve_sampler(void *base, int R, int T) {
     w.y = reinterpret_cast<double *>(take((size_t)R * 9 * sizeof(double)));
     w.ynew = reinterpret_cast<double *>(take((size_t)R * 9 * sizeof(double)));
     w.Kst = reinterpret_cast<double *>(take((size_t)7 * R * 9 * sizeof(double)));
-    w.xch = take(4096 + (size_t)((R + 127) / 128) * 2 * 4 * 128 * 9 * sizeof(float));
+    w.acc = reinterpret_cast<unsigned long long *>(take((size_t)(T > 0 ? T : 1) * sizeof(unsigned long long)));
     w.bytes = off;
     return w;
 }

@@ -76,8 +76,13 @@ struct TcPcParams {
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
-__device__ __forceinline__ void red_release_add(unsigned *p, unsigned v) {
-    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+__device__ __forceinline__ void red_relaxed_add_u64(unsigned long long *p, unsigned long long v) {
+    asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
 }
 
 // bias + ReLU + bf16 hi/lo split of 32 accumulator columns -> 16 + 16 packed words (column pairs)
@@ -351,7 +356,6 @@ tc_pc_sampler_kernel(TcPcParams tp) {
         const float sqrt_step = sqrtf(step_size);
         const float snr_norm = (float)((double)p.snr * 3.0);
         uint32_t u = 0;
-        unsigned bar_target = 0;
 
         // relu(acc + obj_bias + t_bias) . O over one 32-column block whose first stacked hidden unit is n (one head per block)
         auto head_block = [&](const uint32_t (&v)[32], int n, float &o0, float &o1, float &o2) {
@@ -538,36 +542,45 @@ tc_pc_sampler_kernel(TcPcParams tp) {
             }
             // ---- every rank: score, batch-mean gradient norm (published by the leaders), update — redundantly, bit-identically ----
             float gr[9], n2 = 0.f;
+            const float inv_std = 1.0f / stdv;   // one IEEE division per row and step instead of nine (<= 1.5 ulp from f / std, scorenet.py:217)
 #pragma unroll
             for (int c = 0; c < 9; ++c) {
-                gr[c] = (f[c] + sOw[9 * 256 + c]) / stdv;
+                gr[c] = (f[c] + sOw[9 * 256 + c]) * inv_std;
                 n2 = fmaf(gr[c], gr[c], n2);
             }
-            // ---- batch-mean gradient norm: leaders publish the tile partial + one RED on the counter; thread 0 of every CTA polls
-            //      the counter, then every warp fetches the partials.  (Measured alternatives, both slower: per-warp partials as
-            //      tagged 64-bit words polled by every warp, 8.2 k cycles instead of 2.8 k — the pollers starve the writers;
-            //      tagged tile sums polled by one warp per CTA, 4.4 k.)
-            bar_target += (unsigned)n_tiles;
+            // ---- batch-mean gradient norm = ONE 64-bit word per step: the leader of every tile adds
+            //          (1 << 58 | poisoned << 52 | tile sum as 32.20 fixed point)
+            //      with a single relaxed RED; thread 0 of every CTA polls the word until the arrival count reaches n_tiles and then
+            //      holds the count AND the sum.  Integer addition is associative, so the total is independent of arrival order
+            //      (bitwise reproducible, identical in every CTA) and exact to 2^-20 per tile; no payload travels beside the word, so
+            //      no release/acquire pair and no second round trip for the partials.  (Measured predecessors: partial array +
+            //      RED.release counter + acquire poll + __ldcg of the partials, 2.8 k + 0.9 k cycles per step; per-warp tagged words
+            //      polled by every warp 8.2 k; tagged tile sums polled by one warp per CTA 4.4 k.)  A tile whose sum is NaN or
+            //      >= 2^26 marks the word poisoned and the step's norm becomes NaN, as it would be (or diverge) in the reference.
             if (leader) {
                 const float wsum = warp_sum(valid ? sqrtf(n2) : 0.f);
                 if (lane == 0) s_red[q] = wsum;
                 named_bar_sync(2, 128);
                 if (tid == 0) {
                     if (ds) ds[14] = clock64();
-                    p.partial[(step & 1) * n_tiles + tile] = (s_red[0] + s_red[1]) + (s_red[2] + s_red[3]);
-                    red_release_add(p.barrier, 1u);
+                    const float tile_sum = (s_red[0] + s_red[1]) + (s_red[2] + s_red[3]);
+                    const bool ok = tile_sum >= 0.f && tile_sum < 67108864.f;                  // false for NaN
+                    const unsigned long long fx = ok ? __float2ull_rn(tile_sum * 1048576.f) : 0ull;
+                    red_relaxed_add_u64(p.acc + step, (1ull << 58) | (ok ? 0ull : (1ull << 52)) | fx);
                 }
             }
             if (tid == 0) {
-                while (ld_acquire_u32(p.barrier) < bar_target) {
-                }
+                unsigned long long v;
+                do {
+                    v = ld_relaxed_u64(p.acc + step);
+                } while ((unsigned)(v >> 58) < (unsigned)n_tiles);
+                const bool poisoned = ((v >> 52) & 63ull) != 0ull;
+                s_red[4] = poisoned ? __int_as_float(0x7fc00000) : (float)((double)(v & ((1ull << 52) - 1ull)) * (1.0 / 1048576.0));
                 if (ds) ds[15] = clock64();
             }
             named_bar_sync(2, 128);
             if (ds) ds[12] = clock64();
-            float tot = 0.f;   // every warp: lanes fetch the per-tile partials in parallel, fixed-shape shuffle tree => identical everywhere
-            for (int i = lane; i < n_tiles; i += 32) tot += __ldcg(p.partial + (step & 1) * n_tiles + i);
-            tot = warp_sum(tot);
+            const float tot = s_red[4];
             const float grad_norm = tot / (float)p.R;
             const PcStepConsts sc = pc_step_consts(grad_norm, snr_norm, sigma, step_size, sqrt_step);
             if (valid) {
@@ -640,10 +653,12 @@ extern "C" int gpb_sample_pc_tc_dbg(const float *x0, int R, int K, int num_steps
     GPB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     const int n_tiles = (R + kTcRows - 1) / kTcRows;
     const int grid = n_tiles * kTeam;
+    GPB_REQUIRE(n_tiles < 64, "sample_pc_tc: R=%d is %d tiles; the per-step reduction word counts at most 63", R, n_tiles);
     GPB_REQUIRE(grid <= sms, "sample_pc_tc: R=%d needs %d co-resident CTAs but the device has %d SMs; split the batch", R, grid, sms);
 
     SamplerWs w = carve_sampler(workspace, R, num_steps);
     GPB_CUDA(cudaMemsetAsync(w.barrier, 0, 256, st));
+    GPB_CUDA(cudaMemsetAsync(w.acc, 0, (size_t)num_steps * sizeof(unsigned long long), st));
     int rc = launch_time_bias_table(time_grid, num_steps, W, w.tb_table, st);
     if (rc) return rc;
 
@@ -651,7 +666,7 @@ extern "C" int gpb_sample_pc_tc_dbg(const float *x0, int R, int K, int num_steps
     PcParams &p = tp.pc;
     p.x0 = x0; p.R = R; p.K = K; p.T = num_steps; p.snr = snr;
     p.obj_bias = obj_bias; p.W = W; p.pts_center = pts_center; p.noise = step_noise; p.seed = seed;
-    p.ts = time_grid; p.tb_table = w.tb_table; p.partial = w.partial; p.barrier = w.barrier;
+    p.ts = time_grid; p.tb_table = w.tb_table; p.partial = w.partial; p.barrier = w.barrier; p.acc = w.acc;
     p.mean_x = mean_x; p.process = process; p.tiles_per_cta = 1; p.dbg = dbg; p.dbg_cta = dbg ? dbg_cta_sel : 0;
     tp.wstream = reinterpret_cast<const uint8_t *>(tc_stream);
 
