@@ -94,13 +94,26 @@ __device__ __forceinline__ void pc_row_update(const PcParams &p, const PcStepCon
     gram_schmidt6(x);                                                                   // (:152)
 }
 
+// Dormand-Prince 5(4) tableau exactly as scipy/integrate/_ivp/rk.py (class RK45) states it
+static __constant__ double kRkC[6] = {0.0, 1.0 / 5, 3.0 / 10, 4.0 / 5, 8.0 / 9, 1.0};
+static __constant__ double kRkA[6][5] = {
+    {0, 0, 0, 0, 0},
+    {1.0 / 5, 0, 0, 0, 0},
+    {3.0 / 40, 9.0 / 40, 0, 0, 0},
+    {44.0 / 45, -56.0 / 15, 32.0 / 9, 0, 0},
+    {19372.0 / 6561, -25360.0 / 2187, 64448.0 / 6561, -212.0 / 729, 0},
+    {9017.0 / 3168, -355.0 / 33, 46732.0 / 5247, 49.0 / 176, -5103.0 / 18656}};
+static __constant__ double kRkB[6] = {35.0 / 384, 0, 500.0 / 1113, 125.0 / 192, -2187.0 / 6784, 11.0 / 84};
+static __constant__ double kRkE[7] = {-71.0 / 57600, 0, 71.0 / 16695, -71.0 / 1920, 17253.0 / 339200, -22.0 / 525, 1.0 / 40};
+
 // workspace shared by the samplers (gpb_sampler_workspace_bytes)
 struct SamplerWs {
     float *tb_table;     // [T,768]
     float *ts;           // [T]
     float *partial;      // [2*1024] floats (PC)  /  doubles [4*1024] (ODE) share the slot
     unsigned *barrier;   // [64] (256 B)
-    double *y, *ynew, *Kst;
+    double *y, *ynew, *Kst;   // Kst: [4 copies][7][R,9] (the tcgen05 ODE kernel keeps one copy per tile-team rank; the FFMA kernel uses copy 0)
+    float *tb_cta;             // [160 CTAs][6][768] per-CTA time-bias scratch of the tcgen05 ODE kernel
     unsigned long long *acc;   // [T] per-step (arrival count | fixed-point norm sum) words of the tcgen05 sampler's grid reduction
     size_t bytes;
 };
@@ -118,7 +131,8 @@ inline SamplerWs carve_sampler(void *base, int R, int T) {
     w.tb_table = reinterpret_cast<float *>(take((size_t)(T > 0 ? T : 1) * 768 * sizeof(float)));
     w.y = reinterpret_cast<double *>(take((size_t)R * 9 * sizeof(double)));
     w.ynew = reinterpret_cast<double *>(take((size_t)R * 9 * sizeof(double)));
-    w.Kst = reinterpret_cast<double *>(take((size_t)7 * R * 9 * sizeof(double)));
+    w.Kst = reinterpret_cast<double *>(take((size_t)4 * 7 * R * 9 * sizeof(double)));
+    w.tb_cta = reinterpret_cast<float *>(take((size_t)160 * 6 * 768 * sizeof(float)));
     w.acc = reinterpret_cast<unsigned long long *>(take((size_t)(T > 0 ? T : 1) * sizeof(unsigned long long)));
     w.bytes = off;
     return w;

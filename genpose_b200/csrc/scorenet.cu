@@ -453,17 +453,6 @@ struct OdeParams {
     int tiles_per_cta;
 };
 
-__constant__ double kRkC[6] = {0.0, 1.0 / 5, 3.0 / 10, 4.0 / 5, 8.0 / 9, 1.0};
-__constant__ double kRkA[6][5] = {
-    {0, 0, 0, 0, 0},
-    {1.0 / 5, 0, 0, 0, 0},
-    {3.0 / 40, 9.0 / 40, 0, 0, 0},
-    {44.0 / 45, -56.0 / 15, 32.0 / 9, 0, 0},
-    {19372.0 / 6561, -25360.0 / 2187, 64448.0 / 6561, -212.0 / 729, 0},
-    {9017.0 / 3168, -355.0 / 33, 46732.0 / 5247, 49.0 / 176, -5103.0 / 18656}};
-__constant__ double kRkB[6] = {35.0 / 384, 0, 500.0 / 1113, 125.0 / 192, -2187.0 / 6784, 11.0 / 84};
-__constant__ double kRkE[7] = {-71.0 / 57600, 0, 71.0 / 16695, -71.0 / 1920, 17253.0 / 339200, -22.0 / 525, 1.0 / 40};
-
 // f(t, Y) for every owned row: Y (double, global [R,9]) -> Kout (double, global [R,9]).
 // ode_func (samplers.py:189-198): x -> fp32, t -> fp32, score in fp32, f = 0 - fp32(0.5 g^2) * score (fp32,
 // NumPy-1.23 value-based casting), g = double(sigma_fp32(t32)) * sqrt(2 ln(5000)) (float64).

@@ -34,6 +34,7 @@
 // History (3200 rows x 500 steps, one B200): A in shared memory + 2-deep weight ring 18.2 ms; A in TMEM, deep ring,
 // warp-uniform issue, one issue group per unit 12.6 ms (one CTA per tile, all three heads); this version: see DESIGN.md §5.
 #include <cstdlib>
+#include <type_traits>
 
 #include "common.cuh"
 #include "sampler_common.cuh"
@@ -66,13 +67,43 @@ constexpr uint32_t kOffBias = kOffOw + (9 * 256 + 16) * 4;            // p1_b [2
 constexpr uint32_t kOffFpart = kOffBias + 512 * 4;                    // [128][12] fp32 partial scores of column sub-half 1
 constexpr uint32_t kOffMail = kOffFpart + 128 * 12 * 4;               // [2 parities][4 ranks][128][8] fp32: the team's partial sums (DSMEM)
 constexpr uint32_t kTcSmemBytes = kOffMail + 2 * 4 * 128 * 8 * 4;
-static_assert(kTcSmemBytes <= 227 * 1024 - 768, "tc sampler shared memory budget");
+constexpr uint32_t kOffOdeY = kTcSmemBytes;                           // ODE only: y [9][128] | y_new [9][128] float64
+constexpr uint32_t kTcSmemBytesOde = kOffOdeY + 2 * 9 * 128 * 8;
+static_assert(kTcSmemBytesOde <= 227 * 1024 - 1536, "tc sampler shared memory budget");
+
+// probability-flow ODE mode (cond_ode_sampler, samplers.py:163-227): everything PcParams does not already carry
+struct TcOdeParams {
+    float T0, rtol, atol;
+    int denoise_steps;
+    double *Kst;        // [4 ranks][7 stages][R,9] float64 stage derivatives, one private copy per tile-team rank
+    double *partial;    // [4 slots][n_tiles][2] per-tile partial sums of the step controller's norms
+    float *tb_cta;      // [gridDim][6][768] time biases of the evaluation group in flight (private per CTA)
+    double *pose;       // [R,9] float64 out (samplers.py:206-207)
+    int *stats;         // [4] nfev, accepted, rejected, status (optional)
+};
 
 struct TcPcParams {
     PcParams pc;
     const uint8_t *wstream;   // kSlotsPerStep x 16 KiB of bf16 operand images (genpose_b200/weights.py::pack_trunk_tc)
+    TcOdeParams ode;          // used by tc_ode_sampler_kernel only
 };
 
+__device__ __forceinline__ int ld_volatile_shared(const int *p) {
+    int v;
+    asm volatile("ld.volatile.shared.s32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_volatile_shared(int *p, int v) {
+    asm volatile("st.volatile.shared.s32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
+}
+__device__ __forceinline__ void red_release_add_u32(unsigned *p, unsigned v) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ double warp_sum_f64(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -94,8 +125,13 @@ __device__ __forceinline__ void relu_split32(const uint32_t (&v)[32], const floa
     }
 }
 
-__global__ void __launch_bounds__(kTcThreads, 1)   // 10 warps are allocated as 12 (granularity 4): <= 168 registers per thread
-tc_pc_sampler_kernel(TcPcParams tp) {
+// One body, two kernels: kOde = false is the predictor-corrector sampler (tc_pc_sampler_kernel), kOde = true the RK45
+// probability-flow ODE sampler (tc_ode_sampler_kernel).  They share the score-network evaluation (weight producer, MMA issuer,
+// epilogues, team exchange) and differ in what the row warps do with the score and in how the trip count is known:
+// PC runs exactly T evaluations; the ODE solver's count depends on its step controller, so the row warps publish how many
+// evaluations are known to exist (s_allowed, always at least one ahead of every decision point) and when the last one is (s_final).
+template <bool kOde>
+__device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
     const PcParams &p = tp.pc;
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t *sRing = smem + kOffRing;
@@ -108,6 +144,10 @@ tc_pc_sampler_kernel(TcPcParams tp) {
         bar_mail[2];
     __shared__ uint32_t s_tmem_base;
     __shared__ float s_red[8];
+    // ODE mode: evaluation bookkeeping shared with the producer / MMA warps, the evaluation group in flight, fp64 reduction scratch
+    __shared__ int s_allowed, s_final, s_gn;
+    __shared__ float s_times[8];
+    __shared__ double s_redd[12];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int tile = blockIdx.x / kTeam, rank = (int)cluster_ctarank();   // cluster = tile team (launch: cluster dims 4x1x1); rank 0 leads
@@ -133,9 +173,17 @@ tc_pc_sampler_kernel(TcPcParams tp) {
         mbar_init(&bar_mail[0], 1);                // one local arrive.expect_tx per use; the peers' st.async complete the bytes
         mbar_init(&bar_mail[1], 1);
         fence_mbar_init();
+        if constexpr (kOde) {
+            s_allowed = 2 + 6 + 1;     // f0, f1 (select_initial_step), the first RK45 attempt, and whatever follows it
+            s_final = 0;
+            s_gn = 1;
+            s_times[0] = tp.ode.T0;
+        }
     }
     if (warp == kTcRowWarps) tmem_alloc(&s_tmem_base, 512);
-    for (int i = tid; i < n_obj * 768; i += kTcThreads) sObt[i] = p.obj_bias[(size_t)obj_lo * 768 + i] + p.tb_table[i % 768];   // step 0
+    if constexpr (!kOde) {
+        for (int i = tid; i < n_obj * 768; i += kTcThreads) sObt[i] = p.obj_bias[(size_t)obj_lo * 768 + i] + p.tb_table[i % 768];   // step 0
+    }
     for (int i = tid; i < 9 * 256 + 12; i += kTcThreads) sOw[i] = W[TL::o_w + i];   // o_w then o_b are adjacent
     for (int i = tid; i < 256; i += kTcThreads) {
         sBias[i] = W[TL::p1_b + i];
@@ -152,14 +200,31 @@ tc_pc_sampler_kernel(TcPcParams tp) {
     if (warp == kTcRowWarps + 1) {
         // =============================== weight producer ===============================
         if (lane == 0) {
-            const uint32_t total = (uint32_t)p.T * kSlotsPerCtaStep;
-            for (uint32_t it = 0; it < total; ++it) {
+            auto produce = [&](uint32_t it) {
                 const uint32_t s = it % kSlots;
                 const uint32_t idx = it % kSlotsPerCtaStep;
                 const uint32_t src = idx < (uint32_t)kCommonSlots ? idx : idx + (uint32_t)(rank * kHeadSlots);
                 mbar_wait(&bar_empty[s], ((it / kSlots) & 1u) ^ 1u);
                 mbar_arrive_expect_tx(&bar_full[s], kSlotBytes);
                 bulk_g2s(sRing + s * kSlotBytes, tp.wstream + (size_t)src * kSlotBytes, kSlotBytes, &bar_full[s]);
+            };
+            if constexpr (!kOde) {
+                const uint32_t total = (uint32_t)p.T * kSlotsPerCtaStep;
+                for (uint32_t it = 0; it < total; ++it) produce(it);
+            } else {
+                // stream the weights of evaluation e only once it is known to exist; the row warps keep s_allowed one evaluation
+                // ahead of every decision point, so this loop only ever waits at the very end (no copy is left in flight at exit)
+                bool more = true;
+                for (int e = 0; more; ++e) {
+                    while (e >= ld_volatile_shared(&s_allowed)) {
+                        if (ld_volatile_shared(&s_final)) {
+                            more = false;
+                            break;
+                        }
+                    }
+                    if (!more) break;
+                    for (uint32_t k = 0; k < (uint32_t)kSlotsPerCtaStep; ++k) produce((uint32_t)e * kSlotsPerCtaStep + k);
+                }
             }
         }
     } else if (warp == kTcRowWarps) {
@@ -178,9 +243,10 @@ tc_pc_sampler_kernel(TcPcParams tp) {
             __syncwarp();
             tc_fence_after_sync();
         };
-        for (int step = 0; step < p.T; ++step) {
-            unsigned long long *ds = (dbg_cta && lane == 0) ? p.dbg + ((size_t)p.T + step) * 16 : nullptr;
+        for (int step = 0; kOde || step < p.T; ++step) {
+            unsigned long long *ds = (!kOde && dbg_cta && lane == 0) ? p.dbg + ((size_t)p.T + step) * 16 : nullptr;
             unsigned long long w_full = 0, w_a = 0, w_acc = 0, tq = 0, w_issue = 0;
+            unsigned long long u_full[4] = {0, 0, 0, 0}, u_a[4] = {0, 0, 0, 0}, u_issue[4] = {0, 0, 0, 0};   // per-unit split (profiling only)
             if (ds) ds[0] = clock64();
             // ---- layer 0: h1_pre = x . P1^T   (K = 16; x pieces x1,x2,x3 at A_hi[0,8),[8,16),[16,24); P1 hi|lo per unit)
             mbar_wait(&bar_x_ready, xr & 1u);
@@ -212,6 +278,7 @@ tc_pc_sampler_kernel(TcPcParams tp) {
             }
             // ---- units with K = 256: layer 1 (P2: two 128-column units) and this rank's head slice (128 + 64 columns) ----
             for (int unit = 0; unit < 4; ++unit) {
+                const unsigned long long f0 = w_full, a0 = w_a, i0 = w_issue;
                 if (ds) tq = clock64();
                 // Units 0 and 2 are the first consumers of a freshly written A operand (h1 / pf).  The row warps publish it in
                 // two halves (K columns [0,128) as soon as the first accumulator unit is converted, [128,256) after the second),
@@ -301,6 +368,11 @@ tc_pc_sampler_kernel(TcPcParams tp) {
                     it += 4u;
                 }
                 ++u;
+                if (ds) {
+                    u_full[unit] = w_full - f0;
+                    u_a[unit] = w_a - a0;
+                    u_issue[unit] = w_issue - i0;
+                }
             }
             if (ds) {
                 ds[7] = clock64();
@@ -308,6 +380,15 @@ tc_pc_sampler_kernel(TcPcParams tp) {
                 ds[9] = w_a;
                 ds[10] = w_acc;
                 ds[11] = w_issue;
+                ds[2] = u_full[0] | (u_a[0] << 32);
+                ds[5] = u_full[1] | (u_a[1] << 32);
+                ds[6] = u_full[2] | (u_a[2] << 32);
+                ds[12] = u_full[3] | (u_a[3] << 32);
+                ds[13] = u_issue[0] | (u_issue[1] << 32);
+                ds[14] = u_issue[2] | (u_issue[3] << 32);
+            }
+            if constexpr (kOde) {   // the flags were written before the x_ready arrival that released this evaluation
+                if (ld_volatile_shared(&s_final) && step + 1 == ld_volatile_shared(&s_allowed)) break;
             }
         }
     } else {
@@ -352,10 +433,129 @@ tc_pc_sampler_kernel(TcPcParams tp) {
         };
         if (cs == 0) publish_x();
 
-        const float step_size = p.ts[0] - p.ts[1];
+        const float step_size = kOde ? 0.f : p.ts[0] - p.ts[1];
         const float sqrt_step = sqrtf(step_size);
         const float snr_norm = (float)((double)p.snr * 3.0);
         uint32_t u = 0;
+
+        // ================= ODE mode: helpers and solver state (dead code in the PC instantiation) =================
+        const TcOdeParams &od = tp.ode;
+        const int rt = tid;                                                   // 0..255 over the eight row warps
+        float *tb_mine = od.tb_cta + (size_t)blockIdx.x * 6 * 768;           // this CTA's [6][768] time biases
+        double *sY = reinterpret_cast<double *>(smem + kOffOdeY);             // [9][128]
+        double *sYn = sY + 9 * 128;                                           // [9][128]
+        // t_bias(t_j)[0:768] for the gn times in s_times (scorenet.py:63-64, :195; same operation order as compute_time_bias in
+        // scorenet.cu): all eight row warps, scratch = sFpart (free between the team exchange and the next head epilogue)
+        auto time_biases = [&](auto GN) {
+            constexpr int gn = decltype(GN)::value;
+            float *tf = sFpart, *te = sFpart + 768;
+            for (int i = rt; i < gn * 64; i += 256) {
+                const int j = i >> 6, k = i & 63;
+                const float xp = ((s_times[j] * W[TL::fourier_w + k]) * 2.0f) * 3.14159265358979323846f;
+                tf[j * 128 + k] = sinf(xp);
+                tf[j * 128 + 64 + k] = cosf(xp);
+            }
+            named_bar_sync(5, 256);
+            {
+                constexpr int per = (gn + 1) / 2;                             // times per thread half
+                const int n = rt & 127, j0 = (rt >> 7) * per;
+                float acc[per];
+                const float b = W[TL::t_b + n];
+#pragma unroll
+                for (int jj = 0; jj < per; ++jj) acc[jj] = b;
+                const float *w = W + TL::t_w + n;
+#pragma unroll 4
+                for (int k = 0; k < 128; ++k) {
+                    const float wk = __ldg(w + k * 128);
+#pragma unroll
+                    for (int jj = 0; jj < per; ++jj) acc[jj] = fmaf(tf[(j0 + jj < gn ? j0 + jj : 0) * 128 + k], wk, acc[jj]);
+                }
+#pragma unroll
+                for (int jj = 0; jj < per; ++jj)
+                    if (j0 + jj < gn) te[(j0 + jj) * 128 + n] = fmaxf(acc[jj], 0.f);
+            }
+            named_bar_sync(5, 256);
+            {
+                float acc[3][gn];
+#pragma unroll
+                for (int m = 0; m < 3; ++m)
+#pragma unroll
+                    for (int j = 0; j < gn; ++j) acc[m][j] = 0.f;
+                const float *w = W + TL::a_t + rt;
+#pragma unroll 2
+                for (int k = 0; k < 128; ++k) {
+                    const float w0 = __ldg(w + k * 768), w1 = __ldg(w + k * 768 + 256), w2 = __ldg(w + k * 768 + 512);
+#pragma unroll
+                    for (int j = 0; j < gn; ++j) {
+                        const float e = te[j * 128 + k];
+                        acc[0][j] = fmaf(e, w0, acc[0][j]);
+                        acc[1][j] = fmaf(e, w1, acc[1][j]);
+                        acc[2][j] = fmaf(e, w2, acc[2][j]);
+                    }
+                }
+#pragma unroll
+                for (int m = 0; m < 3; ++m)
+#pragma unroll
+                    for (int j = 0; j < gn; ++j) __stcg(tb_mine + j * 768 + rt + 256 * m, acc[m][j]);
+            }
+            named_bar_sync(5, 256);
+        };
+        // (object bias + time bias of evaluation `gi` of the group) -> sObt, by `nthr` threads starting at thread `t0`
+        auto fill_obt = [&](int gi, int t0, int nthr) {
+            for (int i = tid - t0; i < n_obj * 768; i += nthr)
+                sObt[i] = __ldg(p.obj_bias + (size_t)obj_lo * 768 + i) + __ldcg(tb_mine + gi * 768 + i % 768);
+        };
+        // solver state, replicated bit-identically in every row thread of every rank (scipy/integrate/_ivp/rk.py, common.py)
+        enum { kPhF0 = 0, kPhF1 = 1, kPhAttempt = 2, kPhDenoise = 3 };
+        int phase = kPhF0, st = 0, gi = 0, gn = 1, slot = 0, nfev = 0, n_acc = 0, n_rej = 0, status = 0;
+        unsigned bar_target = 0;
+        bool rejected = false;
+        const double t_end = 1e-5, direction = -1.0;                          // eps as a Python float; T0 > eps is checked by the host
+        double t_cur = (double)od.T0, t_next = 0.0, h = 0.0, h_abs = 0.0, h0 = 0.0, d1 = 0.0, min_step = 0.0;
+        const double rtol = (double)od.rtol, atol = (double)od.atol, n_total = (double)p.R * 9.0;
+        double *Kmine = od.Kst + ((size_t)rank * 7 * p.R + (valid ? row : 0)) * 9;   // stage j of this row: Kmine + j * R * 9
+        const size_t kst = (size_t)p.R * 9;
+        // two grid-wide float64 sums with ONE barrier; every CTA obtains the identical fixed-order totals
+        auto grid_sum2 = [&](double a, double b, double &A, double &B) {
+            a = warp_sum_f64(valid ? a : 0.0);
+            b = warp_sum_f64(valid ? b : 0.0);
+            if (lane == 0) {
+                s_redd[2 * q] = a;
+                s_redd[2 * q + 1] = b;
+            }
+            named_bar_sync(2, 128);
+            bar_target += (unsigned)n_tiles;
+            if (tid == 0) {
+                if (leader) {
+                    double *dst = od.partial + ((size_t)slot * n_tiles + tile) * 2;
+                    __stcg(dst, (s_redd[0] + s_redd[2]) + (s_redd[4] + s_redd[6]));
+                    __stcg(dst + 1, (s_redd[1] + s_redd[3]) + (s_redd[5] + s_redd[7]));
+                    red_release_add_u32(p.barrier, 1u);
+                }
+                while (ld_acquire_u32(p.barrier) < bar_target) {
+                }
+                double ta = 0.0, tb = 0.0;
+                for (int i = 0; i < n_tiles; ++i) {
+                    ta += __ldcg(od.partial + ((size_t)slot * n_tiles + i) * 2);
+                    tb += __ldcg(od.partial + ((size_t)slot * n_tiles + i) * 2 + 1);
+                }
+                s_redd[8] = ta;
+                s_redd[9] = tb;
+            }
+            named_bar_sync(2, 128);
+            A = s_redd[8];
+            B = s_redd[9];
+            slot = (slot + 1) & 3;
+        };
+        if constexpr (kOde) {
+            if (cs == 0) {
+#pragma unroll
+                for (int c = 0; c < 9; ++c) sY[c * 128 + r] = (double)x[c];   // y0 = float64(init_x) (samplers.py:205)
+            }
+            time_biases(std::integral_constant<int, 1>{});
+            fill_obt(0, 0, 256);
+            // no barrier needed here: the first reader of sObt is the head epilogue, behind named barrier 3 of the first evaluation
+        }
 
         // relu(acc + obj_bias + t_bias) . O over one 32-column block whose first stacked hidden unit is n (one head per block)
         auto head_block = [&](const uint32_t (&v)[32], int n, float &o0, float &o1, float &o2) {
@@ -377,10 +577,10 @@ tc_pc_sampler_kernel(TcPcParams tp) {
             }
         };
 
-        for (int step = 0; step < p.T; ++step) {
-            unsigned long long *ds = dbg ? p.dbg + (size_t)step * 16 : nullptr;
+        for (int step = 0; kOde || step < p.T; ++step) {
+            unsigned long long *ds = (!kOde && dbg) ? p.dbg + (size_t)step * 16 : nullptr;
             if (ds) ds[0] = clock64();
-            const float t = p.ts[step];
+            const float t = kOde ? s_times[gi] : p.ts[step];
             const float sigma = sigma_of_t(t);
             const float stdv = sigma + 1e-7f;
             // ---- layers 0 and 1: accumulator -> bias + ReLU -> bf16 hi/lo -> A operand in tensor memory ----
@@ -442,7 +642,7 @@ tc_pc_sampler_kernel(TcPcParams tp) {
             }
             // noise of this step, generated while the tensor core runs the head slice (the leader's warps 0-3 own the rows)
             float z1[9], z2[9];
-            if (cs == 0 && valid) {
+            if (!kOde && cs == 0 && valid) {
                 row_noise(p, step, 0, row, z1);
                 row_noise(p, step, 1, row, z2);
             }
@@ -495,12 +695,28 @@ tc_pc_sampler_kernel(TcPcParams tp) {
             if (ds) ds[9] = clock64();
             if (cs == 1) {
                 // warps 4-7: table of (object bias + time bias) for the NEXT step, while warps 0-3 exchange / reduce / update
-                if (step + 1 < p.T) {
-                    const float *tbn = p.tb_table + (size_t)(step + 1) * 768;
-                    for (int i = tid - 128; i < n_obj * 768; i += 128)
-                        sObt[i] = __ldg(p.obj_bias + (size_t)obj_lo * 768 + i) + __ldg(tbn + i % 768);
+                if constexpr (!kOde) {
+                    if (step + 1 < p.T) {
+                        const float *tbn = p.tb_table + (size_t)(step + 1) * 768;
+                        for (int i = tid - 128; i < n_obj * 768; i += 128)
+                            sObt[i] = __ldg(p.obj_bias + (size_t)obj_lo * 768 + i) + __ldg(tbn + i % 768);
+                    }
+                    continue;
+                } else {
+                    if (gi + 1 < gn) {                    // inside an evaluation group: the next time bias is already in tb_mine
+                        ++gi;
+                        fill_obt(gi, 128, 128);
+                        continue;
+                    }
+                    named_bar_sync(4, 256);               // group boundary: warps 0-3 have decided what comes next
+                    gn = s_gn;
+                    gi = 0;
+                    if (gn == 0) break;                   // solved
+                    if (gn == 6) time_biases(std::integral_constant<int, 6>{});
+                    else time_biases(std::integral_constant<int, 1>{});
+                    fill_obt(0, 128, 128);
+                    continue;
                 }
-                continue;
             }
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
@@ -540,88 +756,347 @@ tc_pc_sampler_kernel(TcPcParams tp) {
                     if (hb != ha) { f[3 * hb + 0] += a.w; f[3 * hb + 1] += b.x; f[3 * hb + 2] += b.y; }
                 }
             }
-            // ---- every rank: score, batch-mean gradient norm (published by the leaders), update — redundantly, bit-identically ----
-            float gr[9], n2 = 0.f;
-            const float inv_std = 1.0f / stdv;   // one IEEE division per row and step instead of nine (<= 1.5 ulp from f / std, scorenet.py:217)
-#pragma unroll
-            for (int c = 0; c < 9; ++c) {
-                gr[c] = (f[c] + sOw[9 * 256 + c]) * inv_std;
-                n2 = fmaf(gr[c], gr[c], n2);
-            }
-            // ---- batch-mean gradient norm = ONE 64-bit word per step: the leader of every tile adds
-            //          (1 << 58 | poisoned << 52 | tile sum as 32.20 fixed point)
-            //      with a single relaxed RED; thread 0 of every CTA polls the word until the arrival count reaches n_tiles and then
-            //      holds the count AND the sum.  Integer addition is associative, so the total is independent of arrival order
-            //      (bitwise reproducible, identical in every CTA) and exact to 2^-20 per tile; no payload travels beside the word, so
-            //      no release/acquire pair and no second round trip for the partials.  (Measured predecessors: partial array +
-            //      RED.release counter + acquire poll + __ldcg of the partials, 2.8 k + 0.9 k cycles per step; per-warp tagged words
-            //      polled by every warp 8.2 k; tagged tile sums polled by one warp per CTA 4.4 k.)  A tile whose sum is NaN or
-            //      >= 2^26 marks the word poisoned and the step's norm becomes NaN, as it would be (or diverge) in the reference.
-            if (leader) {
-                const float wsum = warp_sum(valid ? sqrtf(n2) : 0.f);
-                if (lane == 0) s_red[q] = wsum;
-                named_bar_sync(2, 128);
-                if (tid == 0) {
-                    if (ds) ds[14] = clock64();
-                    const float tile_sum = (s_red[0] + s_red[1]) + (s_red[2] + s_red[3]);
-                    const bool ok = tile_sum >= 0.f && tile_sum < 67108864.f;                  // false for NaN
-                    const unsigned long long fx = ok ? __float2ull_rn(tile_sum * 1048576.f) : 0ull;
-                    red_relaxed_add_u64(p.acc + step, (1ull << 58) | (ok ? 0ull : (1ull << 52)) | fx);
-                }
-            }
-            if (tid == 0) {
-                unsigned long long v;
-                do {
-                    v = ld_relaxed_u64(p.acc + step);
-                } while ((unsigned)(v >> 58) < (unsigned)n_tiles);
-                const bool poisoned = ((v >> 52) & 63ull) != 0ull;
-                s_red[4] = poisoned ? __int_as_float(0x7fc00000) : (float)((double)(v & ((1ull << 52) - 1ull)) * (1.0 / 1048576.0));
-                if (ds) ds[15] = clock64();
-            }
-            named_bar_sync(2, 128);
-            if (ds) ds[12] = clock64();
-            const float tot = s_red[4];
-            const float grad_norm = tot / (float)p.R;
-            const PcStepConsts sc = pc_step_consts(grad_norm, snr_norm, sigma, step_size, sqrt_step);
-            if (valid) {
-                float m[9];
-#pragma unroll
-                for (int c = 0; c < 9; ++c) x[c] = (x[c] + sc.ls * gr[c]) + sc.sq2ls * z1[c];           // corrector (samplers.py:132)
+            if constexpr (kOde) {
+                // ======================= RK45 with SciPy's controller (samplers.py:178-227, scipy/integrate/_ivp) =======================
+                // k = f(t, x) as ode_func returns it (samplers.py:189-198): score in fp32, f = 0 - fp32(0.5 g^2) * score in fp32
+                // (NumPy-1.23 value-based casting), g = float64(sigma_fp32) * sqrt(2 ln 5000)
+                double kc[9];
                 {
-                    const float n1 = sqrtf(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);                    // (:142-143), no eps
-                    const float n3 = sqrtf(x[3] * x[3] + x[4] * x[4] + x[5] * x[5]);
-                    x[0] /= n1; x[1] /= n1; x[2] /= n1;
-                    x[3] /= n3; x[4] /= n3; x[5] /= n3;
+                    const double gd = (double)sigma * 4.12727348049926;
+                    const float coef = (float)(0.5 * gd * gd);
+#pragma unroll
+                    for (int c = 0; c < 9; ++c) kc[c] = valid ? (double)(0.0f - coef * ((f[c] + sOw[9 * 256 + c]) / stdv)) : 0.0;
                 }
+                ++nfev;
+                bool boundary = false, finished = false;
+                double xn[9];                                     // input of the next evaluation (float64, rounded to fp32 on publication)
+                // start one attempt of a step from (t_cur, y, K0): RungeKutta._step_impl, rk.py; returns false when the step size underflows
+                auto begin_attempt = [&]() -> bool {
+                    if (h_abs < min_step) {
+                        status = -1;
+                        return false;
+                    }
+                    h = h_abs * direction;
+                    t_next = t_cur + h;
+                    if (direction * (t_next - t_end) > 0) t_next = t_end;
+                    h = t_next - t_cur;
+                    h_abs = fabs(h);
 #pragma unroll
-                for (int c = 0; c < 9; ++c) m[c] = x[c] + (0.0f - sc.g2 * gr[c]) * sc.step_size;        // predictor mean (:147-148), sign as written
+                    for (int c = 0; c < 9; ++c) {
+                        const double k0 = valid ? __ldcg(Kmine + c) : 0.0;
+                        xn[c] = sY[c * 128 + r] + (k0 * kRkA[1][0]) * h;
+                    }
+                    if (tid == 0) {
+                        for (int j = 1; j < 6; ++j) s_times[j - 1] = (float)(t_cur + kRkC[j] * h);
+                        s_times[5] = (float)(t_cur + h);
+                        s_gn = 6;
+                    }
+                    phase = kPhAttempt;
+                    st = 1;
+                    return true;
+                };
+                auto begin_step = [&]() {                        // the outer `while` of solve_ivp / RK45.step
+                    min_step = 10.0 * fabs(nextafter(t_cur, direction * INFINITY) - t_cur);
+                    if (h_abs < min_step) h_abs = min_step;
+                    rejected = false;
+                };
+                auto begin_denoise = [&]() {                     // samplers.py:209-218: one more score evaluation at t = eps
 #pragma unroll
-                for (int c = 0; c < 9; ++c) x[c] = m[c] + (sc.g * sc.sqrt_step) * z2[c];                // (:149)
-                gram_schmidt6(x);                                                                        // (:152)
+                    for (int c = 0; c < 9; ++c) xn[c] = sY[c * 128 + r];
+                    if (tid == 0) {
+                        s_times[0] = kSamplingEps;
+                        s_gn = 1;
+                        st_volatile_shared(&s_allowed, step + 2);     // this evaluation and the denoise one (already so after an attempt)
+                        st_volatile_shared(&s_final, 1);
+                    }
+                    phase = kPhDenoise;
+                };
+                if (phase == kPhF0) {
+                    // ---- select_initial_step (scipy/integrate/_ivp/common.py), first half
+                    double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+                    for (int c = 0; c < 9; ++c) {
+                        const double yv = sY[c * 128 + r], sc = atol + fabs(yv) * rtol;
+                        const double uu = yv / sc, vv = kc[c] / sc;
+                        a0 += uu * uu;
+                        a1 += vv * vv;
+                        if (valid) __stcg(Kmine + c, kc[c]);                          // K0 = f0
+                    }
+                    double A0, A1;
+                    grid_sum2(a0, a1, A0, A1);
+                    const double d0 = sqrt(A0 / n_total);
+                    d1 = sqrt(A1 / n_total);
+                    h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
+                    h0 = fmin(h0, fabs(t_end - t_cur));
+#pragma unroll
+                    for (int c = 0; c < 9; ++c) xn[c] = sY[c * 128 + r] + h0 * direction * kc[c];
+                    if (tid == 0) {
+                        s_times[0] = (float)(t_cur + h0 * direction);
+                        s_gn = 1;
+                    }
+                    phase = kPhF1;
+                    boundary = true;
+                } else if (phase == kPhF1) {
+                    // ---- select_initial_step, second half: d2 from f1 - f0, then the first attempt
+                    double a2 = 0.0;
+#pragma unroll
+                    for (int c = 0; c < 9; ++c) {
+                        const double yv = sY[c * 128 + r], sc = atol + fabs(yv) * rtol;
+                        const double k0 = valid ? __ldcg(Kmine + c) : 0.0;
+                        const double ww = (kc[c] - k0) / sc;
+                        a2 += ww * ww;
+                    }
+                    double A2, unused;
+                    grid_sum2(a2, 0.0, A2, unused);
+                    const double d2 = sqrt(A2 / n_total) / h0;
+                    double h1;
+                    if (d1 <= 1e-15 && d2 <= 1e-15) h1 = fmax(1e-6, h0 * 1e-3);
+                    else h1 = pow(0.01 / fmax(d1, d2), 1.0 / 5.0);
+                    h_abs = fmin(fmin(100.0 * h0, h1), fabs(t_end - t_cur));
+                    begin_step();
+                    if (!begin_attempt()) begin_denoise();
+                    boundary = true;
+                } else if (phase == kPhAttempt) {
+                    if (valid) {
+#pragma unroll
+                        for (int c = 0; c < 9; ++c) __stcg(Kmine + (size_t)st * kst + c, kc[c]);     // K[st]
+                    }
+                    if (st < 6) {
+                        // next stage input: y + h * sum_j a[st+1][j] K_j for st < 5, the 5th-order solution y_new (b weights) for st == 5
+#pragma unroll
+                        for (int c = 0; c < 9; ++c) {
+                            double dy = 0.0;
+                            for (int j = 0; j < st; ++j) {
+                                const double kj = valid ? __ldcg(Kmine + (size_t)j * kst + c) : 0.0;
+                                dy += kj * (st < 5 ? kRkA[st + 1][j] : kRkB[j]);
+                            }
+                            dy += kc[c] * (st < 5 ? kRkA[st + 1][st] : kRkB[st]);
+                            xn[c] = st < 5 ? sY[c * 128 + r] + dy * h : sY[c * 128 + r] + h * dy;
+                            if (st == 5) sYn[c * 128 + r] = xn[c];
+                        }
+                        ++st;
+                    } else {
+                        // ---- error estimate over the WHOLE batch (one controller, samplers.py:205 / rk.py _estimate_error_norm)
+                        double ae = 0.0;
+#pragma unroll
+                        for (int c = 0; c < 9; ++c) {
+                            double err = 0.0;
+                            for (int j = 0; j < 6; ++j) {
+                                const double kj = valid ? __ldcg(Kmine + (size_t)j * kst + c) : 0.0;
+                                err += kj * kRkE[j];
+                            }
+                            err += kc[c] * kRkE[6];
+                            const double sc = atol + fmax(fabs(sY[c * 128 + r]), fabs(sYn[c * 128 + r])) * rtol;
+                            const double ww = err * h / sc;
+                            ae += ww * ww;
+                        }
+                        double AE, unused;
+                        grid_sum2(ae, 0.0, AE, unused);
+                        const double error_norm = sqrt(AE / n_total);
+                        const double SAFETY = 0.9, MIN_FACTOR = 0.2, MAX_FACTOR = 10.0, ERR_EXP = -1.0 / 5.0;
+                        bool go_on;
+                        if (error_norm < 1.0) {
+                            double factor = error_norm == 0.0 ? MAX_FACTOR : fmin(MAX_FACTOR, SAFETY * pow(error_norm, ERR_EXP));
+                            if (rejected) factor = fmin(1.0, factor);
+                            h_abs *= factor;
+                            ++n_acc;
+                            // accept: y <- y_new, K0 <- K6 = f_new (FSAL), t <- t + h clipped to the bound
+#pragma unroll
+                            for (int c = 0; c < 9; ++c) {
+                                sY[c * 128 + r] = sYn[c * 128 + r];
+                                if (valid) __stcg(Kmine + c, kc[c]);
+                            }
+                            t_cur = t_next;
+                            go_on = direction * (t_cur - t_end) < 0;
+                            if (go_on) begin_step();
+                        } else {
+                            h_abs *= fmax(MIN_FACTOR, SAFETY * pow(error_norm, ERR_EXP));
+                            rejected = true;
+                            ++n_rej;
+                            go_on = true;
+                        }
+                        if (go_on && begin_attempt()) {
+                            if (tid == 0) st_volatile_shared(&s_allowed, ld_volatile_shared(&s_allowed) + 6);
+                        } else {
+                            begin_denoise();
+                        }
+                        boundary = true;
+                    }
+                } else {
+                    // ---- denoise (samplers.py:209-218), normalize_rotation in float64 (:225), + pts_center (:226)
+                    double v[9];
+                    {
+                        const float g = sigma * kGCoef, g2 = g * g;
+                        const double dt = od.denoise_steps > 0 ? (1.0 - 1e-5) / (double)od.denoise_steps : 0.0;
+#pragma unroll
+                        for (int c = 0; c < 9; ++c) {
+                            const float drift = 0.0f - g2 * ((f[c] + sOw[9 * 256 + c]) / stdv);
+                            v[c] = sY[c * 128 + r] + (double)drift * dt;
+                        }
+                    }
+                    if (leader && valid) {
+                        const double n1 = fmax(sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]), 1e-12);
+                        const double b0 = v[0] / n1, b1 = v[1] / n1, b2 = v[2] / n1;
+                        const double d = b0 * v[3] + b1 * v[4] + b2 * v[5];
+                        const double c0 = v[3] - d * b0, c1 = v[4] - d * b1, c2 = v[5] - d * b2;
+                        const double n2 = fmax(sqrt(c0 * c0 + c1 * c1 + c2 * c2), 1e-12);
+                        double *o = od.pose + (size_t)row * 9;
+                        o[0] = b0; o[1] = b1; o[2] = b2;
+                        o[3] = c0 / n2; o[4] = c1 / n2; o[5] = c2 / n2;
+                        const float *ctr = p.pts_center + (size_t)(row / p.K) * 3;
+#pragma unroll
+                        for (int c = 6; c < 9; ++c) o[c] = v[c] + (double)ctr[c - 6];
+                    }
+                    if (od.denoise_steps <= 0) --nfev;            // the reference skips this evaluation; we run it and drop its result
+                    if (od.stats && blockIdx.x == 0 && tid == 0) {
+                        od.stats[0] = nfev;
+                        od.stats[1] = n_acc;
+                        od.stats[2] = n_rej;
+                        od.stats[3] = status;
+                    }
+                    if (tid == 0) s_gn = 0;
+                    boundary = true;
+                    finished = true;
+                }
+                if (!finished) {
+#pragma unroll
+                    for (int c = 0; c < 9; ++c) x[c] = (float)xn[c];
+                    publish_x();                                  // the MMA warp starts on layer 0 while the time biases are refreshed
+                }
+                if (!boundary) {
+                    ++gi;
+                    continue;
+                }
+                named_bar_sync(4, 256);
+                gn = s_gn;
+                gi = 0;
+                if (gn == 0) break;
+                if (gn == 6) time_biases(std::integral_constant<int, 6>{});
+                else time_biases(std::integral_constant<int, 1>{});
+                continue;
+            } else {
+                // ---- every rank: score, batch-mean gradient norm (published by the leaders), update — redundantly, bit-identically ----
+                float gr[9], n2 = 0.f;
+                const float inv_std = 1.0f / stdv;   // one IEEE division per row and step instead of nine (<= 1.5 ulp from f / std, scorenet.py:217)
+#pragma unroll
+                for (int c = 0; c < 9; ++c) {
+                    gr[c] = (f[c] + sOw[9 * 256 + c]) * inv_std;
+                    n2 = fmaf(gr[c], gr[c], n2);
+                }
+                // ---- batch-mean gradient norm = ONE 64-bit word per step: the leader of every tile adds
+                //          (1 << 58 | poisoned << 52 | tile sum as 32.20 fixed point)
+                //      with a single relaxed RED; thread 0 of every CTA polls the word until the arrival count reaches n_tiles and then
+                //      holds the count AND the sum.  Integer addition is associative, so the total is independent of arrival order
+                //      (bitwise reproducible, identical in every CTA) and exact to 2^-20 per tile; no payload travels beside the word, so
+                //      no release/acquire pair and no second round trip for the partials.  (Measured predecessors: partial array +
+                //      RED.release counter + acquire poll + __ldcg of the partials, 2.8 k + 0.9 k cycles per step; per-warp tagged words
+                //      polled by every warp 8.2 k; tagged tile sums polled by one warp per CTA 4.4 k.)  A tile whose sum is NaN or
+                //      >= 2^26 marks the word poisoned and the step's norm becomes NaN, as it would be (or diverge) in the reference.
                 if (leader) {
-                    const float *ctr = p.pts_center + (size_t)(row / p.K) * 3;
-                    if (p.process) {
-                        float *dst = p.process + ((size_t)row * p.T + step) * 9;
-#pragma unroll
-                        for (int c = 0; c < 9; ++c) dst[c] = x[c] + (c >= 6 ? ctr[c - 6] : 0.f);
-                    }
-                    if (step == p.T - 1) {
-#pragma unroll
-                        for (int c = 6; c < 9; ++c) m[c] += ctr[c - 6];
-                        gram_schmidt6(m);
-#pragma unroll
-                        for (int c = 0; c < 9; ++c) p.mean_x[(size_t)row * 9 + c] = m[c];
+                    const float wsum = warp_sum(valid ? sqrtf(n2) : 0.f);
+                    if (lane == 0) s_red[q] = wsum;
+                    named_bar_sync(2, 128);
+                    if (tid == 0) {
+                        if (ds) ds[14] = clock64();
+                        const float tile_sum = (s_red[0] + s_red[1]) + (s_red[2] + s_red[3]);
+                        const bool ok = tile_sum >= 0.f && tile_sum < 67108864.f;                  // false for NaN
+                        const unsigned long long fx = ok ? __float2ull_rn(tile_sum * 1048576.f) : 0ull;
+                        red_relaxed_add_u64(p.acc + step, (1ull << 58) | (ok ? 0ull : (1ull << 52)) | fx);
                     }
                 }
+                if (tid == 0) {
+                    unsigned long long v;
+                    do {
+                        v = ld_relaxed_u64(p.acc + step);
+                    } while ((unsigned)(v >> 58) < (unsigned)n_tiles);
+                    const bool poisoned = ((v >> 52) & 63ull) != 0ull;
+                    s_red[4] = poisoned ? __int_as_float(0x7fc00000) : (float)((double)(v & ((1ull << 52) - 1ull)) * (1.0 / 1048576.0));
+                    if (ds) ds[15] = clock64();
+                }
+                named_bar_sync(2, 128);
+                if (ds) ds[12] = clock64();
+                const float tot = s_red[4];
+                const float grad_norm = tot / (float)p.R;
+                const PcStepConsts sc = pc_step_consts(grad_norm, snr_norm, sigma, step_size, sqrt_step);
+                if (valid) {
+                    float m[9];
+#pragma unroll
+                    for (int c = 0; c < 9; ++c) x[c] = (x[c] + sc.ls * gr[c]) + sc.sq2ls * z1[c];           // corrector (samplers.py:132)
+                    {
+                        const float n1 = sqrtf(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);                    // (:142-143), no eps
+                        const float n3 = sqrtf(x[3] * x[3] + x[4] * x[4] + x[5] * x[5]);
+                        x[0] /= n1; x[1] /= n1; x[2] /= n1;
+                        x[3] /= n3; x[4] /= n3; x[5] /= n3;
+                    }
+#pragma unroll
+                    for (int c = 0; c < 9; ++c) m[c] = x[c] + (0.0f - sc.g2 * gr[c]) * sc.step_size;        // predictor mean (:147-148), sign as written
+#pragma unroll
+                    for (int c = 0; c < 9; ++c) x[c] = m[c] + (sc.g * sc.sqrt_step) * z2[c];                // (:149)
+                    gram_schmidt6(x);                                                                        // (:152)
+                    if (leader) {
+                        const float *ctr = p.pts_center + (size_t)(row / p.K) * 3;
+                        if (p.process) {
+                            float *dst = p.process + ((size_t)row * p.T + step) * 9;
+#pragma unroll
+                            for (int c = 0; c < 9; ++c) dst[c] = x[c] + (c >= 6 ? ctr[c - 6] : 0.f);
+                        }
+                        if (step == p.T - 1) {
+#pragma unroll
+                            for (int c = 6; c < 9; ++c) m[c] += ctr[c - 6];
+                            gram_schmidt6(m);
+#pragma unroll
+                            for (int c = 0; c < 9; ++c) p.mean_x[(size_t)row * 9 + c] = m[c];
+                        }
+                    }
+                }
+                publish_x();
+                if (ds) ds[13] = clock64();
             }
-            publish_x();
-            if (ds) ds[13] = clock64();
         }
     }
     tc_fence_before_sync();
     __syncthreads();
     cluster_sync_all();          // nobody leaves while a team mate may still write into its mailbox
     if (warp == kTcRowWarps) tmem_dealloc(tmem_base, 512);
+}
+
+__global__ void __launch_bounds__(kTcThreads, 1)   // 10 warps are allocated as 12 (granularity 4): <= 168 registers per thread
+tc_pc_sampler_kernel(TcPcParams tp) {
+    tc_sampler_body<false>(tp);
+}
+__global__ void __launch_bounds__(kTcThreads, 1)
+tc_ode_sampler_kernel(TcPcParams tp) {
+    tc_sampler_body<true>(tp);
+}
+
+// cluster (4 CTAs = one tile team, DSMEM) + cooperative (grid barrier => all CTAs must be co-resident) launch of either kernel
+static int launch_tc_sampler(void (*kernel)(TcPcParams), const char *what, const TcPcParams &tp, int n_tiles, uint32_t smem_bytes,
+                             cudaStream_t st) {
+    GPB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(n_tiles * kTeam);
+    cfg.blockDim = dim3(kTcThreads);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attrs[2];
+    attrs[0].id = cudaLaunchAttributeClusterDimension;
+    attrs[0].val.clusterDim.x = kTeam;
+    attrs[0].val.clusterDim.y = 1;
+    attrs[0].val.clusterDim.z = 1;
+    attrs[1].id = cudaLaunchAttributeCooperative;
+    attrs[1].val.cooperative = 1;
+    cfg.attrs = attrs;
+    // Nsight Compute cannot launch a kernel that is both clustered and cooperative (every replay mode ends in LaunchFailed,
+    // profiles/README): GPB_PROFILE_NO_COOP=1 drops the cooperative attribute for profiling runs only.  Co-residency, which the
+    // grid barrier needs, is still established by the occupancy check below (1 CTA per SM, grid <= #SMs, idle device).
+    const char *no_coop = getenv("GPB_PROFILE_NO_COOP");
+    cfg.numAttrs = (no_coop && no_coop[0] == '1') ? 1 : 2;
+    int max_clusters = 0;
+    GPB_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, kernel, &cfg));
+    GPB_REQUIRE(max_clusters >= n_tiles, "%s: only %d co-resident 4-CTA clusters fit, %d needed; split the batch", what, max_clusters, n_tiles);
+    GPB_CUDA(cudaLaunchKernelEx(&cfg, kernel, tp));
+    g_launches.fetch_add(1);
+    return GPB_OK;
 }
 
 }  // namespace gpb
@@ -670,32 +1145,43 @@ extern "C" int gpb_sample_pc_tc_dbg(const float *x0, int R, int K, int num_steps
     p.mean_x = mean_x; p.process = process; p.tiles_per_cta = 1; p.dbg = dbg; p.dbg_cta = dbg ? dbg_cta_sel : 0;
     tp.wstream = reinterpret_cast<const uint8_t *>(tc_stream);
 
-    GPB_CUDA(cudaFuncSetAttribute(tc_pc_sampler_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes));
-    // cluster (4 CTAs = one tile team, DSMEM) + cooperative (grid barrier => all CTAs must be co-resident)
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(kTcThreads);
-    cfg.dynamicSmemBytes = kTcSmemBytes;
-    cfg.stream = st;
-    cudaLaunchAttribute attrs[2];
-    attrs[0].id = cudaLaunchAttributeClusterDimension;
-    attrs[0].val.clusterDim.x = kTeam;
-    attrs[0].val.clusterDim.y = 1;
-    attrs[0].val.clusterDim.z = 1;
-    attrs[1].id = cudaLaunchAttributeCooperative;
-    attrs[1].val.cooperative = 1;
-    cfg.attrs = attrs;
-    // Nsight Compute cannot launch a kernel that is both clustered and cooperative (every replay mode ends in LaunchFailed,
-    // profiles/README): GPB_PROFILE_NO_COOP=1 drops the cooperative attribute for profiling runs only.  Co-residency, which the
-    // grid barrier needs, is still established by the occupancy check below (1 CTA per SM, grid <= #SMs, idle device).
-    const char *no_coop = getenv("GPB_PROFILE_NO_COOP");
-    cfg.numAttrs = (no_coop && no_coop[0] == '1') ? 1 : 2;
-    int max_clusters = 0;
-    GPB_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, tc_pc_sampler_kernel, &cfg));
-    GPB_REQUIRE(max_clusters >= n_tiles, "sample_pc_tc: only %d co-resident 4-CTA clusters fit, %d needed; split the batch", max_clusters, n_tiles);
-    GPB_CUDA(cudaLaunchKernelEx(&cfg, tc_pc_sampler_kernel, tp));
-    g_launches.fetch_add(1);
-    return GPB_OK;
+    return launch_tc_sampler(tc_pc_sampler_kernel, "sample_pc_tc", tp, n_tiles, kTcSmemBytes, st);
+}
+
+extern "C" int gpb_sample_ode_tc(const float *x0, int R, int K, float T0, float rtol, float atol, int denoise_steps,
+                                 const float *obj_bias, const float *W, const void *tc_stream, const float *pts_center, double *pose,
+                                 int *stats, void *workspace, size_t workspace_bytes, void *stream) {
+    GPB_REQUIRE(R >= 0 && K >= 1, "sample_ode_tc: need R >= 0, K >= 1");
+    if (R == 0) return GPB_OK;
+    GPB_REQUIRE(x0 && obj_bias && W && tc_stream && pts_center && pose && workspace, "sample_ode_tc: NULL buffer");
+    GPB_REQUIRE(T0 > 1e-5f && rtol > 0 && atol > 0, "sample_ode_tc: need T0 > eps and positive tolerances");
+    GPB_REQUIRE(127 / K + 2 <= kMaxObjPerTile, "sample_ode_tc: K=%d too small (a 128-row tile may span at most %d objects); "
+                "use gpb_sample_ode", K, kMaxObjPerTile);
+    GPB_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0 && (reinterpret_cast<uintptr_t>(tc_stream) & 15) == 0,
+                "sample_ode_tc: workspace must be 256-byte and the weight stream 16-byte aligned");
+    SamplerWs w = carve_sampler(workspace, R, 1);
+    if (workspace_bytes < w.bytes) {
+        set_error("sample_ode_tc: workspace %zu < required %zu bytes", workspace_bytes, w.bytes);
+        return GPB_EWORKSPACE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    int dev = 0, sms = 0;
+    GPB_CUDA(cudaGetDevice(&dev));
+    GPB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int n_tiles = (R + kTcRows - 1) / kTcRows;
+    GPB_REQUIRE(n_tiles * kTeam <= sms && n_tiles * kTeam <= 160, "sample_ode_tc: R=%d needs %d co-resident CTAs but the device has %d SMs; "
+                "split the batch", R, n_tiles * kTeam, sms);
+    GPB_CUDA(cudaMemsetAsync(w.barrier, 0, 256, st));
+
+    TcPcParams tp{};
+    PcParams &p = tp.pc;
+    p.x0 = x0; p.R = R; p.K = K; p.T = 0;
+    p.obj_bias = obj_bias; p.W = W; p.pts_center = pts_center; p.barrier = w.barrier; p.tiles_per_cta = 1;
+    tp.wstream = reinterpret_cast<const uint8_t *>(tc_stream);
+    tp.ode.T0 = T0; tp.ode.rtol = rtol; tp.ode.atol = atol; tp.ode.denoise_steps = denoise_steps;
+    tp.ode.Kst = w.Kst; tp.ode.partial = reinterpret_cast<double *>(w.partial); tp.ode.tb_cta = w.tb_cta;
+    tp.ode.pose = pose; tp.ode.stats = stats;
+    return launch_tc_sampler(tc_ode_sampler_kernel, "sample_ode_tc", tp, n_tiles, kTcSmemBytesOde, st);
 }
 
 extern "C" int gpb_sample_pc_tc(const float *x0, int R, int K, int num_steps, float snr, const float *obj_bias, const float *W,

@@ -181,16 +181,25 @@ class Engine:
 
     # ---- a10: ODE sampler --------------------------------------------------------------------------------
     def sample_ode(self, obj_bias: torch.Tensor, pts_center: torch.Tensor, x0: torch.Tensor, K: int, T0: float = 1.0,
-                   rtol: float = 1e-5, atol: float = 1e-5, denoise_steps: int = 1000):
+                   rtol: float = 1e-5, atol: float = 1e-5, denoise_steps: int = 1000, precision: str = "fp32"):
+        """cond_ode_sampler (samplers.py:163-227): RK45 with SciPy's controller on device -> (pose [R,9] float64, stats [4]).
+        precision 'fp32' = FFMA parity kernel; 'bf16x3' = tcgen05 kernel; 'auto' = tensor cores when the shape allows."""
         R = x0.shape[0]
+        if precision == "auto":
+            precision = "bf16x3" if self.tc_supported(R, K) else "fp32"
+        if precision not in ("fp32", "bf16x3"):
+            raise lib.GenPoseB200Error(f"sample_ode: unknown precision {precision!r}")
         L = lib.load()
         ws = self._workspace("samp", L.gpb_sampler_workspace_bytes(R, 1))
         pose = torch.empty(R, 9, dtype=torch.float64, device=self.device)
         stats = torch.zeros(4, dtype=torch.int32, device=self.device)
-        lib.check(L.gpb_sample_ode(
-            _chk(x0, torch.float32, "x0"), R, K, float(T0), float(rtol), float(atol), int(denoise_steps),
-            _chk(obj_bias, torch.float32, "obj_bias"), self.trunk_w.data_ptr(), _chk(pts_center, torch.float32, "pts_center"),
-            pose.data_ptr(), stats.data_ptr(), ws.data_ptr(), ws.numel(), _stream()), "sample_ode")
+        head = (_chk(x0, torch.float32, "x0"), R, K, float(T0), float(rtol), float(atol), int(denoise_steps),
+                _chk(obj_bias, torch.float32, "obj_bias"), self.trunk_w.data_ptr())
+        tail = (_chk(pts_center, torch.float32, "pts_center"), pose.data_ptr(), stats.data_ptr(), ws.data_ptr(), ws.numel(), _stream())
+        if precision == "bf16x3":
+            lib.check(L.gpb_sample_ode_tc(*head, self.trunk_tc.data_ptr(), *tail), "sample_ode_tc")
+        else:
+            lib.check(L.gpb_sample_ode(*head, *tail), "sample_ode")
         return pose, stats
 
     # ---- a12: energy ------------------------------------------------------------------------------------------

@@ -133,7 +133,7 @@ class GFObjectPose:
             x0 = prior if init_x is None else init_x + prior
             num_steps = self.cfg.sampling_steps
             pose, stats = eng.sample_ode(ob, center, x0.float().contiguous(), repeat_num, T0=T0, rtol=1e-5, atol=1e-5,
-                                         denoise_steps=1000 if num_steps is None else num_steps)
+                                         denoise_steps=1000 if num_steps is None else num_steps, precision=self.precision)
             self.last_ode_stats = stats
             # in_process_sample: the reference returns SciPy's accepted steps; we return the final state only
             return (pose, pose.unsqueeze(1)) if return_process else (None, pose)

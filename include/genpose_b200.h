@@ -156,6 +156,14 @@ GPB_API int gpb_sample_ode(const float *x0, int R, int K, float T0, float rtol, 
                    const float *obj_bias, const float *trunk_weights, const float *pts_center, double *pose,
                    int *stats, void *workspace, size_t workspace_bytes, void *stream);
 
+/* gpb_sample_ode on the tensor cores: the same solver (same controller, float64 state, one error norm over the whole
+ * batch) with the score network's dense layers evaluated by tcgen05.mma (bf16x3 split, fp32 accumulation in tensor
+ * memory), four CTAs (one thread-block cluster) per 128-row tile as in gpb_sample_pc_tc.  tc_stream as there.
+ * Constraints: K >= 43, 4*ceil(R/128) <= #SMs; otherwise use gpb_sample_ode. */
+GPB_API int gpb_sample_ode_tc(const float *x0, int R, int K, float T0, float rtol, float atol, int denoise_steps,
+                      const float *obj_bias, const float *trunk_weights, const void *tc_stream, const float *pts_center,
+                      double *pose, int *stats, void *workspace, size_t workspace_bytes, void *stream);
+
 /* replaces PoseNet.get_energy's arithmetic after the encoder (networks/posenet_agent.py:508-523 ->
  * PoseEnergyNet.get_energy energynet.py:143-198, 'IP' decoupled): energy [B,K,2] = (rot, trans). */
 GPB_API int gpb_energy(const float *pose, int R, int K, float t, const float *obj_bias, const float *trunk_weights,

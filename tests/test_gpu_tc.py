@@ -101,3 +101,37 @@ def test_tc_sampler_philox_deterministic():
     c = eng.sample_pc(ob, data["pts_center"], x0, K, T, seed=5, precision="fp32")
     assert torch.equal(a, b)
     assert float((a - c).abs().max()) <= 1e-3
+
+
+@pytest.mark.parametrize("B,K,T0", [(3, 50, 0.55), (2, 64, 0.15), (64, 50, 0.55)])
+def test_tc_ode_sampler_against_oracle_and_fp32_kernel(B, K, T0):
+    """cond_ode_sampler on the tensor cores (gpb_sample_ode_tc): same RK45 controller as the FFMA kernel and the
+    oracle's SciPy port; poses within the ODE tolerance (adaptive stepping is reproducible to ~2e-4
+    relative), the same number of evaluations up to a couple of controller decisions."""
+    from genpose_b200 import ops
+    seed = 70 + B
+    sd = synth.make_state_dict(seed, kappa=0.3)
+    clouds = synth.make_clouds(B, seed)
+    sig = float(O.sigma_of_t(torch.tensor(T0)))
+    x0 = synth.make_prior_noise(B * K, seed, sigma=sig)
+    data = synth.batch_from_clouds(clouds)
+    eng = ops.Engine(sd)
+    ob = eng.object_bias(eng.encode(torch.from_numpy(clouds).cuda()))
+    cen = data["pts_center"].cuda()
+    p_tc, s_tc = eng.sample_ode(ob, cen, torch.from_numpy(x0).cuda(), K, T0=T0, precision="bf16x3")
+    p_32, s_32 = eng.sample_ode(ob, cen, torch.from_numpy(x0).cuda(), K, T0=T0, precision="fp32")
+    torch.cuda.synchronize()
+    s_tc, s_32 = s_tc.cpu().numpy(), s_32.cpu().numpy()
+    print(f"tc ode stats {s_tc.tolist()} fp32 ode stats {s_32.tolist()} max|diff| {float((p_tc - p_32).abs().max()):.3e}")
+    assert s_tc[3] == 0 and torch.isfinite(p_tc).all()
+    assert abs(int(s_tc[0]) - int(s_32[0])) <= 12
+    np.testing.assert_allclose(p_tc.cpu().numpy(), p_32.cpu().numpy(), rtol=2e-4, atol=1e-3)
+    if B * K <= 400:
+        feat = O.encode(sd, data["pts"])
+        rep = feat.unsqueeze(1).repeat(1, K, 1).view(B * K, -1)
+        cenr = data["pts_center"].unsqueeze(1).repeat(1, K, 1).view(B * K, -1)
+        ref = O.ode_sampler(sd, rep, cenr, torch.from_numpy(x0), T0=T0)
+        np.testing.assert_allclose(p_tc.cpu().numpy(), ref.numpy(), rtol=2e-4, atol=1e-3)
+    # bitwise reproducible run to run (fixed-order reductions, identical control flow in every CTA)
+    p_again, _ = eng.sample_ode(ob, cen, torch.from_numpy(x0).cuda(), K, T0=T0, precision="bf16x3")
+    assert torch.equal(p_tc, p_again)
