@@ -244,9 +244,8 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
             tc_fence_after_sync();
         };
         for (int step = 0; kOde || step < p.T; ++step) {
-            unsigned long long *ds = (!kOde && dbg_cta && lane == 0) ? p.dbg + ((size_t)p.T + step) * 16 : nullptr;
+            unsigned long long *ds = (dbg_cta && lane == 0 && step < p.T) ? p.dbg + ((size_t)p.T + step) * 16 : nullptr;   // ODE: T = recorded evaluations
             unsigned long long w_full = 0, w_a = 0, w_acc = 0, tq = 0, w_issue = 0;
-            unsigned long long u_full[4] = {0, 0, 0, 0}, u_a[4] = {0, 0, 0, 0}, u_issue[4] = {0, 0, 0, 0};   // per-unit split (profiling only)
             if (ds) ds[0] = clock64();
             // ---- layer 0: h1_pre = x . P1^T   (K = 16; x pieces x1,x2,x3 at A_hi[0,8),[8,16),[16,24); P1 hi|lo per unit)
             mbar_wait(&bar_x_ready, xr & 1u);
@@ -278,7 +277,6 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
             }
             // ---- units with K = 256: layer 1 (P2: two 128-column units) and this rank's head slice (128 + 64 columns) ----
             for (int unit = 0; unit < 4; ++unit) {
-                const unsigned long long f0 = w_full, a0 = w_a, i0 = w_issue;
                 if (ds) tq = clock64();
                 // Units 0 and 2 are the first consumers of a freshly written A operand (h1 / pf).  The row warps publish it in
                 // two halves (K columns [0,128) as soon as the first accumulator unit is converted, [128,256) after the second),
@@ -368,11 +366,6 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
                     it += 4u;
                 }
                 ++u;
-                if (ds) {
-                    u_full[unit] = w_full - f0;
-                    u_a[unit] = w_a - a0;
-                    u_issue[unit] = w_issue - i0;
-                }
             }
             if (ds) {
                 ds[7] = clock64();
@@ -380,12 +373,6 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
                 ds[9] = w_a;
                 ds[10] = w_acc;
                 ds[11] = w_issue;
-                ds[2] = u_full[0] | (u_a[0] << 32);
-                ds[5] = u_full[1] | (u_a[1] << 32);
-                ds[6] = u_full[2] | (u_a[2] << 32);
-                ds[12] = u_full[3] | (u_a[3] << 32);
-                ds[13] = u_issue[0] | (u_issue[1] << 32);
-                ds[14] = u_issue[2] | (u_issue[3] << 32);
             }
             if constexpr (kOde) {   // the flags were written before the x_ready arrival that released this evaluation
                 if (ld_volatile_shared(&s_final) && step + 1 == ld_volatile_shared(&s_allowed)) break;
@@ -441,11 +428,13 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
         // ================= ODE mode: helpers and solver state (dead code in the PC instantiation) =================
         const TcOdeParams &od = tp.ode;
         const int rt = tid;                                                   // 0..255 over the eight row warps
-        float *tb_mine = od.tb_cta + (size_t)blockIdx.x * 6 * 768;           // this CTA's [6][768] time biases
+        float *tb_mine = od.tb_cta + (size_t)blockIdx.x * 6 * 192;           // this CTA's [6][192] time biases (its head columns)
         double *sY = reinterpret_cast<double *>(smem + kOffOdeY);             // [9][128]
         double *sYn = sY + 9 * 128;                                           // [9][128]
-        // t_bias(t_j)[0:768] for the gn times in s_times (scorenet.py:63-64, :195; same operation order as compute_time_bias in
-        // scorenet.cu): all eight row warps, scratch = sFpart (free between the team exchange and the next head epilogue)
+        // t_bias(t_j) for the gn times in s_times (scorenet.py:63-64, :195; same operation order as compute_time_bias in scorenet.cu),
+        // restricted to THIS rank's 192 head columns [n_lo, n_lo + 192) — the only ones its head epilogue reads.  All eight row
+        // warps; scratch = sFpart (free between the team exchange and the next head epilogue).  The weights come from L2: every
+        // thread keeps a batch of 32 loads in flight while it works on the previous batch.
         auto time_biases = [&](auto GN) {
             constexpr int gn = decltype(GN)::value;
             float *tf = sFpart, *te = sFpart + 768;
@@ -456,54 +445,83 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
                 tf[j * 128 + 64 + k] = cosf(xp);
             }
             named_bar_sync(5, 256);
-            {
-                constexpr int per = (gn + 1) / 2;                             // times per thread half
+            {   // te[j][n] = relu(L_t . [sin | cos] + b): column n = rt & 127, times [j0, j0 + per)
+                constexpr int per = (gn + 1) / 2;
                 const int n = rt & 127, j0 = (rt >> 7) * per;
+                const bool act = j0 < gn;
                 float acc[per];
                 const float b = W[TL::t_b + n];
 #pragma unroll
                 for (int jj = 0; jj < per; ++jj) acc[jj] = b;
                 const float *w = W + TL::t_w + n;
-#pragma unroll 4
-                for (int k = 0; k < 128; ++k) {
-                    const float wk = __ldg(w + k * 128);
+                const float *tfj = tf + (act ? j0 : 0) * 128;
+                float wa[32], wb[32];
 #pragma unroll
-                    for (int jj = 0; jj < per; ++jj) acc[jj] = fmaf(tf[(j0 + jj < gn ? j0 + jj : 0) * 128 + k], wk, acc[jj]);
+                for (int k = 0; k < 32; ++k) wa[k] = __ldg(w + k * 128);
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+#pragma unroll
+                    for (int k = 0; k < 32; ++k) wb[k] = __ldg(w + (64 * half + 32 + k) * 128);
+#pragma unroll
+                    for (int k = 0; k < 32; ++k)
+#pragma unroll
+                        for (int jj = 0; jj < per; ++jj) acc[jj] = fmaf(tfj[(j0 + jj < gn ? jj : 0) * 128 + 64 * half + k], wa[k], acc[jj]);
+                    if (half == 0) {
+#pragma unroll
+                        for (int k = 0; k < 32; ++k) wa[k] = __ldg(w + (64 + k) * 128);
+                    }
+#pragma unroll
+                    for (int k = 0; k < 32; ++k)
+#pragma unroll
+                        for (int jj = 0; jj < per; ++jj) acc[jj] = fmaf(tfj[(j0 + jj < gn ? jj : 0) * 128 + 64 * half + 32 + k], wb[k], acc[jj]);
                 }
 #pragma unroll
                 for (int jj = 0; jj < per; ++jj)
                     if (j0 + jj < gn) te[(j0 + jj) * 128 + n] = fmaxf(acc[jj], 0.f);
             }
             named_bar_sync(5, 256);
-            {
-                float acc[3][gn];
+            if (rt < 192) {   // tb[j][n_lo + rt] = A_t[:, n] . te[j]
+                float acc[gn];
 #pragma unroll
-                for (int m = 0; m < 3; ++m)
+                for (int j = 0; j < gn; ++j) acc[j] = 0.f;
+                const float *w = W + TL::a_t + n_lo + rt;
+                float wa[32], wb[32];
 #pragma unroll
-                    for (int j = 0; j < gn; ++j) acc[m][j] = 0.f;
-                const float *w = W + TL::a_t + rt;
-#pragma unroll 2
-                for (int k = 0; k < 128; ++k) {
-                    const float w0 = __ldg(w + k * 768), w1 = __ldg(w + k * 768 + 256), w2 = __ldg(w + k * 768 + 512);
+                for (int k = 0; k < 32; ++k) wa[k] = __ldg(w + k * 768);
 #pragma unroll
-                    for (int j = 0; j < gn; ++j) {
-                        const float e = te[j * 128 + k];
-                        acc[0][j] = fmaf(e, w0, acc[0][j]);
-                        acc[1][j] = fmaf(e, w1, acc[1][j]);
-                        acc[2][j] = fmaf(e, w2, acc[2][j]);
+                for (int half = 0; half < 2; ++half) {
+#pragma unroll
+                    for (int k = 0; k < 32; ++k) wb[k] = __ldg(w + (64 * half + 32 + k) * 768);
+#pragma unroll
+                    for (int k4 = 0; k4 < 32; k4 += 4)
+#pragma unroll
+                        for (int j = 0; j < gn; ++j) {
+                            const float4 e = *reinterpret_cast<const float4 *>(te + j * 128 + 64 * half + k4);
+                            acc[j] = fmaf(e.w, wa[k4 + 3], fmaf(e.z, wa[k4 + 2], fmaf(e.y, wa[k4 + 1], fmaf(e.x, wa[k4], acc[j]))));
+                        }
+                    if (half == 0) {
+#pragma unroll
+                        for (int k = 0; k < 32; ++k) wa[k] = __ldg(w + (64 + k) * 768);
                     }
+#pragma unroll
+                    for (int k4 = 0; k4 < 32; k4 += 4)
+#pragma unroll
+                        for (int j = 0; j < gn; ++j) {
+                            const float4 e = *reinterpret_cast<const float4 *>(te + j * 128 + 64 * half + 32 + k4);
+                            acc[j] = fmaf(e.w, wb[k4 + 3], fmaf(e.z, wb[k4 + 2], fmaf(e.y, wb[k4 + 1], fmaf(e.x, wb[k4], acc[j]))));
+                        }
                 }
 #pragma unroll
-                for (int m = 0; m < 3; ++m)
-#pragma unroll
-                    for (int j = 0; j < gn; ++j) __stcg(tb_mine + j * 768 + rt + 256 * m, acc[m][j]);
+                for (int j = 0; j < gn; ++j) __stcg(tb_mine + j * 192 + rt, acc[j]);
             }
             named_bar_sync(5, 256);
         };
-        // (object bias + time bias of evaluation `gi` of the group) -> sObt, by `nthr` threads starting at thread `t0`
+        // (object bias + time bias of evaluation `gi` of the group) -> this rank's column slice of sObt, by `nthr` threads from `t0`
         auto fill_obt = [&](int gi, int t0, int nthr) {
-            for (int i = tid - t0; i < n_obj * 768; i += nthr)
-                sObt[i] = __ldg(p.obj_bias + (size_t)obj_lo * 768 + i) + __ldcg(tb_mine + gi * 768 + i % 768);
+            for (int i = tid - t0; i < n_obj * 192; i += nthr) {
+                const int o = i / 192, cc = n_lo + i % 192;
+                sObt[o * 768 + cc] = __ldg(p.obj_bias + (size_t)(obj_lo + o) * 768 + cc) + __ldcg(tb_mine + gi * 192 + i % 192);
+            }
         };
         // solver state, replicated bit-identically in every row thread of every rank (scipy/integrate/_ivp/rk.py, common.py)
         enum { kPhF0 = 0, kPhF1 = 1, kPhAttempt = 2, kPhDenoise = 3 };
@@ -513,8 +531,27 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
         const double t_end = 1e-5, direction = -1.0;                          // eps as a Python float; T0 > eps is checked by the host
         double t_cur = (double)od.T0, t_next = 0.0, h = 0.0, h_abs = 0.0, h0 = 0.0, d1 = 0.0, min_step = 0.0;
         const double rtol = (double)od.rtol, atol = (double)od.atol, n_total = (double)p.R * 9.0;
-        double *Kmine = od.Kst + ((size_t)rank * 7 * p.R + (valid ? row : 0)) * 9;   // stage j of this row: Kmine + j * R * 9
-        const size_t kst = (size_t)p.R * 9;
+        // stage derivatives K_j of this row: the reference's f is fp32 converted to float64 (samplers.py:198), so fp32 storage is
+        // exact; [rank][stage][row][12] floats = three 16-byte words per row and stage, private to this thread, L2-resident
+        float *Kmine = reinterpret_cast<float *>(od.Kst) + ((size_t)rank * 7 * p.R + (valid ? row : 0)) * 12;
+        const size_t kst = (size_t)p.R * 12;
+        auto store_k = [&](int stage, const double (&k)[9]) {
+            float4 *dst = reinterpret_cast<float4 *>(Kmine + (size_t)stage * kst);
+            __stcg(dst, make_float4((float)k[0], (float)k[1], (float)k[2], (float)k[3]));
+            __stcg(dst + 1, make_float4((float)k[4], (float)k[5], (float)k[6], (float)k[7]));
+            __stcg(dst + 2, make_float4((float)k[8], 0.f, 0.f, 0.f));
+        };
+        // all requested stages are fetched with volatile loads issued back to back (one L2 round trip for the lot; a plain load
+        // would be sunk into the select that consumes it and the stages would be fetched one after the other)
+        auto load_k = [&](int stage, float (&k)[12]) {
+            const float *src = Kmine + (size_t)stage * kst;
+#pragma unroll
+            for (int w4 = 0; w4 < 3; ++w4)
+                asm volatile("ld.global.cg.v4.f32 {%0, %1, %2, %3}, [%4];"
+                             : "=f"(k[4 * w4]), "=f"(k[4 * w4 + 1]), "=f"(k[4 * w4 + 2]), "=f"(k[4 * w4 + 3])
+                             : "l"(src + 4 * w4)
+                             : "memory");
+        };
         // two grid-wide float64 sums with ONE barrier; every CTA obtains the identical fixed-order totals
         auto grid_sum2 = [&](double a, double b, double &A, double &B) {
             a = warp_sum_f64(valid ? a : 0.0);
@@ -525,22 +562,30 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
             }
             named_bar_sync(2, 128);
             bar_target += (unsigned)n_tiles;
-            if (tid == 0) {
-                if (leader) {
-                    double *dst = od.partial + ((size_t)slot * n_tiles + tile) * 2;
-                    __stcg(dst, (s_redd[0] + s_redd[2]) + (s_redd[4] + s_redd[6]));
-                    __stcg(dst + 1, (s_redd[1] + s_redd[3]) + (s_redd[5] + s_redd[7]));
-                    red_release_add_u32(p.barrier, 1u);
+            if (warp == 0) {
+                if (lane == 0) {
+                    if (leader) {
+                        double *dst = od.partial + ((size_t)slot * n_tiles + tile) * 2;
+                        __stcg(dst, (s_redd[0] + s_redd[2]) + (s_redd[4] + s_redd[6]));
+                        __stcg(dst + 1, (s_redd[1] + s_redd[3]) + (s_redd[5] + s_redd[7]));
+                        red_release_add_u32(p.barrier, 1u);
+                    }
+                    while (ld_acquire_u32(p.barrier) < bar_target) {
+                    }
                 }
-                while (ld_acquire_u32(p.barrier) < bar_target) {
-                }
+                __syncwarp();
+                // lanes fetch the per-tile partials in parallel (n_tiles < 64); fixed-shape shuffle tree => identical in every CTA
                 double ta = 0.0, tb = 0.0;
-                for (int i = 0; i < n_tiles; ++i) {
+                for (int i = lane; i < n_tiles; i += 32) {
                     ta += __ldcg(od.partial + ((size_t)slot * n_tiles + i) * 2);
                     tb += __ldcg(od.partial + ((size_t)slot * n_tiles + i) * 2 + 1);
                 }
-                s_redd[8] = ta;
-                s_redd[9] = tb;
+                ta = warp_sum_f64(ta);
+                tb = warp_sum_f64(tb);
+                if (lane == 0) {
+                    s_redd[8] = ta;
+                    s_redd[9] = tb;
+                }
             }
             named_bar_sync(2, 128);
             A = s_redd[8];
@@ -578,11 +623,16 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
         };
 
         for (int step = 0; kOde || step < p.T; ++step) {
-            unsigned long long *ds = (!kOde && dbg) ? p.dbg + (size_t)step * 16 : nullptr;
+            unsigned long long *ds = (dbg && step < p.T) ? p.dbg + (size_t)step * 16 : nullptr;
             if (ds) ds[0] = clock64();
             const float t = kOde ? s_times[gi] : p.ts[step];
             const float sigma = sigma_of_t(t);
             const float stdv = sigma + 1e-7f;
+            float ode_coef = 0.f;                       // fp32(0.5 g^2), g = float64(sigma_fp32) * sqrt(2 ln 5000): off the critical path here
+            if constexpr (kOde) {
+                const double gd = (double)sigma * 4.12727348049926;
+                ode_coef = (float)(0.5 * gd * gd);
+            }
             // ---- layers 0 and 1: accumulator -> bias + ReLU -> bf16 hi/lo -> A operand in tensor memory ----
 #pragma unroll 1
             for (int layer = 0; layer < 2; ++layer) {
@@ -761,13 +811,11 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
                 // k = f(t, x) as ode_func returns it (samplers.py:189-198): score in fp32, f = 0 - fp32(0.5 g^2) * score in fp32
                 // (NumPy-1.23 value-based casting), g = float64(sigma_fp32) * sqrt(2 ln 5000)
                 double kc[9];
-                {
-                    const double gd = (double)sigma * 4.12727348049926;
-                    const float coef = (float)(0.5 * gd * gd);
 #pragma unroll
-                    for (int c = 0; c < 9; ++c) kc[c] = valid ? (double)(0.0f - coef * ((f[c] + sOw[9 * 256 + c]) / stdv)) : 0.0;
-                }
+                for (int c = 0; c < 9; ++c) kc[c] = valid ? (double)(0.0f - ode_coef * ((f[c] + sOw[9 * 256 + c]) / stdv)) : 0.0;
                 ++nfev;
+                long long dbg_a = 0, dbg_b = 0;                   // profiling: after f -> k, after the stage combination
+                if (ds) dbg_a = -(long long)clock64();
                 bool boundary = false, finished = false;
                 double xn[9];                                     // input of the next evaluation (float64, rounded to fp32 on publication)
                 // start one attempt of a step from (t_cur, y, K0): RungeKutta._step_impl, rk.py; returns false when the step size underflows
@@ -781,11 +829,10 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
                     if (direction * (t_next - t_end) > 0) t_next = t_end;
                     h = t_next - t_cur;
                     h_abs = fabs(h);
+                    float k0[12];
+                    load_k(0, k0);
 #pragma unroll
-                    for (int c = 0; c < 9; ++c) {
-                        const double k0 = valid ? __ldcg(Kmine + c) : 0.0;
-                        xn[c] = sY[c * 128 + r] + (k0 * kRkA[1][0]) * h;
-                    }
+                    for (int c = 0; c < 9; ++c) xn[c] = sY[c * 128 + r] + ((valid ? (double)k0[c] : 0.0) * kRkA[1][0]) * h;
                     if (tid == 0) {
                         for (int j = 1; j < 6; ++j) s_times[j - 1] = (float)(t_cur + kRkC[j] * h);
                         s_times[5] = (float)(t_cur + h);
@@ -820,8 +867,8 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
                         const double uu = yv / sc, vv = kc[c] / sc;
                         a0 += uu * uu;
                         a1 += vv * vv;
-                        if (valid) __stcg(Kmine + c, kc[c]);                          // K0 = f0
                     }
+                    if (valid) store_k(0, kc);                                        // K0 = f0
                     double A0, A1;
                     grid_sum2(a0, a1, A0, A1);
                     const double d0 = sqrt(A0 / n_total);
@@ -839,10 +886,12 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
                 } else if (phase == kPhF1) {
                     // ---- select_initial_step, second half: d2 from f1 - f0, then the first attempt
                     double a2 = 0.0;
+                    float k0f[12];
+                    load_k(0, k0f);
 #pragma unroll
                     for (int c = 0; c < 9; ++c) {
                         const double yv = sY[c * 128 + r], sc = atol + fabs(yv) * rtol;
-                        const double k0 = valid ? __ldcg(Kmine + c) : 0.0;
+                        const double k0 = valid ? (double)k0f[c] : 0.0;
                         const double ww = (kc[c] - k0) / sc;
                         a2 += ww * ww;
                     }
@@ -857,35 +906,51 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
                     if (!begin_attempt()) begin_denoise();
                     boundary = true;
                 } else if (phase == kPhAttempt) {
-                    if (valid) {
-#pragma unroll
-                        for (int c = 0; c < 9; ++c) __stcg(Kmine + (size_t)st * kst + c, kc[c]);     // K[st]
-                    }
+                    if (valid && st < 6) store_k(st, kc);                           // K[st] (K[6] = f_new stays in registers)
                     if (st < 6) {
                         // next stage input: y + h * sum_j a[st+1][j] K_j for st < 5, the 5th-order solution y_new (b weights) for st == 5
+                        // (the earlier stages come back from L2; every load is issued unconditionally so that all of them are in
+                        // flight together, and a stage that does not take part is discarded by the select, not by a branch)
+                        double dy[9];
+                        float kf[5][12];
 #pragma unroll
-                        for (int c = 0; c < 9; ++c) {
-                            double dy = 0.0;
-                            for (int j = 0; j < st; ++j) {
-                                const double kj = valid ? __ldcg(Kmine + (size_t)j * kst + c) : 0.0;
-                                dy += kj * (st < 5 ? kRkA[st + 1][j] : kRkB[j]);
-                            }
-                            dy += kc[c] * (st < 5 ? kRkA[st + 1][st] : kRkB[st]);
-                            xn[c] = st < 5 ? sY[c * 128 + r] + dy * h : sY[c * 128 + r] + h * dy;
-                            if (st == 5) sYn[c * 128 + r] = xn[c];
+                        for (int j = 0; j < 5; ++j) load_k(j, kf[j]);
+#pragma unroll
+                        for (int c = 0; c < 9; ++c) dy[c] = 0.0;
+#pragma unroll
+                        for (int j = 0; j < 5; ++j) {
+                            const double a = st < 5 ? kRkA[st + 1][j] : kRkB[j];
+#pragma unroll
+                            for (int c = 0; c < 9; ++c) dy[c] += (j < st && valid) ? (double)kf[j][c] * a : 0.0;
                         }
+                        {
+                            const double a = st < 5 ? kRkA[st + 1][st] : kRkB[st];
+#pragma unroll
+                            for (int c = 0; c < 9; ++c) {
+                                dy[c] += kc[c] * a;
+                                xn[c] = sY[c * 128 + r] + dy[c] * h;
+                                if (st == 5) sYn[c * 128 + r] = xn[c];
+                            }
+                        }
+                        if (ds) dbg_b = -(long long)clock64();
                         ++st;
                     } else {
                         // ---- error estimate over the WHOLE batch (one controller, samplers.py:205 / rk.py _estimate_error_norm)
                         double ae = 0.0;
+                        double errv[9];
+                        float kf[6][12];
+#pragma unroll
+                        for (int j = 0; j < 6; ++j) load_k(j, kf[j]);
+#pragma unroll
+                        for (int c = 0; c < 9; ++c) errv[c] = 0.0;
+#pragma unroll
+                        for (int j = 0; j < 6; ++j) {
+#pragma unroll
+                            for (int c = 0; c < 9; ++c) errv[c] += valid ? (double)kf[j][c] * kRkE[j] : 0.0;
+                        }
 #pragma unroll
                         for (int c = 0; c < 9; ++c) {
-                            double err = 0.0;
-                            for (int j = 0; j < 6; ++j) {
-                                const double kj = valid ? __ldcg(Kmine + (size_t)j * kst + c) : 0.0;
-                                err += kj * kRkE[j];
-                            }
-                            err += kc[c] * kRkE[6];
+                            const double err = errv[c] + kc[c] * kRkE[6];
                             const double sc = atol + fmax(fabs(sY[c * 128 + r]), fabs(sYn[c * 128 + r])) * rtol;
                             const double ww = err * h / sc;
                             ae += ww * ww;
@@ -902,10 +967,8 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
                             ++n_acc;
                             // accept: y <- y_new, K0 <- K6 = f_new (FSAL), t <- t + h clipped to the bound
 #pragma unroll
-                            for (int c = 0; c < 9; ++c) {
-                                sY[c * 128 + r] = sYn[c * 128 + r];
-                                if (valid) __stcg(Kmine + c, kc[c]);
-                            }
+                            for (int c = 0; c < 9; ++c) sY[c * 128 + r] = sYn[c * 128 + r];
+                            if (valid) store_k(0, kc);
                             t_cur = t_next;
                             go_on = direction * (t_cur - t_end) < 0;
                             if (go_on) begin_step();
@@ -958,21 +1021,29 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
                     boundary = true;
                     finished = true;
                 }
+                if (ds) ds[12] = clock64();
                 if (!finished) {
 #pragma unroll
                     for (int c = 0; c < 9; ++c) x[c] = (float)xn[c];
                     publish_x();                                  // the MMA warp starts on layer 0 while the time biases are refreshed
+                }
+                if (ds) {
+                    ds[13] = clock64();
+                    ds[14] = (unsigned long long)dbg_a;           // negative inside a group; overwritten with positive stamps at a group end
+                    ds[15] = (unsigned long long)dbg_b;
                 }
                 if (!boundary) {
                     ++gi;
                     continue;
                 }
                 named_bar_sync(4, 256);
+                if (ds) ds[14] = clock64();
                 gn = s_gn;
                 gi = 0;
                 if (gn == 0) break;
                 if (gn == 6) time_biases(std::integral_constant<int, 6>{});
                 else time_biases(std::integral_constant<int, 1>{});
+                if (ds) ds[15] = clock64();
                 continue;
             } else {
                 // ---- every rank: score, batch-mean gradient norm (published by the leaders), update — redundantly, bit-identically ----
@@ -1148,9 +1219,10 @@ extern "C" int gpb_sample_pc_tc_dbg(const float *x0, int R, int K, int num_steps
     return launch_tc_sampler(tc_pc_sampler_kernel, "sample_pc_tc", tp, n_tiles, kTcSmemBytes, st);
 }
 
-extern "C" int gpb_sample_ode_tc(const float *x0, int R, int K, float T0, float rtol, float atol, int denoise_steps,
-                                 const float *obj_bias, const float *W, const void *tc_stream, const float *pts_center, double *pose,
-                                 int *stats, void *workspace, size_t workspace_bytes, void *stream) {
+extern "C" int gpb_sample_ode_tc_dbg(const float *x0, int R, int K, float T0, float rtol, float atol, int denoise_steps,
+                                     const float *obj_bias, const float *W, const void *tc_stream, const float *pts_center, double *pose,
+                                     int *stats, void *workspace, size_t workspace_bytes, unsigned long long *dbg, int dbg_evals,
+                                     void *stream) {
     GPB_REQUIRE(R >= 0 && K >= 1, "sample_ode_tc: need R >= 0, K >= 1");
     if (R == 0) return GPB_OK;
     GPB_REQUIRE(x0 && obj_bias && W && tc_stream && pts_center && pose && workspace, "sample_ode_tc: NULL buffer");
@@ -1175,8 +1247,9 @@ extern "C" int gpb_sample_ode_tc(const float *x0, int R, int K, float T0, float 
 
     TcPcParams tp{};
     PcParams &p = tp.pc;
-    p.x0 = x0; p.R = R; p.K = K; p.T = 0;
+    p.x0 = x0; p.R = R; p.K = K; p.T = dbg ? dbg_evals : 0;       // ODE: T only bounds the profiling record [2][T][16]
     p.obj_bias = obj_bias; p.W = W; p.pts_center = pts_center; p.barrier = w.barrier; p.tiles_per_cta = 1;
+    p.dbg = dbg; p.dbg_cta = 0;
     tp.wstream = reinterpret_cast<const uint8_t *>(tc_stream);
     tp.ode.T0 = T0; tp.ode.rtol = rtol; tp.ode.atol = atol; tp.ode.denoise_steps = denoise_steps;
     tp.ode.Kst = w.Kst; tp.ode.partial = reinterpret_cast<double *>(w.partial); tp.ode.tb_cta = w.tb_cta;
@@ -1190,4 +1263,11 @@ extern "C" int gpb_sample_pc_tc(const float *x0, int R, int K, int num_steps, fl
                                 void *stream) {
     return gpb_sample_pc_tc_dbg(x0, R, K, num_steps, snr, obj_bias, W, tc_stream, pts_center, step_noise, seed, time_grid, mean_x,
                                 process, workspace, workspace_bytes, nullptr, stream);
+}
+
+extern "C" int gpb_sample_ode_tc(const float *x0, int R, int K, float T0, float rtol, float atol, int denoise_steps,
+                                 const float *obj_bias, const float *W, const void *tc_stream, const float *pts_center, double *pose,
+                                 int *stats, void *workspace, size_t workspace_bytes, void *stream) {
+    return gpb_sample_ode_tc_dbg(x0, R, K, T0, rtol, atol, denoise_steps, obj_bias, W, tc_stream, pts_center, pose, stats, workspace,
+                                 workspace_bytes, nullptr, 0, stream);
 }

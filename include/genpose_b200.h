@@ -164,6 +164,13 @@ GPB_API int gpb_sample_ode_tc(const float *x0, int R, int K, float T0, float rto
                       const float *obj_bias, const float *trunk_weights, const void *tc_stream, const float *pts_center,
                       double *pose, int *stats, void *workspace, size_t workspace_bytes, void *stream);
 
+/* profiling aid: as gpb_sample_ode_tc, additionally records clock64 stamps of CTA 0 for the first dbg_evals evaluations
+ * into dbg [2][dbg_evals][16] (row thread 0 | MMA warp); see tools/tc_ode_phase_times.py. */
+GPB_API int gpb_sample_ode_tc_dbg(const float *x0, int R, int K, float T0, float rtol, float atol, int denoise_steps,
+                          const float *obj_bias, const float *trunk_weights, const void *tc_stream, const float *pts_center,
+                          double *pose, int *stats, void *workspace, size_t workspace_bytes, unsigned long long *dbg,
+                          int dbg_evals, void *stream);
+
 /* replaces PoseNet.get_energy's arithmetic after the encoder (networks/posenet_agent.py:508-523 ->
  * PoseEnergyNet.get_energy energynet.py:143-198, 'IP' decoupled): energy [B,K,2] = (rot, trans). */
 GPB_API int gpb_energy(const float *pose, int R, int K, float t, const float *obj_bias, const float *trunk_weights,
