@@ -47,7 +47,6 @@ constexpr int kTcRows = 128;
 constexpr int kTcRowWarps = 8;
 constexpr int kTcThreads = (kTcRowWarps + 2) * 32;
 constexpr uint32_t kSlotBytes = 16384;
-constexpr int kSlots = 9;
 constexpr int kTeam = 4;                           // CTAs per tile
 constexpr int kCommonSlots = 1 + 16;               // P1 (both units) + P2 (2 units x 8 K-chunks); slot = hi image | lo image
 constexpr int kHeadSlots = 8 + 4;                  // head slice: 128-row unit (8 K-chunks) + 64-row unit (2 K-chunks per slot)
@@ -60,16 +59,19 @@ constexpr uint32_t kColD = 0, kColAhi = 256, kColAlo = 384;
 using TL = TrunkLayout;
 
 // dynamic shared memory map (bytes)
-constexpr uint32_t kOffRing = 0;
-constexpr uint32_t kOffObt = kOffRing + kSlots * kSlotBytes;          // [4][768] fp32: obj_bias + t_bias(step)
+constexpr uint32_t kOffObt = 0;                                       // [4][768] fp32: obj_bias + t_bias(step)
 constexpr uint32_t kOffOw = kOffObt + kMaxObjPerTile * 768 * 4;       // [9][256] fp32 output layer + [16] bias
 constexpr uint32_t kOffBias = kOffOw + (9 * 256 + 16) * 4;            // p1_b [256] | p2_b [256]
 constexpr uint32_t kOffFpart = kOffBias + 512 * 4;                    // [128][12] fp32 partial scores of column sub-half 1
 constexpr uint32_t kOffMail = kOffFpart + 128 * 12 * 4;               // [2 parities][4 ranks][128][8] fp32: the team's partial sums (DSMEM)
-constexpr uint32_t kTcSmemBytes = kOffMail + 2 * 4 * 128 * 8 * 4;
-constexpr uint32_t kOffOdeY = kTcSmemBytes;                           // ODE only: y [9][128] | y_new [9][128] float64
-constexpr uint32_t kTcSmemBytesOde = kOffOdeY + 2 * 9 * 128 * 8;
-static_assert(kTcSmemBytesOde <= 227 * 1024 - 1536, "tc sampler shared memory budget");
+constexpr uint32_t kOffOdeY = kOffMail + 2 * 4 * 128 * 8 * 4;         // ODE only: y [9][128] | y_new [9][128] float64
+// the weight ring takes what is left: 10 slots for the PC kernel, 9 for the ODE kernel (which keeps its float64 state in smem)
+template <bool kOde> struct TcSmem {
+    static constexpr int kSlots = kOde ? 9 : 10;
+    static constexpr uint32_t kOffRing = ((kOde ? kOffOdeY + 2 * 9 * 128 * 8 : kOffOdeY) + 1023u) & ~1023u;
+    static constexpr uint32_t kBytes = kOffRing + kSlots * kSlotBytes;
+};
+static_assert(TcSmem<false>::kBytes <= 227 * 1024 - 1280 && TcSmem<true>::kBytes <= 227 * 1024 - 1280, "tc sampler shared memory budget");
 
 // probability-flow ODE mode (cond_ode_sampler, samplers.py:163-227): everything PcParams does not already carry
 struct TcOdeParams {
@@ -134,7 +136,8 @@ template <bool kOde>
 __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
     const PcParams &p = tp.pc;
     extern __shared__ __align__(1024) uint8_t smem[];
-    uint8_t *sRing = smem + kOffRing;
+    constexpr int kSlots = TcSmem<kOde>::kSlots;
+    uint8_t *sRing = smem + TcSmem<kOde>::kOffRing;
     float *sObt = reinterpret_cast<float *>(smem + kOffObt);
     float *sOw = reinterpret_cast<float *>(smem + kOffOw);
     float *sBias = reinterpret_cast<float *>(smem + kOffBias);
@@ -298,7 +301,10 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
                 const uint32_t d = tmem_base + kColD + b * 128u;
                 const bool small = unit == 3;                      // the 64-column unit: 2 K-chunks per slot
                 if (!small) {
-                    // 8 slots = 16 K-steps, issued as one group (unit 1) or two groups of 4 slots (units 0, 2)
+                    // 8 slots = 16 K-steps, issued as one group (unit 1) or two groups of 4 slots (units 0, 2).  Every slot wait costs
+                    // the MMA warp ~250 cycles even when the data is there (measured: groups of 2 slots, 7.45 -> 8.0 ms per launch), so
+                    // groups are as large as the A-operand hand-off allows.  (Also measured without effect: a 10th ring slot, one private
+                    // copy of the weight stream per tile team — the waits are not L2 hot-line contention — and one 8-slot wait for unit 0.)
                     const int groups = split ? 2 : 1, per = split ? 4 : 8;
                     for (int g = 0; g < groups; ++g) {
                         if (g == 1) {
@@ -1216,7 +1222,7 @@ extern "C" int gpb_sample_pc_tc_dbg(const float *x0, int R, int K, int num_steps
     p.mean_x = mean_x; p.process = process; p.tiles_per_cta = 1; p.dbg = dbg; p.dbg_cta = dbg ? dbg_cta_sel : 0;
     tp.wstream = reinterpret_cast<const uint8_t *>(tc_stream);
 
-    return launch_tc_sampler(tc_pc_sampler_kernel, "sample_pc_tc", tp, n_tiles, kTcSmemBytes, st);
+    return launch_tc_sampler(tc_pc_sampler_kernel, "sample_pc_tc", tp, n_tiles, TcSmem<false>::kBytes, st);
 }
 
 extern "C" int gpb_sample_ode_tc_dbg(const float *x0, int R, int K, float T0, float rtol, float atol, int denoise_steps,
@@ -1254,7 +1260,7 @@ extern "C" int gpb_sample_ode_tc_dbg(const float *x0, int R, int K, float T0, fl
     tp.ode.T0 = T0; tp.ode.rtol = rtol; tp.ode.atol = atol; tp.ode.denoise_steps = denoise_steps;
     tp.ode.Kst = w.Kst; tp.ode.partial = reinterpret_cast<double *>(w.partial); tp.ode.tb_cta = w.tb_cta;
     tp.ode.pose = pose; tp.ode.stats = stats;
-    return launch_tc_sampler(tc_ode_sampler_kernel, "sample_ode_tc", tp, n_tiles, kTcSmemBytesOde, st);
+    return launch_tc_sampler(tc_ode_sampler_kernel, "sample_ode_tc", tp, n_tiles, TcSmem<true>::kBytes, st);
 }
 
 extern "C" int gpb_sample_pc_tc(const float *x0, int R, int K, int num_steps, float snr, const float *obj_bias, const float *W,

@@ -67,3 +67,15 @@ print(f"  {'            waiting on weight slots':42s} {np.mean(mma[:, 8]):9.0f}"
 print(f"  {'            waiting on the A operand':42s} {np.mean(mma[:, 9]):9.0f}")
 print(f"  {'            waiting on accumulator slots':42s} {np.mean(mma[:, 10]):9.0f}")
 print(f"  {'step total':42s} {np.mean(mma[1:, 0] - mma[:-1, 0]):9.0f}")
+# merged timeline of one step (same SM => same clock): offsets from the row thread's step start, mean over steps
+ev = [("row: step start", row[:, 0]), ("row: L0 acc ready", row[:, 1]), ("row: L0 epilogue done (h1 published)", row[:, 2]),
+      ("row: L1 unit a acc ready", row[:, 3]), ("row: L1 epilogue done (pf published)", row[:, 4]), ("row: head128 acc ready", row[:, 5]),
+      ("row: head128 epilogue done", row[:, 6]), ("row: head64 acc ready", row[:, 7]), ("row: head64 epilogue done", row[:, 8]),
+      ("row: partials sent", row[:, 11]), ("row: peers' partials in", row[:, 10]), ("row: norm published", row[:, 14]),
+      ("row: grid word complete", row[:, 15]), ("row: x published", row[:, 13]),
+      ("mma: x_ready seen", mma[:, 1]), ("mma: L1 unit a first half A ready", mma[:, 3]), ("mma: head128 first half A ready", mma[:, 4]),
+      ("mma: all issued", mma[:, 7])]
+base = row[:, 0]
+print("timeline (cycles after the row thread's step start; x_ready / x published belong to the step boundary):")
+for name, v in sorted(ev, key=lambda e: np.mean((e[1] - base) % 1e9)):
+    print(f"  {np.mean(v - base):9.0f}  {name}")
