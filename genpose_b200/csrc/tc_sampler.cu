@@ -251,11 +251,13 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
             unsigned long long w_full = 0, w_a = 0, w_acc = 0, tq = 0, w_issue = 0;
             if (ds) ds[0] = clock64();
             // ---- layer 0: h1_pre = x . P1^T   (K = 16; x pieces x1,x2,x3 at A_hi[0,8),[8,16),[16,24); P1 hi|lo per unit)
+            // (every slot wait costs ~250 cycles even when the data is there: it is taken BEFORE the wait for the operand it
+            // accompanies, where this warp idles anyway, not between that wait and the first MMA)
+            wait_slots(1);
             mbar_wait(&bar_x_ready, xr & 1u);
             ++xr;
             if (ds) ds[1] = clock64();
             {
-                wait_slots(1);
                 const uint32_t s = it % kSlots;
                 for (int half = 0; half < 2; ++half) {
                     const uint32_t b = u & 1u, n = u >> 1;
@@ -285,19 +287,7 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
                 // two halves (K columns [0,128) as soon as the first accumulator unit is converted, [128,256) after the second),
                 // so the first 8 K-steps are issued while the second half is still in the epilogue.
                 const bool split = unit == 0 || unit == 2;
-                if (split) {
-                    mbar_wait(&bar_a_ready, ar & 1u);
-                    ++ar;
-                }
-                if (ds) {
-                    w_a += clock64() - tq;
-                    if (unit == 0) ds[3] = clock64();
-                    if (unit == 2) ds[4] = clock64();
-                    tq = clock64();
-                }
                 const uint32_t b = u & 1u, n = u >> 1;
-                mbar_wait(&bar_acc_empty[b], (n & 1u) ^ 1u);
-                if (ds) { w_acc += clock64() - tq; tq = clock64(); }
                 const uint32_t d = tmem_base + kColD + b * 128u;
                 const bool small = unit == 3;                      // the 64-column unit: 2 K-chunks per slot
                 if (!small) {
@@ -305,16 +295,24 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
                     // the MMA warp ~250 cycles even when the data is there (measured: groups of 2 slots, 7.45 -> 8.0 ms per launch), so
                     // groups are as large as the A-operand hand-off allows.  (Also measured without effect: a 10th ring slot, one private
                     // copy of the weight stream per tile team — the waits are not L2 hot-line contention — and one 8-slot wait for unit 0.)
-                    const int groups = split ? 2 : 1, per = split ? 4 : 8;
+                    const int groups = split ? 2 : 1, per = split ? 4 : 8;   // (unit 1 in two groups of 4: slower, 7.26 -> 7.35 ms)
                     for (int g = 0; g < groups; ++g) {
-                        if (g == 1) {
-                            if (ds) tq = clock64();
+                        if (ds) tq = clock64();
+                        wait_slots(per);                           // before the operand wait (see layer 0)
+                        if (ds) { w_full += clock64() - tq; tq = clock64(); }
+                        if (split) {
                             mbar_wait(&bar_a_ready, ar & 1u);
                             ++ar;
-                            if (ds) { w_a += clock64() - tq; tq = clock64(); }
                         }
-                        wait_slots(per);
-                        if (ds) { w_full += clock64() - tq; tq = clock64(); }
+                        if (ds) {
+                            w_a += clock64() - tq;
+                            if (unit == 0 && g == 0) ds[3] = clock64();
+                            if (unit == 2 && g == 0) ds[4] = clock64();
+                            tq = clock64();
+                        }
+                        if (g == 0) mbar_wait(&bar_acc_empty[b], (n & 1u) ^ 1u);
+                        tc_fence_after_sync();
+                        if (ds) { w_acc += clock64() - tq; tq = clock64(); }
                         const uint32_t s_first = it % kSlots;
                         const int kc0 = g * per;
                         if (elect_one_sync()) {
@@ -342,8 +340,12 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
                         it += (uint32_t)per;
                     }
                 } else {
+                    if (ds) tq = clock64();
                     wait_slots(4);
                     if (ds) { w_full += clock64() - tq; tq = clock64(); }
+                    mbar_wait(&bar_acc_empty[b], (n & 1u) ^ 1u);
+                    tc_fence_after_sync();
+                    if (ds) { w_acc += clock64() - tq; tq = clock64(); }
                     const uint32_t s_first = it % kSlots;
                     if (elect_one_sync()) {
 #pragma unroll

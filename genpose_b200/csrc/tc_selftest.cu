@@ -91,6 +91,23 @@ umma_selftest_kernel(const float *__restrict__ A, const uint16_t *__restrict__ B
         const uint32_t ahi = smem_u32(sAhi), alo = smem_u32(sAlo), bhi = smem_u32(sBhi), blo = smem_u32(sBlo);
         bool acc = false;
         const unsigned long long t_start = clock64();
+        if (repeat > 1) {
+            // timing mode: ONE elected lane issues the whole stream back to back (as the sampler kernels do)
+            if (elect_one_sync()) {
+                for (int rep = 0; rep < repeat; ++rep)
+                    for (int term = 0; term < n_terms; ++term) {
+                        const uint32_t a0 = term == 2 ? alo : ahi, b0 = term == 1 ? blo : bhi;
+                        for (int k16 = 0; k16 < K / 16; ++k16) {
+                            const uint64_t ad = make_smem_desc(a0 + k16 * 2 * a_lbo, a_lbo, a_sbo);
+                            const uint64_t bd = make_smem_desc(b0 + k16 * 2 * b_lbo, b_lbo, b_sbo);
+                            if (a_tmem) umma_bf16_ts(tmem_base, tmem_base + (term == 2 ? 384u : 256u) + (uint32_t)k16 * 8u, bd, idesc, acc);
+                            else umma_bf16(tmem_base, ad, bd, idesc, acc);
+                            acc = true;
+                        }
+                    }
+            }
+            __syncwarp();
+        } else
         for (int rep = 0; rep < repeat; ++rep)
         for (int term = 0; term < n_terms; ++term) {   // 0: Ahi.Bhi  1: Ahi.Blo  2: Alo.Bhi
             const uint32_t a0 = term == 2 ? alo : ahi, b0 = term == 1 ? blo : bhi;
