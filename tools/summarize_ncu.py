@@ -9,7 +9,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OUT = os.path.join(ROOT, "gpurun_out")
-PROF = os.path.join(ROOT, "profiles")
+PROF = os.environ.get("GPB_SUMMARY_DIR", os.path.join(ROOT, "profiles"))
 
 KEYS = [
     "gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
@@ -76,5 +76,5 @@ if __name__ == "__main__":
     tag = sys.argv[1]
     os.makedirs(PROF, exist_ok=True)
     launches(tag)
-    for n in ("sampler", "encoder", "tc_sampler"):
+    for n in ("sampler", "encoder", "tc_sampler", "tc_ode_sampler"):
         full(tag, n)
