@@ -161,3 +161,48 @@ def checksum(arr) -> float:
     a = np.asarray(arr, dtype=np.float64).ravel()
     w = np.cos(np.arange(a.size, dtype=np.float64) * 0.7853981633974483 + 0.3)
     return float(np.dot(a, w))
+
+
+# ---- synthetic RGB-D frames for the point-cloud preparation path (runners/evaluation_single.py:168-216) -------------
+def make_frame(seed: int, n_inst: int = 6, H: int = 480, W: int = 640):
+    """A REAL275-shaped frame: depth [H,W] uint16 in millimetres (a tilted background plane with dropout holes and one
+    raised blob per instance), Mask-RCNN style instance masks [H,W,n_inst] bool and rois [n_inst,4] (y1,x1,y2,x2).
+    The instances cover the cases the reference distinguishes: large (> 1024 valid pixels: random subset), small
+    (< 1024: tiled), touching the image border (crop window clipped / out-of-bounds ROI pixels), holes inside the
+    mask (depth == 0), a mask with no valid depth at all (instance skipped) and a one-pixel mask (skipped)."""
+    rs = np.random.RandomState(1000 + seed)
+    yy, xx = np.mgrid[0:H, 0:W]
+    depth = 900.0 + 0.35 * xx + 0.2 * yy + rs.normal(0, 2.0, (H, W))
+    masks = np.zeros((H, W, n_inst), dtype=bool)
+    rois = np.zeros((n_inst, 4), dtype=np.int32)
+    for i in range(n_inst):
+        kind = i % 6
+        if kind == 0:      # large object in the middle
+            cy, cx, ry, rx = rs.randint(150, 330), rs.randint(200, 440), rs.randint(50, 90), rs.randint(60, 110)
+        elif kind == 1:    # small object (< 1024 pixels)
+            cy, cx, ry, rx = rs.randint(60, 420), rs.randint(60, 580), rs.randint(8, 14), rs.randint(8, 14)
+        elif kind == 2:    # at the top-left border
+            cy, cx, ry, rx = rs.randint(5, 30), rs.randint(5, 40), rs.randint(30, 60), rs.randint(30, 60)
+        elif kind == 3:    # at the bottom-right border
+            cy, cx, ry, rx = H - rs.randint(5, 30), W - rs.randint(5, 40), rs.randint(40, 80), rs.randint(40, 80)
+        elif kind == 4:    # no valid depth under the mask
+            cy, cx, ry, rx = rs.randint(100, 380), rs.randint(100, 540), rs.randint(10, 20), rs.randint(10, 20)
+        else:              # single pixel
+            cy, cx, ry, rx = rs.randint(100, 380), rs.randint(100, 540), 0, 0
+        m = ((yy - cy) / max(ry, 0.5)) ** 2 + ((xx - cx) / max(rx, 0.5)) ** 2 <= 1.0
+        if kind == 5:
+            m = (yy == cy) & (xx == cx)
+        masks[:, :, i] = m
+        depth = np.where(m, depth - 150.0 * np.exp(-(((yy - cy) / (ry + 1.0)) ** 2 + ((xx - cx) / (rx + 1.0)) ** 2)), depth)
+        ys, xs = np.nonzero(m)
+        rois[i] = [ys.min(), xs.min(), ys.max() + 1, xs.max() + 1]
+    depth = np.clip(depth, 1, 60000).astype(np.uint16)
+    holes = rs.rand(H, W) < 0.08
+    depth[holes] = 0
+    for i in range(n_inst):
+        if i % 6 == 4:
+            depth[masks[:, :, i]] = 0
+    return depth, masks, rois
+
+
+REAL_INTRINSICS = np.array([[591.0125, 0, 322.525], [0, 590.16775, 244.11084], [0, 0, 1]], dtype=np.float32)   # evaluation_single.py:54

@@ -203,6 +203,27 @@ GPB_API int gpb_selftest_umma(const float *A, const uint16_t *Bhi, const uint16_
                               int variant, int swap_fields, int n_terms, int a_tmem, int repeat,
                               unsigned long long *cycles_out, void *stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * 3. point-cloud preparation (the step before the path)
+ * ------------------------------------------------------------------------------------------------
+ * replaces, per detected instance, the body of the instance loop of detect_mrcnn_genpose
+ * (runners/evaluation_single.py:168-216): three cv2.warpAffine(INTER_NEAREST) crops to 256 x 256
+ * (utils/datasets_utils.py:82-95: coordinate map, mask, depth), depth_to_pcl (:107-119), "/ 1000.0" (:211) and
+ * sample_points (:121-133).  One launch per frame, all instances.
+ *   depth  [H,W] u16 (device)       millimetres, 0 = no measurement (load_depth, utils/sgpa_utils.py:194-211)
+ *   masks  u8 (device)              Mask-RCNN masks; instance i at pixel p: masks[p*mask_pixel_stride + i*mask_inst_stride]
+ *                                   ([H,W,n] bool as the detector pickles store it: strides (n, 1))
+ *   trans  [n_inst,6] f64 (device)  forward 2x3 crop matrices exactly as get_affine_transform returns them
+ *                                   (utils/datasets_utils.py:97-138, cv2.getAffineTransform)
+ *   intrinsics [4] f32 (HOST)       cx, cy, fx, fy of the float32 camera matrix (evaluation_single.py:50,54)
+ *   subset_ids [n_inst,1024] i32 (device) or NULL   the reference's np.random.permutation(n)[:1024] per instance with
+ *                                   n > 1024 valid pixels (parity mode); NULL = keyed in-kernel permutation of `seed`
+ *   pts    [n_inst,1024,3] f32 out  camera-frame metres; all zero for an instance the reference skips
+ *   n_valid [n_inst] i32 out        valid crop pixels; <= 1 means "skip the instance" (:201-209) */
+GPB_API int gpb_prepare_clouds(const unsigned short *depth, const unsigned char *masks, long long mask_pixel_stride,
+                       long long mask_inst_stride, int H, int W, int n_inst, const double *trans, const float *intrinsics,
+                       const int *subset_ids, uint64_t seed, float *pts, int *n_valid, void *stream);
+
 #ifdef __cplusplus
 }
 #endif
