@@ -186,7 +186,8 @@ def run_ode_line(args, rank, world, local_rank):
     import torch.distributed as dist
     from genpose_b200 import lib, synth
     from genpose_b200.pipeline import PosePipeline
-    from genpose_b200.sde import ve_prior
+    from genpose_b200.sde import init_sde
+    ve_prior = init_sde("ve")[0]               # sigma_max = 50 (sde.py:90-97)
     dev = torch.device("cuda", local_rank)
     T0 = 0.55
     sd = synth.make_state_dict(0, kappa=-0.3)

@@ -44,3 +44,20 @@ class PosePipeline:
             sp, se, rt = ops.rank_pool(pose, energy.contiguous(), ratio=ratio)                       # :344 + sgpa_utils.py:897
             out.update(energy=energy, sorted_pose=sp, sorted_energy=se, pooled_RT=rt)
         return out
+
+    def track_step(self, data: Dict[str, torch.Tensor], initial_sRT: torch.Tensor, repeat_num: int = 50, T0: float = 0.15,
+                   ratio: float = 0.6):
+        """One frame of the tracking runner (runners/evaluation_tracking.py:302-316): warm-start every object from the
+        previous frame's pooled pose `initial_sRT [B,4,4]` — initial_pose = [R[:, 0] | R[:, 1] | t - pts_center] (:309-310) —
+        sample K candidates from T0 (`cond_ode_sampler` adds the T0-prior noise to init_x, samplers.py:180), rank by
+        energy, pool the best `ratio` (cal_average_sRT, :58-75).  -> run()'s dict; out['pooled_RT'] feeds the next frame."""
+        initial_pose = initial_sRT[:, :3, [0, 1, 3]].permute(0, 2, 1).reshape(initial_sRT.shape[0], -1).float().clone()
+        initial_pose[:, -3:] -= data["pts_center"]
+        out = {"pred_pose": self.score_agent.pred_func(data, repeat_num=repeat_num, save_path=None, init_x=initial_pose, T0=T0)}
+        if self.energy_agent is not None:
+            pose = out["pred_pose"].float().contiguous()
+            energy = self.energy_agent.get_energy(data=data, pose_samples=pose, T=1e-5)
+            sp, se, rt = ops.rank_pool(pose, energy.contiguous(), ratio=ratio)
+            out.update(energy=energy, sorted_pose=sp, sorted_energy=se, pooled_RT=rt)
+        return out
+

@@ -215,3 +215,42 @@ def test_no_cpu_path(ops):
     from genpose_b200 import lib
     with pytest.raises(lib.GenPoseB200Error):
         ops.furthest_point_sample(torch.zeros(1, 8, 3), 4)
+
+
+def test_tracking_warm_start_matches_oracle(ops):
+    """The tracking hand-off (runners/evaluation_tracking.py:302-316): init_x from the previous frame's pose, ODE sampler
+    from T0 = 0.15.  The agent draws the T0-prior noise from torch's CPU generator like the reference (sde.py:26-28), so a
+    seeded run can be replayed by the oracle."""
+    from genpose_b200.pipeline import PosePipeline
+    from genpose_b200.sde import init_sde
+    ve_prior = init_sde("ve")[0]               # sigma_max = 50 (sde.py:90-97)
+    B, K, T0, seed = 3, 50, 0.15, 21
+    sd = synth.make_state_dict(seed, kappa=0.3)
+    esd = synth.make_state_dict(seed + 100, kappa=0.3)
+    clouds = synth.make_clouds(B, seed)
+    data_cpu = synth.batch_from_clouds(clouds)
+    rs = np.random.RandomState(seed)
+    init_sRT = torch.eye(4).repeat(B, 1, 1)
+    q, _ = np.linalg.qr(rs.randn(B, 3, 3))
+    init_sRT[:, :3, :3] = torch.from_numpy(q).float()
+    init_sRT[:, :3, 3] = data_cpu["pts_center"] + torch.from_numpy(rs.randn(B, 3).astype(np.float32)) * 0.02
+    for precision in ("fp32", "bf16x3"):
+        pipe = PosePipeline(sd, esd, sampler="ode", sampling_steps=None, precision=precision)
+        data = synth.batch_from_clouds(clouds, device="cuda")
+        torch.manual_seed(5)
+        out = pipe.track_step(data, init_sRT.cuda(), repeat_num=K, T0=T0)
+        # oracle replay: same initial pose, same prior draw
+        init_pose = init_sRT[:, :3, [0, 1, 3]].permute(0, 2, 1).reshape(B, -1).clone()
+        init_pose[:, -3:] -= data_cpu["pts_center"]
+        torch.manual_seed(5)
+        prior = ve_prior((B * K, 9), T=T0)
+        x0 = init_pose.unsqueeze(1).repeat(1, K, 1).view(B * K, -1) + prior
+        feat = O.encode(sd, data_cpu["pts"])
+        rep = feat.unsqueeze(1).repeat(1, K, 1).view(B * K, -1)
+        cen = data_cpu["pts_center"].unsqueeze(1).repeat(1, K, 1).view(B * K, -1)
+        ref = O.ode_sampler(sd, rep, cen, x0, T0=T0).reshape(B, K, 9)
+        np.testing.assert_allclose(out["pred_pose"].cpu().numpy(), ref.numpy(), rtol=2e-4, atol=1e-3)
+        en = O.get_energy(esd, data_cpu, ref.float())
+        _, _, rt_ref = O.rank_and_pool(ref.float(), en)
+        np.testing.assert_allclose(out["pooled_RT"].cpu().numpy(), np.asarray(rt_ref), rtol=0, atol=2e-3)
+        assert out["pooled_RT"].shape == (B, 4, 4)

@@ -6,7 +6,9 @@ import torch
 
 sys.path.insert(0, ".")
 from genpose_b200 import ops, synth  # noqa: E402
-from genpose_b200.sde import ve_prior  # noqa: E402
+from genpose_b200.sde import init_sde  # noqa: E402
+
+ve_prior = init_sde("ve")[0]               # sigma_max = 50 (sde.py:90-97)
 
 precision = sys.argv[1] if len(sys.argv) > 1 else "fp32"
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 64

@@ -23,7 +23,8 @@ for i in range(2):
     if what == "tc_sampler":
         eng.sample_pc(ob, center, x0, K, T, seed=i, precision="bf16x3")
     if what == "tc_ode":
-        from genpose_b200.sde import ve_prior
+        from genpose_b200.sde import init_sde
+        ve_prior = init_sde("ve")[0]               # sigma_max = 50 (sde.py:90-97)
         torch.manual_seed(0)
         eng.sample_ode(ob, center, ve_prior((B * K, 9), T=0.55).cuda().contiguous(), K, T0=0.55, precision="bf16x3")
 torch.cuda.synchronize()

@@ -8,7 +8,9 @@ import torch
 
 sys.path.insert(0, ".")
 from genpose_b200 import lib, ops, synth  # noqa: E402
-from genpose_b200.sde import ve_prior  # noqa: E402
+from genpose_b200.sde import init_sde  # noqa: E402
+
+ve_prior = init_sde("ve")[0]               # sigma_max = 50 (sde.py:90-97)
 
 B, K, T0, NE = 64, 50, 0.55, 128
 sd = synth.make_state_dict(0, kappa=-0.3)
