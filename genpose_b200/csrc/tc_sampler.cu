@@ -1,6 +1,9 @@
-// Predictor-corrector sampler on the 5th-generation tensor cores (tcgen05 + TMEM), throughput mode.
+// The two samplers on the 5th-generation tensor cores (tcgen05 + TMEM): predictor-corrector (tc_pc_sampler_kernel, the
+// BASELINE metric) and the RK45 probability-flow ODE (tc_ode_sampler_kernel, the reference's shipped recipe).  ONE body
+// (tc_sampler_body<kOde>) evaluates the score network for both; they differ in what the row warps do with the score and in
+// how the number of evaluations is known.
 //
-// Same algorithm, launch contract and update code as pc_sampler_kernel (scorenet.cu); only the score network's
+// Same algorithm, launch contract and update code as pc_sampler_kernel / ode_sampler_kernel (scorenet.cu); only the score network's
 // dense layers change engine: every layer is evaluated by tcgen05.mma (kind::f16, bf16 operands, fp32
 // accumulation in TMEM) as the error-compensated split
 //        A.B ~= Ahi.Bhi + Alo.Bhi + Ahi.Blo          (A = Ahi + Alo, B = Bhi + Blo, all bf16)
@@ -18,8 +21,9 @@
 //   * activations never touch shared memory: the A operand of every layer lives in TENSOR MEMORY (written by the
 //     epilogue with tcgen05.st, lane = row, two bf16 per 32-bit column; consumed by the TS form of tcgen05.mma),
 //     TMEM map: D0 [0,128) D1 [128,256) accumulators (N = 128 "units", ping-pong), A_hi [256,384), A_lo [384,512);
-//   * the whole 227 KB of shared memory is therefore free for the weight stream: 9 slots x 16 KiB of pre-tiled bf16
-//     operand images (hi | lo; 1,040 KiB per step, L2-resident) fetched with cp.async.bulk on mbarriers, up to 9 K-chunks ahead;
+//   * the whole 227 KB of shared memory is therefore free for the weight stream: 10 slots x 16 KiB (9 in the ODE kernel,
+//     which keeps its float64 state in shared memory) of pre-tiled bf16 operand images (hi | lo; 1,040 KiB per step,
+//     L2-resident) fetched with cp.async.bulk on mbarriers, up to a ring ahead;
 //   * pose state, noise and score of a row live in the registers of "its" thread.
 // Roles (warp-specialised, 320 threads):
 //   warps 0-7  row warps: warp w owns TMEM lanes 32*(w%4).. (rows) and the column sub-half w/4 of every unit.
@@ -112,11 +116,7 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 __device__ __forceinline__ void red_relaxed_add_u64(unsigned long long *p, unsigned long long v) {
     asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
-__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long *p) {
-    unsigned long long v;
-    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
+
 
 // bias + ReLU + bf16 hi/lo split of 32 accumulator columns -> 16 + 16 packed words (column pairs)
 __device__ __forceinline__ void relu_split32(const uint32_t (&v)[32], const float *bias, uint32_t *hi, uint32_t *lo) {
@@ -535,7 +535,7 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
         enum { kPhF0 = 0, kPhF1 = 1, kPhAttempt = 2, kPhDenoise = 3 };
         int phase = kPhF0, st = 0, gi = 0, gn = 1, slot = 0, nfev = 0, n_acc = 0, n_rej = 0, status = 0;
         unsigned bar_target = 0;
-        bool rejected = false;
+        bool rejected = false, tb_pending = kOde;                             // time biases of the current group still to be computed
         const double t_end = 1e-5, direction = -1.0;                          // eps as a Python float; T0 > eps is checked by the host
         double t_cur = (double)od.T0, t_next = 0.0, h = 0.0, h_abs = 0.0, h0 = 0.0, d1 = 0.0, min_step = 0.0;
         const double rtol = (double)od.rtol, atol = (double)od.atol, n_total = (double)p.R * 9.0;
@@ -605,9 +605,7 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
 #pragma unroll
                 for (int c = 0; c < 9; ++c) sY[c * 128 + r] = (double)x[c];   // y0 = float64(init_x) (samplers.py:205)
             }
-            time_biases(std::integral_constant<int, 1>{});
-            fill_obt(0, 0, 256);
-            // no barrier needed here: the first reader of sObt is the head epilogue, behind named barrier 3 of the first evaluation
+            // the time biases of the first group are computed inside the first evaluation (tb_pending, below)
         }
 
         // relu(acc + obj_bias + t_bias) . O over one 32-column block whose first stacked hidden unit is n (one head per block)
@@ -697,6 +695,16 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
                     ++u;
                 }
                 if (ds) ds[2 + 2 * layer] = clock64();
+                if constexpr (kOde) {
+                    // First evaluation of a group: its time biases are only needed by the head epilogue, so they are computed
+                    // here, after h1 has been handed to the MMA warp — under the layer-1 MMAs instead of in front of layer 0.
+                    if (layer == 0 && tb_pending) {
+                        if (gn == 6) time_biases(std::integral_constant<int, 6>{});
+                        else time_biases(std::integral_constant<int, 1>{});
+                        fill_obt(0, 0, 256);
+                        tb_pending = false;
+                    }
+                }
             }
             // noise of this step, generated while the tensor core runs the head slice (the leader's warps 0-3 own the rows)
             float z1[9], z2[9];
@@ -770,9 +778,7 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
                     gn = s_gn;
                     gi = 0;
                     if (gn == 0) break;                   // solved
-                    if (gn == 6) time_biases(std::integral_constant<int, 6>{});
-                    else time_biases(std::integral_constant<int, 1>{});
-                    fill_obt(0, 128, 128);
+                    tb_pending = true;
                     continue;
                 }
             }
@@ -1049,8 +1055,7 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
                 gn = s_gn;
                 gi = 0;
                 if (gn == 0) break;
-                if (gn == 6) time_biases(std::integral_constant<int, 6>{});
-                else time_biases(std::integral_constant<int, 1>{});
+                tb_pending = true;
                 if (ds) ds[15] = clock64();
                 continue;
             } else {
@@ -1086,7 +1091,7 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
                 if (tid == 0) {
                     unsigned long long v;
                     do {
-                        v = ld_relaxed_u64(p.acc + step);
+                        v = ld_relaxed_gpu_u64(p.acc + step);
                     } while ((unsigned)(v >> 58) < (unsigned)n_tiles);
                     const bool poisoned = ((v >> 52) & 63ull) != 0ull;
                     s_red[4] = poisoned ? __int_as_float(0x7fc00000) : (float)((double)(v & ((1ull << 52) - 1ull)) * (1.0 / 1048576.0));
