@@ -1189,6 +1189,34 @@ using namespace gpb;
 
 extern "C" size_t gpb_trunk_tc_stream_bytes(void) { return (size_t)kSlotsPerStep * kSlotBytes; }
 
+// Largest row count R the tensor-core samplers accept on the current device for K candidates per object (0 = not at all):
+// every 128-row tile needs one co-resident 4-CTA cluster, and a tile may span at most kMaxObjPerTile objects.
+extern "C" int gpb_sampler_tc_max_rows(int K) {
+    if (K < 1 || 127 / K + 2 > kMaxObjPerTile) return 0;
+    static int cached = -1;                       // per process; the answer depends on the device model only
+    if (cached < 0) {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(kTeam * 64);
+        cfg.blockDim = dim3(kTcThreads);
+        cfg.dynamicSmemBytes = TcSmem<true>::kBytes;
+        cudaLaunchAttribute attr{};
+        attr.id = cudaLaunchAttributeClusterDimension;
+        attr.val.clusterDim.x = kTeam;
+        attr.val.clusterDim.y = 1;
+        attr.val.clusterDim.z = 1;
+        cfg.attrs = &attr;
+        cfg.numAttrs = 1;
+        int n = 0;
+        if (cudaFuncSetAttribute(tc_ode_sampler_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcSmem<true>::kBytes) != cudaSuccess ||
+            cudaOccupancyMaxActiveClusters(&n, tc_ode_sampler_kernel, &cfg) != cudaSuccess) {
+            cudaGetLastError();
+            return 0;
+        }
+        cached = n < 63 ? n : 63;
+    }
+    return cached * kTcRows;
+}
+
 extern "C" int gpb_sample_pc_tc_dbg(const float *x0, int R, int K, int num_steps, float snr, const float *obj_bias, const float *W,
                                     const void *tc_stream, const float *pts_center, const float *step_noise, uint64_t seed,
                                     const float *time_grid, float *mean_x, float *process, void *workspace, size_t workspace_bytes,

@@ -33,6 +33,7 @@ SIGNATURES = {
     "gpb_sample_pc_tc": (_i, [_vp, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _u64, _vp, _vp, _vp, _vp, _sz, _vp]),
     "gpb_sample_pc_tc_dbg": (_i, [_vp, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _u64, _vp, _vp, _vp, _vp, _sz, _vp, _vp]),
     "gpb_sample_ode": (_i, [_vp, _i, _i, _f, _f, _f, _i, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "gpb_sampler_tc_max_rows": (_i, [_i]),
     "gpb_sample_ode_tc": (_i, [_vp, _i, _i, _f, _f, _f, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "gpb_sample_ode_tc_dbg": (_i, [_vp, _i, _i, _f, _f, _f, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _i, _vp]),
     "gpb_energy": (_i, [_vp, _i, _i, _f, _vp, _vp, _vp, _vp, _vp]),

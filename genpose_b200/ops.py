@@ -146,9 +146,9 @@ class Engine:
     # ---- a9: PC sampler -------------------------------------------------------------------------------
     @staticmethod
     def tc_supported(R: int, K: int) -> bool:
-        """tcgen05 sampler constraints: a 128-row tile spans <= 4 objects, four co-resident CTAs per tile."""
-        sms = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
-        return 127 // K + 2 <= 4 and 4 * ((R + 127) // 128) <= sms
+        """tcgen05 sampler constraints (asked of the library): a 128-row tile spans <= 4 objects (K >= 43) and every tile
+        needs one co-resident 4-CTA cluster (33 tiles = 4224 rows on a B200)."""
+        return 0 < R <= lib.load().gpb_sampler_tc_max_rows(int(K))
 
     def sample_pc(self, obj_bias: torch.Tensor, pts_center: torch.Tensor, x0: torch.Tensor, K: int, num_steps: int,
                   step_noise: Optional[torch.Tensor] = None, seed: int = 0, snr: float = arch.SNR,

@@ -156,6 +156,10 @@ GPB_API int gpb_sample_ode(const float *x0, int R, int K, float T0, float rtol, 
                    const float *obj_bias, const float *trunk_weights, const float *pts_center, double *pose,
                    int *stats, void *workspace, size_t workspace_bytes, void *stream);
 
+/* largest R gpb_sample_pc_tc / gpb_sample_ode_tc accept on the current device for K candidates per object (0 = K too
+ * small or no device): one co-resident 4-CTA cluster per 128-row tile. */
+GPB_API int gpb_sampler_tc_max_rows(int K);
+
 /* gpb_sample_ode on the tensor cores: the same solver (same controller, float64 state, one error norm over the whole
  * batch) with the score network's dense layers evaluated by tcgen05.mma (bf16x3 split, fp32 accumulation in tensor
  * memory), four CTAs (one thread-block cluster) per 128-row tile as in gpb_sample_pc_tc.  tc_stream as there.

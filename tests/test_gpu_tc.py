@@ -135,3 +135,25 @@ def test_tc_ode_sampler_against_oracle_and_fp32_kernel(B, K, T0):
     # bitwise reproducible run to run (fixed-order reductions, identical control flow in every CTA)
     p_again, _ = eng.sample_ode(ob, cen, torch.from_numpy(x0).cuda(), K, T0=T0, precision="bf16x3")
     assert torch.equal(p_tc, p_again)
+
+
+def test_tc_capacity_is_asked_of_the_library_and_auto_falls_back():
+    """`precision='auto'` must never hand the tensor-core kernels a batch they cannot hold co-resident: the limit comes from
+    the library (cudaOccupancyMaxActiveClusters), and larger batches run on the FFMA kernels."""
+    from genpose_b200 import ops
+    L = lib.load()
+    assert L.gpb_sampler_tc_max_rows(1) == 0 and L.gpb_sampler_tc_max_rows(42) == 0
+    cap = L.gpb_sampler_tc_max_rows(50)
+    assert cap >= 3200 and cap % 128 == 0                       # the bench shape fits
+    seed, K, T = 13, 50, 6
+    B = cap // K + 2                                            # just too many rows
+    sd = synth.make_state_dict(seed, kappa=synth.stable_kappa(T))
+    eng = ops.Engine(sd)
+    assert eng.tc_supported(3200, K) and not eng.tc_supported(B * K, K)
+    data = synth.batch_from_clouds(synth.make_clouds(B, seed), device="cuda")
+    ob = eng.object_bias(eng.encode(data["pts"]))
+    x0 = torch.from_numpy(synth.make_prior_noise(B * K, seed)).cuda()
+    pose = eng.sample_pc(ob, data["pts_center"], x0, K, T, seed=1, precision="auto")
+    assert torch.isfinite(pose).all()
+    with pytest.raises(lib.GenPoseB200Error):
+        eng.sample_pc(ob, data["pts_center"], x0, K, T, seed=1, precision="bf16x3")
