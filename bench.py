@@ -319,6 +319,8 @@ def main():
     gathered = torch.empty(world * B_PER_GPU, K_CAND, 9, device=dev) if world > 1 else None
     out_host = torch.empty(B_PER_GPU, K_CAND, 9).pin_memory()
 
+    side = torch.cuda.Stream() if eeng is not None else None
+
     def step_resident(i, ev=None):
         feat = eng.encode(clouds_dev)
         ob = eng.object_bias(feat)
@@ -329,7 +331,12 @@ def main():
             ev[1].record()
         res = pose
         if eeng is not None:
-            eob = eeng.object_bias(eeng.encode(clouds_dev))
+            # the energy net's own encoder pass is launched once the sampler is in flight and runs beside it, on the 48 SMs the
+            # sampler's 100 CTAs leave free (the resident clouds are long complete), like PosePipeline.run
+            with torch.cuda.stream(side):
+                eob = eeng.object_bias(eeng.encode(clouds_dev))
+            eob.record_stream(torch.cuda.current_stream())
+            torch.cuda.current_stream().wait_stream(side)
             en = eeng.energy(eob, center_dev, pose, K_CAND, 1e-5)
             _, _, res = ops.rank_pool(pose.view(B_PER_GPU, K_CAND, 9), en.view(B_PER_GPU, K_CAND, 2))
         if world > 1:

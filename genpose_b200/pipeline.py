@@ -25,9 +25,41 @@ class PosePipeline:
         self.score_agent = PoseNet(default_cfg(sampler, sampling_steps, "score", noise_mode, precision))
         self.score_agent.net.load_state_dict(score_state_dict)
         self.energy_agent = None
+        self._side = None
         if energy_state_dict is not None:
             self.energy_agent = PoseNet(default_cfg(sampler, sampling_steps, "energy", noise_mode, precision))
             self.energy_agent.net.load_state_dict(energy_state_dict)
+            # The energy network has its own encoder (evaluation_single.py:431) whose input is the same cloud, and the
+            # tensor-core sampler holds only 100 of the 148 SMs: the second encoder pass runs on a side stream, on the SMs
+            # the sampler leaves free, instead of after it.
+            self._side = torch.cuda.Stream()
+
+    def _mark_clouds_ready(self):
+        """Call on entry, before the score path is enqueued: whatever produced the clouds on the main stream is ordered
+        before this event."""
+        if self._side is not None:
+            self._clouds_ready = torch.cuda.Event()
+            self._clouds_ready.record(torch.cuda.current_stream())
+
+    def _energy_features_async(self, data):
+        """Start the energy net's encoder on the side stream -> pts_feat (join with _energy_rank_pool).  It waits for the
+        clouds only (the event of _mark_clouds_ready), NOT for the main stream: it is launched after the sampler has been
+        enqueued and must run beside it, not behind it."""
+        main = torch.cuda.current_stream()
+        self._side.wait_event(self._clouds_ready)
+        with torch.cuda.stream(self._side):
+            feat = self.energy_agent.net(data, mode="pts_feature")
+        feat.record_stream(main)
+        return feat
+
+    def _energy_rank_pool(self, data, efeat, pred_pose, ratio):
+        pose = pred_pose.float().contiguous()
+        torch.cuda.current_stream().wait_stream(self._side)
+        d2 = dict(data)
+        d2["pts_feat"] = efeat                           # posenet_agent.py:484: extract_pts_feature=False reads data['pts_feat']
+        energy = self.energy_agent.get_energy(data=d2, pose_samples=pose, T=1e-5, extract_pts_feature=False)   # evaluation_single.py:339-343
+        sp, se, rt = ops.rank_pool(pose, energy.contiguous(), ratio=ratio)                                     # :344 + sgpa_utils.py:897
+        return dict(energy=energy, sorted_pose=sp, sorted_energy=se, pooled_RT=rt)
 
     @staticmethod
     def make_batch(pts: torch.Tensor) -> Dict[str, torch.Tensor]:
@@ -37,12 +69,11 @@ class PosePipeline:
 
     def run(self, data: Dict[str, torch.Tensor], repeat_num: int = 50, T0: Optional[float] = None, ratio: float = 0.6):
         """-> dict(pred_pose [B,K,9], and with an energy net: energy [B,K,2], sorted_pose, sorted_energy, pooled_RT [B,4,4])."""
+        self._mark_clouds_ready()
         out = {"pred_pose": self.score_agent.pred_func(data, repeat_num=repeat_num, save_path=None, T0=T0)}
         if self.energy_agent is not None:
-            pose = out["pred_pose"].float().contiguous()
-            energy = self.energy_agent.get_energy(data=data, pose_samples=pose, T=1e-5)            # evaluation_single.py:339-343
-            sp, se, rt = ops.rank_pool(pose, energy.contiguous(), ratio=ratio)                       # :344 + sgpa_utils.py:897
-            out.update(energy=energy, sorted_pose=sp, sorted_energy=se, pooled_RT=rt)
+            efeat = self._energy_features_async(data)     # launched while the sampler (already in flight) runs
+            out.update(self._energy_rank_pool(data, efeat, out["pred_pose"], ratio))
         return out
 
     def track_step(self, data: Dict[str, torch.Tensor], initial_sRT: torch.Tensor, repeat_num: int = 50, T0: float = 0.15,
@@ -53,11 +84,10 @@ class PosePipeline:
         energy, pool the best `ratio` (cal_average_sRT, :58-75).  -> run()'s dict; out['pooled_RT'] feeds the next frame."""
         initial_pose = initial_sRT[:, :3, [0, 1, 3]].permute(0, 2, 1).reshape(initial_sRT.shape[0], -1).float().clone()
         initial_pose[:, -3:] -= data["pts_center"]
+        self._mark_clouds_ready()
         out = {"pred_pose": self.score_agent.pred_func(data, repeat_num=repeat_num, save_path=None, init_x=initial_pose, T0=T0)}
         if self.energy_agent is not None:
-            pose = out["pred_pose"].float().contiguous()
-            energy = self.energy_agent.get_energy(data=data, pose_samples=pose, T=1e-5)
-            sp, se, rt = ops.rank_pool(pose, energy.contiguous(), ratio=ratio)
-            out.update(energy=energy, sorted_pose=sp, sorted_energy=se, pooled_RT=rt)
+            efeat = self._energy_features_async(data)
+            out.update(self._energy_rank_pool(data, efeat, out["pred_pose"], ratio))
         return out
 
