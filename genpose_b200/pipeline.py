@@ -91,3 +91,41 @@ class PosePipeline:
             out.update(self._energy_rank_pool(data, efeat, out["pred_pose"], ratio))
         return out
 
+    def run_stream(self, batches, repeat_num: int = 50):
+        """Throughput mode for a stream of independent batches (PC sampler): yields pred_pose [B,K,9] per batch.  Batch
+        i+1's encoder is launched on a side stream as soon as batch i's sampler is in flight and runs beside it on the SMs the
+        sampler leaves free, so a batch costs the sampler's time only (bench.py `pipelined`: 8.4 -> 7.4 ms per 64 objects).
+        Same kernels and results as run(); only the launch order differs.  `batches` yields `data` dicts (make_batch)."""
+        net = self.score_agent.net
+        if self.score_agent.cfg.sampler_mode[0] != "pc":
+            raise NotImplementedError("run_stream pipelines the PC sampler; use run() for the ODE sampler")
+        eng = net._eng()
+        side = self._side if self._side is not None else torch.cuda.Stream()
+        main = torch.cuda.current_stream()
+
+        def encode(data):
+            ready = torch.cuda.Event()
+            ready.record(main)
+            side.wait_event(ready)
+            with torch.cuda.stream(side):
+                ob = eng.object_bias(eng.encode(data["pts"].float().contiguous(), precision=net.precision))
+            ob.record_stream(main)
+            return ob
+
+        it = iter(batches)
+        cur = next(it, None)
+        ob = encode(cur) if cur is not None else None
+        while cur is not None:
+            main.wait_stream(side)
+            B = cur["pts"].shape[0]
+            R = B * repeat_num
+            x0 = net.prior_fn((R, 9)).to(cur["pts"].device)                                      # samplers.py:117
+            noise, seed = net._step_noise(net.cfg.sampling_steps, R, cur["pts"].device)          # (None, key) in philox mode
+            pose = eng.sample_pc(ob, cur["pts_center"].float().contiguous(), x0.float().contiguous(), repeat_num,
+                                 net.cfg.sampling_steps, step_noise=noise, seed=seed, snr=0.16, precision=net.precision)
+            nxt = next(it, None)
+            if nxt is not None:
+                ob = encode(nxt)
+            yield pose.reshape(B, repeat_num, 9)
+            cur = nxt
+

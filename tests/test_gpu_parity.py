@@ -254,3 +254,19 @@ def test_tracking_warm_start_matches_oracle(ops):
         _, _, rt_ref = O.rank_and_pool(ref.float(), en)
         np.testing.assert_allclose(out["pooled_RT"].cpu().numpy(), np.asarray(rt_ref), rtol=0, atol=2e-3)
         assert out["pooled_RT"].shape == (B, 4, 4)
+
+
+def test_run_stream_equals_run(ops):
+    """PosePipeline.run_stream (next batch's encoder beside the current sampler) must give exactly what run() gives."""
+    from genpose_b200.pipeline import PosePipeline
+    sd = synth.make_state_dict(3, kappa=synth.stable_kappa(30))
+    pipe = PosePipeline(sd, None, sampler="pc", sampling_steps=30)
+    batches = [synth.batch_from_clouds(synth.make_clouds(4, 60 + i), device="cuda") for i in range(3)]
+    torch.manual_seed(1)
+    seq = [pipe.run(dict(b), repeat_num=50)["pred_pose"].clone() for b in batches]
+    torch.manual_seed(1)
+    stream = [p.clone() for p in pipe.run_stream([dict(b) for b in batches], repeat_num=50)]
+    torch.cuda.synchronize()
+    assert len(stream) == 3
+    for a, b in zip(seq, stream):
+        assert torch.equal(a, b)
