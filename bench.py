@@ -381,6 +381,33 @@ def main():
         torch.cuda.synchronize()
         return a.elapsed_time(b)
 
+    def saturating_sampler(n):
+        """the tensor-roofline fraction is also reported at the largest batch the tensor-core sampler holds
+        (every co-resident 4-CTA cluster owns a 128-row tile), sampler launch alone.  Extra key `roofline.saturating_batch`."""
+        b_sat = int(lib.load().gpb_sampler_tc_max_rows(K_CAND)) // K_CAND
+        if b_sat <= B_PER_GPU:
+            return None
+        r_sat = b_sat * K_CAND
+        clouds = torch.from_numpy(synth.make_clouds(b_sat, seed + 1000)).to(dev)
+        ob = eng.object_bias(eng.encode(clouds))
+        cen = clouds.mean(dim=1).contiguous()
+        x0 = torch.from_numpy(synth.make_prior_noise(r_sat, seed + 1000)).to(dev)
+        ms = []
+        for i in range(3 + n):
+            flush.fill_(i & 0xFF)
+            a, b = torch.cuda.Event(True), torch.cuda.Event(True)
+            torch.cuda.synchronize()
+            a.record()
+            eng.sample_pc(ob, cen, x0, K_CAND, T_STEPS, seed=i, precision="bf16x3")
+            b.record()
+            torch.cuda.synchronize()
+            if i >= 3:
+                ms.append(a.elapsed_time(b))
+        k = float(np.mean(ms))
+        tf = r_sat * T_STEPS * FLOP_PER_CAND_STEP / (k / 1000.0) / 1e12
+        return {"objects": b_sat, "rows": r_sat, "kernel_ms": k, "achieved": tf, "frac": tf / peaks["bf16_tflops_sustained"],
+                "candidates_per_s_sampler_only": r_sat / (k / 1000.0)}
+
     def timed(fn, n, with_kernel_events=False):
         per_step, kernel_ms = [], []
         for i in range(n):
@@ -420,6 +447,8 @@ def main():
     sync_all()
     pipelined_ms = pipelined_resident(args.steps) if args.config == 2 else None
     sync_all()
+    saturating = saturating_sampler(min(args.steps, 5)) if (args.config == 2 and use_tc and rank == 0) else None
+    sync_all()
     clock_info = clocks.stop() if rank == 0 else None
 
     total_ms = torch.tensor([sum(per_step), sum(per_step_e2e), pipelined_ms or 0.0], device=dev, dtype=torch.float64)
@@ -456,6 +485,8 @@ def main():
                          "algorithmic_flop_per_launch": R * T_STEPS * FLOP_PER_CAND_STEP},
             "clocks": clock_info,
         }
+        if saturating is not None:
+            line["roofline"]["saturating_batch"] = saturating
         if pipelined_ms is not None:
             line["pipelined"] = {"value": cands / (total_ms[2] / 1000.0), "unit": UNIT, "ms_per_step": total_ms[2] / args.steps,
                                  "note": "extra, not the headline: the same K steps as a stream of batches, batch i+1's encoder on a side "
@@ -463,7 +494,7 @@ def main():
         if clock_info and clock_info.get("sm_mhz"):
             ffma_peak = 148 * 128 * 2 * clock_info["sm_mhz"] * 1e6 / 1e12
             line["roofline"]["frac_ffma"] = ach / ffma_peak
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:                         # rank 0 at N=1 only (the N>1 lines carry none)
             cores = best_cpu_threads(args.ref_objects)
             cpu_oracle_rate(1, K_CAND, 10, args.config, threads=cores)      # page in
             v, secs, detail = cpu_oracle_rate(args.ref_objects, K_CAND, T_STEPS, args.config, threads=cores)

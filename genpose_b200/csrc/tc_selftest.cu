@@ -87,7 +87,9 @@ umma_selftest_kernel(const float *__restrict__ A, const uint16_t *__restrict__ B
     if (warp == 4) {   // MMA issuer: the whole warp runs the loop, one elected lane issues
         mbar_wait(&bar_b, 0);
         tc_fence_after_sync();
-        const uint32_t idesc = make_idesc_bf16_f32(128, N);
+        // swap_fields bit 1 (timing aid only, SS form): issue M = 64 instructions (half the rows; D is then NOT the product the
+        // caller expects) to measure whether a 64-row tile costs half the tensor time of a 128-row one
+        const uint32_t idesc = make_idesc_bf16_f32((swap_fields & 2) ? 64 : 128, N);
         const uint32_t ahi = smem_u32(sAhi), alo = smem_u32(sAlo), bhi = smem_u32(sBhi), blo = smem_u32(sBlo);
         bool acc = false;
         const unsigned long long t_start = clock64();
@@ -112,8 +114,8 @@ umma_selftest_kernel(const float *__restrict__ A, const uint16_t *__restrict__ B
         for (int term = 0; term < n_terms; ++term) {   // 0: Ahi.Bhi  1: Ahi.Blo  2: Alo.Bhi
             const uint32_t a0 = term == 2 ? alo : ahi, b0 = term == 1 ? blo : bhi;
             for (int k16 = 0; k16 < K / 16; ++k16) {
-                const uint64_t ad = swap_fields ? make_smem_desc(a0 + k16 * 2 * a_lbo, a_sbo, a_lbo) : make_smem_desc(a0 + k16 * 2 * a_lbo, a_lbo, a_sbo);
-                const uint64_t bd = swap_fields ? make_smem_desc(b0 + k16 * 2 * b_lbo, b_sbo, b_lbo) : make_smem_desc(b0 + k16 * 2 * b_lbo, b_lbo, b_sbo);
+                const uint64_t ad = (swap_fields & 1) ? make_smem_desc(a0 + k16 * 2 * a_lbo, a_sbo, a_lbo) : make_smem_desc(a0 + k16 * 2 * a_lbo, a_lbo, a_sbo);
+                const uint64_t bd = (swap_fields & 1) ? make_smem_desc(b0 + k16 * 2 * b_lbo, b_sbo, b_lbo) : make_smem_desc(b0 + k16 * 2 * b_lbo, b_lbo, b_sbo);
                 if (elect_one_sync()) {
                     if (a_tmem) umma_bf16_ts(tmem_base, tmem_base + (term == 2 ? 384u : 256u) + (uint32_t)k16 * 8u, bd, idesc, acc);
                     else umma_bf16(tmem_base, ad, bd, idesc, acc);

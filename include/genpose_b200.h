@@ -199,7 +199,8 @@ GPB_API uint64_t gpb_launch_count(void);
  * (4) SELF-TEST of the tcgen05 building block (one CTA: D[128,N] = A[128,K] . B[N,K]^T, bf16 split, fp32
  *     accumulate in TMEM).  A fp32 row-major; Bhi/Blo = bf16 operand images in the canonical K-major
  *     no-swizzle layout (genpose_b200/weights.py::umma_image).  variant/swap_fields select layout
- *     conventions under test; n_terms 1..3 = how many of the bf16x3 products are accumulated; a_tmem = 1 feeds the
+ *     conventions under test (swap_fields bit 0 = LBO/SBO fields exchanged; bit 1 = issue M = 64 instructions, a timing aid
+ *     whose D is not the product); n_terms 1..3 = how many of the bf16x3 products are accumulated; a_tmem = 1 feeds the
  *     A operand from tensor memory (tcgen05.st + the TS form of tcgen05.mma) instead of shared memory; repeat > 1 re-issues
  *     the whole K loop (timing aid: cycles_out[0] = issue cycles, cycles_out[1] = cycles until completion; may be NULL).
  * ---------------------------------------------------------------------------------------------- */
