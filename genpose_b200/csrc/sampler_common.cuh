@@ -17,6 +17,18 @@ __device__ __forceinline__ void gram_schmidt6(float *v) {
     v[3] = c0 / n2; v[4] = c1 / n2; v[5] = c2 / n2;
 }
 
+// the same with MUFU.RSQ reciprocals instead of IEEE sqrt + divisions (<= 2 ulp per factor); min(., 1e12) is the eps clamp
+// (x / max(n, 1e-12)), including n = 0 -> 0.  Used on the tcgen05 sampler's serial update path (tc_sampler.cu).
+__device__ __forceinline__ void gram_schmidt6_rsq(float *v) {
+    const float i1 = fminf(rsqrtf(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]), 1e12f);
+    const float b0 = v[0] * i1, b1 = v[1] * i1, b2 = v[2] * i1;
+    const float d = b0 * v[3] + b1 * v[4] + b2 * v[5];
+    const float c0 = v[3] - d * b0, c1 = v[4] - d * b1, c2 = v[5] - d * b2;
+    const float i2 = fminf(rsqrtf(c0 * c0 + c1 * c1 + c2 * c2), 1e12f);
+    v[0] = b0; v[1] = b1; v[2] = b2;
+    v[3] = c0 * i2; v[4] = c1 * i2; v[5] = c2 * i2;
+}
+
 struct PcParams {
     const float *x0;          // [R,9]
     int R, K, T;

@@ -143,7 +143,7 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
     float *sBias = reinterpret_cast<float *>(smem + kOffBias);
     float *sFpart = reinterpret_cast<float *>(smem + kOffFpart);
     float *sMail = reinterpret_cast<float *>(smem + kOffMail);
-    __shared__ __align__(8) uint64_t bar_full[kSlots], bar_empty[kSlots], bar_acc_full[2], bar_acc_empty[2], bar_x_ready, bar_a_ready,
+    __shared__ __align__(8) uint64_t bar_full[kSlots], bar_empty[kSlots], bar_acc_full[2], bar_acc_empty[2], bar_x_ready, bar_a_ready[2],
         bar_mail[2];
     __shared__ uint32_t s_tmem_base;
     __shared__ float s_red[8];
@@ -172,7 +172,10 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
             mbar_init(&bar_acc_empty[b], kTcRowWarps);
         }
         mbar_init(&bar_x_ready, 4);
-        mbar_init(&bar_a_ready, kTcRowWarps);
+        // one barrier per HALF of a freshly written A operand: a warp's first-half and second-half arrivals must not be
+        // interchangeable (four fast warps arriving twice would otherwise complete the first-half phase for all eight)
+        mbar_init(&bar_a_ready[0], kTcRowWarps);
+        mbar_init(&bar_a_ready[1], kTcRowWarps);
         mbar_init(&bar_mail[0], 1);                // one local arrive.expect_tx per use; the peers' st.async complete the bytes
         mbar_init(&bar_mail[1], 1);
         fence_mbar_init();
@@ -301,7 +304,7 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
                         wait_slots(per);                           // before the operand wait (see layer 0)
                         if (ds) { w_full += clock64() - tq; tq = clock64(); }
                         if (split) {
-                            mbar_wait(&bar_a_ready, ar & 1u);
+                            mbar_wait(&bar_a_ready[g], (ar >> 1) & 1u);   // waits alternate g = 0, 1: phase index of either barrier = ar / 2
                             ++ar;
                         }
                         if (ds) {
@@ -431,6 +434,7 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
         const float step_size = kOde ? 0.f : p.ts[0] - p.ts[1];
         const float sqrt_step = sqrtf(step_size);
         const float snr_norm = (float)((double)p.snr * 3.0);
+        const float snr_R = snr_norm * (float)p.R;   // q = snr |z| / (sum / R)
         uint32_t u = 0;
 
         // ================= ODE mode: helpers and solver state (dead code in the PC instantiation) =================
@@ -677,7 +681,7 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
                         tmem_st_wait();
                         tc_fence_before_sync();
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(&bar_a_ready);
+                        if (lane == 0) mbar_arrive(&bar_a_ready[0]);
                         relu_split32(v, bias + 128, hi, lo);
                         tmem_ld32(tm_row + kColD + b * 128u + (uint32_t)cs * 64u + 32u, v);
                         tmem_ld_wait();
@@ -691,7 +695,7 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
                     tmem_st_wait();
                     tc_fence_before_sync();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&bar_a_ready);
+                    if (lane == 0) mbar_arrive(&bar_a_ready[1]);
                     ++u;
                 }
                 if (ds) ds[2 + 2 * layer] = clock64();
@@ -711,6 +715,27 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
             if (!kOde && cs == 0 && valid) {
                 row_noise(p, step, 0, row, z1);
                 row_noise(p, step, 1, row, z2);
+            }
+            if constexpr (!kOde) {
+                // warps 4-7: (object bias + time bias) table of THIS step, while the tensor core runs the head slice (everyone left
+                // the previous step's table at its barrier 1).  Not in the previous step's tail: a warp that is still here when
+                // x is published would join the layer-0 epilogue late and stall the MMA warp behind it.  Column c0 + 128 j of every
+                // object: the time biases once, then one batch of six independent loads per object.
+                if (cs == 1 && step > 0) {
+                    const int c0 = tid - 128;
+                    const float *tbn = p.tb_table + (size_t)step * 768 + c0;
+                    float tb6[6];
+#pragma unroll
+                    for (int j = 0; j < 6; ++j) tb6[j] = __ldg(tbn + 128 * j);
+                    for (int o = 0; o < n_obj; ++o) {
+                        const float *ob = p.obj_bias + (size_t)(obj_lo + o) * 768 + c0;
+                        float v[6];
+#pragma unroll
+                        for (int j = 0; j < 6; ++j) v[j] = __ldg(ob + 128 * j);
+#pragma unroll
+                        for (int j = 0; j < 6; ++j) sObt[o * 768 + c0 + 128 * j] = v[j] + tb6[j];
+                    }
+                }
             }
             named_bar_sync(3, kTcRowWarps * 32);      // sObt holds obj_bias + t_bias of THIS step (written by warps 4-7)
             // ---- head slice: relu(acc + obj_bias + t_bias) . O, partial sums per touched head (oA: head hA, oB: head hB) ----
@@ -762,11 +787,6 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
             if (cs == 1) {
                 // warps 4-7: table of (object bias + time bias) for the NEXT step, while warps 0-3 exchange / reduce / update
                 if constexpr (!kOde) {
-                    if (step + 1 < p.T) {
-                        const float *tbn = p.tb_table + (size_t)(step + 1) * 768;
-                        for (int i = tid - 128; i < n_obj * 768; i += 128)
-                            sObt[i] = __ldg(p.obj_bias + (size_t)obj_lo * 768 + i) + __ldg(tbn + i % 768);
-                    }
                     continue;
                 } else {
                     if (gi + 1 < gn) {                    // inside an evaluation group: the next time bias is already in tb_mine
@@ -1076,6 +1096,11 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
                 //      RED.release counter + acquire poll + __ldcg of the partials, 2.8 k + 0.9 k cycles per step; per-warp tagged words
                 //      polled by every warp 8.2 k; tagged tile sums polled by one warp per CTA 4.4 k.)  A tile whose sum is NaN or
                 //      >= 2^26 marks the word poisoned and the step's norm becomes NaN, as it would be (or diverge) in the reference.
+                // the step's constants and the predictor drift (0 - g^2 s) dt do not depend on the batch norm: before the grid wait
+                const float g_sde = sigma * kGCoef, g2_sde = g_sde * g_sde, g_sqrt_step = g_sde * sqrt_step;   // ve_sde diffusion (sde.py:20-24)
+                float pd[9];
+#pragma unroll
+                for (int c = 0; c < 9; ++c) pd[c] = (0.0f - g2_sde * gr[c]) * step_size;
                 if (leader) {
                     const float wsum = warp_sum(valid ? sqrtf(n2) : 0.f);
                     if (lane == 0) s_red[q] = wsum;
@@ -1099,24 +1124,28 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
                 }
                 named_bar_sync(2, 128);
                 if (ds) ds[12] = clock64();
+                // Everything between the grid word and the next x is ONE warp per scheduler running a dependent chain with the tensor
+                // core idle, so this update spends latency, not throughput: the reference's divisions by a norm are multiplications by
+                // MUFU.RSQ reciprocals (<= 2 ulp, far below the bf16x3 score's 2^-17), q = snr.R / sum is one fast division and
+                // sqrt(2 ls) = sqrt(4 q^2) = 2 q.  The FFMA parity kernel keeps the IEEE forms (pc_row_update).
                 const float tot = s_red[4];
-                const float grad_norm = tot / (float)p.R;
-                const PcStepConsts sc = pc_step_consts(grad_norm, snr_norm, sigma, step_size, sqrt_step);
+                const float qq = __fdividef(snr_R, tot);                                                     // snr |z| / mean|s| (:130-131)
+                const float ls = 2.0f * (qq * qq), sq2ls = 2.0f * qq;
                 if (valid) {
                     float m[9];
 #pragma unroll
-                    for (int c = 0; c < 9; ++c) x[c] = (x[c] + sc.ls * gr[c]) + sc.sq2ls * z1[c];           // corrector (samplers.py:132)
+                    for (int c = 0; c < 9; ++c) x[c] = (x[c] + ls * gr[c]) + sq2ls * z1[c];                 // corrector (samplers.py:132)
                     {
-                        const float n1 = sqrtf(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);                    // (:142-143), no eps
-                        const float n3 = sqrtf(x[3] * x[3] + x[4] * x[4] + x[5] * x[5]);
-                        x[0] /= n1; x[1] /= n1; x[2] /= n1;
-                        x[3] /= n3; x[4] /= n3; x[5] /= n3;
+                        const float i1 = rsqrtf(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);                   // (:142-143), no eps
+                        const float i3 = rsqrtf(x[3] * x[3] + x[4] * x[4] + x[5] * x[5]);
+                        x[0] *= i1; x[1] *= i1; x[2] *= i1;
+                        x[3] *= i3; x[4] *= i3; x[5] *= i3;
                     }
 #pragma unroll
-                    for (int c = 0; c < 9; ++c) m[c] = x[c] + (0.0f - sc.g2 * gr[c]) * sc.step_size;        // predictor mean (:147-148), sign as written
+                    for (int c = 0; c < 9; ++c) m[c] = x[c] + pd[c];                                         // predictor mean (:147-148), sign as written
 #pragma unroll
-                    for (int c = 0; c < 9; ++c) x[c] = m[c] + (sc.g * sc.sqrt_step) * z2[c];                // (:149)
-                    gram_schmidt6(x);                                                                        // (:152)
+                    for (int c = 0; c < 9; ++c) x[c] = m[c] + g_sqrt_step * z2[c];                           // (:149)
+                    gram_schmidt6_rsq(x);                                                                    // (:152)
                     if (leader) {
                         const float *ctr = p.pts_center + (size_t)(row / p.K) * 3;
                         if (p.process) {
