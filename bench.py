@@ -476,8 +476,8 @@ def main():
                          "bound": "tensor", "achieved": ach, "peak": peak,
                          "unit": "TFLOP/s", "frac": ach / peak,
                          # dram__bytes_read.sum + dram__bytes_write.sum of one 3200-row x 500-step launch, `ncu --set full`
-                         # (profiles/r1h_ncu_tc_sampler.csv); only meaningful for that shape and kernel
-                         "traffic": 3132672 if (use_tc and R == 3200 and T_STEPS == 500) else None, "kernel_ms": k_ms,
+                         # (profiles/r1m_ncu_tc_sampler.csv: 3,025,920 read + 768 written); only meaningful for that shape and kernel
+                         "traffic": 3026688 if (use_tc and R == 3200 and T_STEPS == 500) else None, "kernel_ms": k_ms,
                          "peak_kind": "bf16_tflops_sustained, " + peaks["source"],
                          "note": ("tcgen05 bf16x3: every algorithmic MAC costs 3 tensor-core MACs, so the tensor pipe does 3x `achieved`"
                                   if use_tc else "fp32 FFMA parity path: the tensor pipe is idle; fraction of the fp32-FFMA peak "
