@@ -18,6 +18,11 @@ def pytest_collection_modifyitems(config, items):
 
     has_gpu = torch.cuda.is_available()
     skip_gpu = pytest.mark.skip(reason="no CUDA device")
+    has_timeout = config.pluginmanager.hasplugin("timeout")
     for item in items:
         if "gpu" in item.keywords and not has_gpu:
             item.add_marker(skip_gpu)
+        # A kernel that never returns (a lost arrival in one of the samplers' barrier protocols) must fail the run, not hang the
+        # box: the thread method dumps the stacks and ends the process even while the main thread sits in cudaDeviceSynchronize.
+        if has_timeout and item.get_closest_marker("timeout") is None:
+            item.add_marker(pytest.mark.timeout(180 if "gpu" in item.keywords else 900, method="thread"))
