@@ -385,9 +385,13 @@ def ode_sampler(sd, pts_feat, pts_center, x0, T0: float = 1.0, rtol: float = 1e-
 # ------------------------------------------------------------------------------------------------
 # a11-a13: agent-level functions
 # ------------------------------------------------------------------------------------------------
-def pred_func_pc(sd, data, repeat_num: int, num_steps: int, x0, step_noise, dtype=torch.float32):
-    """PoseNet.pred_func, posenet_agent.py:416-439, sampler 'pc': encoder once, repeat K x, sample."""
-    pts_feat = encode(sd, data["pts"], dtype)
+def pred_func_pc(sd, data, repeat_num: int, num_steps: int, x0, step_noise, dtype=torch.float32, pts_feat=None):
+    """PoseNet.pred_func, posenet_agent.py:416-439, sampler 'pc': encoder once, repeat K x, sample.
+    pts_feat given: skip the encoder and sample from THESE features.  A sampler parity test passes the features of the
+    encoder under test: a feature difference is the same bias error at every step, so a short chain amplifies it coherently
+    (1e-5 of the feature scale moves a T = 20..30 pose by several 1e-3) and would otherwise decide the comparison; the
+    encoder has its own tolerance (1e-4 of the scale) and the end-to-end anchor is the committed golden vectors."""
+    pts_feat = encode(sd, data["pts"], dtype) if pts_feat is None else pts_feat.to(dtype)
     B = pts_feat.shape[0]
     rep_feat = pts_feat.unsqueeze(1).repeat(1, repeat_num, 1).view(B * repeat_num, -1)
     rep_center = data["pts_center"].unsqueeze(1).repeat(1, repeat_num, 1).view(B * repeat_num, -1)

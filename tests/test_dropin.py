@@ -118,7 +118,8 @@ def test_agent_end_to_end_on_gpu(tmp_path):
     x0 = torch.randn(B * K, 9) * 50.0
     like = torch.empty(B * K, 9, device="cuda")
     sn = torch.stack([torch.stack([torch.randn_like(like), torch.randn_like(like)]) for _ in range(T)]).cpu()
-    ref, _ = O.pred_func_pc(sd, synth.batch_from_clouds(synth.make_clouds(B, 3)), K, T, x0, sn)
+    # the oracle samples from the features the agent left in data['pts_feat'] (posenet_agent.py:422); see O.pred_func_pc
+    ref, _ = O.pred_func_pc(sd, synth.batch_from_clouds(synth.make_clouds(B, 3)), K, T, x0, sn, pts_feat=data["pts_feat"].cpu())
     assert float((pose.cpu() - ref).abs().max()) < 1e-3
     cfg_e = get_config(["--sampler_mode", "pc", "--sampling_steps", str(T), "--posenet_mode", "energy"])
     eagent = PoseNet(cfg_e)

@@ -143,12 +143,13 @@ def test_pc_sampler_against_oracle(ops, B, K, T):
     x0 = synth.make_prior_noise(B * K, seed)
     sn = synth.make_step_noise(T, B * K, seed)
     data = synth.batch_from_clouds(clouds)
-    ref_pose, ref_feat = O.pred_func_pc(sd, data, K, T, torch.from_numpy(x0), torch.from_numpy(sn))
     eng = ops.Engine(sd)
-    # FFMA encoder: this test isolates the fp32 sampler.  (At T = 10 the first predictor step multiplies a score
-    # perturbation by g^2*dt = 4.7e3, so the tensor-core encoder's 1e-5 feature difference — checked on its own in
-    # test_encoder_levels_against_oracle — alone moves a translation by 1.5e-3.)
+    # This test isolates the fp32 sampler: FFMA encoder, and the oracle samples from ITS features.  (At T = 10 the first
+    # predictor step multiplies a score perturbation by g^2*dt = 4.7e3, so an encoder's 1e-5 feature difference — checked on
+    # its own in test_encoder_levels_against_oracle — alone moves a translation by 1.5e-3; the end-to-end anchor is
+    # test_fused_path_matches_reference_golden.)
     feat = eng.encode(_dev(clouds), precision="fp32")
+    ref_pose, _ = O.pred_func_pc(sd, data, K, T, torch.from_numpy(x0), torch.from_numpy(sn), pts_feat=feat.cpu())
     ob = eng.object_bias(feat)
     pose, proc = eng.sample_pc(ob, data["pts_center"].cuda(), _dev(x0), K, T, step_noise=_dev(sn), return_process=True)
     # 1e-3 absolute on poses of natural scale; the short chains (T = 10, 30) stop with synthetic translations of O(100),
