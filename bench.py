@@ -200,6 +200,8 @@ def run_ode_line(args, rank, world, local_rank):
     torch.manual_seed(rank)
     x0_dev = ve_prior((R, 9), T=T0).to(dev).contiguous()
     precision = "bf16x3" if args.precision == "bf16x3" or (args.precision == "auto" and eng.tc_supported(R, K_CAND)) else "fp32"
+    if args.precision == "bf16x2":
+        precision = "bf16x2"
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
     out_host = torch.empty(B_PER_GPU, K_CAND, 9, dtype=torch.float64).pin_memory()
     stats_box = {}
@@ -250,7 +252,7 @@ def run_ode_line(args, rank, world, local_rank):
             "metric": "pose-candidates/sec (N=1024 pts, K=50, ODE sampler T0=0.55, rtol=atol=1e-5) — extra line, not BASELINE's metric",
             "value": cands / (tot[0] / 1000.0), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": tot[0] / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16x3 score net, f64 solver state" if precision == "bf16x3" else "f32 score net, f64 solver state", "data": "synthetic",
+            "dtype": f"{precision} score net, f64 solver state" if precision != "fp32" else "f32 score net, f64 solver state", "data": "synthetic",
             "config": {"workload": f"{B_PER_GPU} objects x 1024 pts per GPU, K={K_CAND}, cond_ode_sampler (scripts/eval_single.sh recipe)",
                        "ode_nfev": st[0], "ode_accepted": st[1], "ode_rejected": st[2], "l2_hygiene": "256 MiB buffer written between timed steps"},
             "e2e": {"value": cands / (tot[1] / 1000.0), "unit": UNIT, "h2d_bytes_per_step": int(clouds_host.numel() * 4 + R * 9 * 4),
@@ -274,8 +276,9 @@ def main():
     ap.add_argument("--sampler", default="pc", choices=["pc", "ode"],
                     help="pc = BASELINE.json's metric (T=500 predictor-corrector steps, the default and the headline); ode = the "
                          "reference's shipped recipe (scripts/eval_single.sh: RK45 probability-flow ODE, T0=0.55) as an extra line")
-    ap.add_argument("--precision", default="auto", choices=["auto", "bf16x3", "fp32"],
-                    help="dense layers of the sampler: tcgen05 bf16x3 (auto when the shape allows) or the fp32 FFMA parity kernel")
+    ap.add_argument("--precision", default="auto", choices=["auto", "bf16x3", "fp32", "bf16x2"],
+                    help="dense layers of the sampler: tcgen05 bf16x3 (auto when the shape allows) or the fp32 FFMA parity kernel; "
+                         "bf16x2 = EXPERIMENTAL two-product tensor-core kernel (fp16 weight images), never chosen by auto")
     args = ap.parse_args()
 
     from genpose_b200 import distributed as D
@@ -312,8 +315,9 @@ def main():
     clouds_dev = clouds_host.to(dev)
     center_dev = clouds_dev.mean(dim=1).contiguous()
     R = B_PER_GPU * K_CAND
-    use_tc = args.precision == "bf16x3" or (args.precision == "auto" and eng.tc_supported(R, K_CAND))
-    precision = "bf16x3" if use_tc else "fp32"
+    use_tc = args.precision in ("bf16x3", "bf16x2") or (args.precision == "auto" and eng.tc_supported(R, K_CAND))
+    precision = args.precision if args.precision in ("bf16x3", "bf16x2") else ("bf16x3" if use_tc else "fp32")
+    tc_products = 2 if precision == "bf16x2" else 3
     x0_dev = torch.from_numpy(synth.make_prior_noise(R, seed)).to(dev)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
     gathered = torch.empty(world * B_PER_GPU, K_CAND, 9, device=dev) if world > 1 else None
@@ -398,7 +402,7 @@ def main():
             a, b = torch.cuda.Event(True), torch.cuda.Event(True)
             torch.cuda.synchronize()
             a.record()
-            eng.sample_pc(ob, cen, x0, K_CAND, T_STEPS, seed=i, precision="bf16x3")
+            eng.sample_pc(ob, cen, x0, K_CAND, T_STEPS, seed=i, precision=precision)
             b.record()
             torch.cuda.synchronize()
             if i >= 3:
@@ -466,20 +470,22 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": total_ms[0] / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16x3 (bf16 tensor-core operands, error-compensated split, fp32 accumulate)" if use_tc else "f32",
+            "dtype": ("bf16x3 (bf16 tensor-core operands, error-compensated split, fp32 accumulate)" if precision == "bf16x3" else
+                      "bf16x2 (bf16 hi/lo activations x fp16 weights, fp32 accumulate; experimental)") if use_tc else "f32",
             "data": "synthetic", "config": workload_config(args, world),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(clouds_host.numel() * 4 + R * 9 * 4),
                     "d2h_bytes_per_step": int(out_host.numel() * 4), "ms_per_step": total_ms[1] / args.steps,
                     "api": "PoseNet.pred_func(data, repeat_num=50)" + (" + PoseNet.get_energy + rank_pool" if args.config == 3 else "")},
             "gpu_launches": int(launches),
-            "roofline": {"kernel": ("tc_pc_sampler_kernel" if use_tc else "pc_sampler_kernel") + " (+ time_bias_table_kernel)",
+            "roofline": {"kernel": (("tc_pc_sampler_w16_kernel" if precision == "bf16x2" else "tc_pc_sampler_kernel") if use_tc
+                                    else "pc_sampler_kernel") + " (+ time_bias_table_kernel)",
                          "bound": "tensor", "achieved": ach, "peak": peak,
                          "unit": "TFLOP/s", "frac": ach / peak,
                          # dram__bytes_read.sum + dram__bytes_write.sum of one 3200-row x 500-step launch, `ncu --set full`
                          # (profiles/r1m_ncu_tc_sampler.csv: 3,025,920 read + 768 written); only meaningful for that shape and kernel
-                         "traffic": 3026688 if (use_tc and R == 3200 and T_STEPS == 500) else None, "kernel_ms": k_ms,
+                         "traffic": 3026688 if (precision == "bf16x3" and R == 3200 and T_STEPS == 500) else None, "kernel_ms": k_ms,
                          "peak_kind": "bf16_tflops_sustained, " + peaks["source"],
-                         "note": ("tcgen05 bf16x3: every algorithmic MAC costs 3 tensor-core MACs, so the tensor pipe does 3x `achieved`"
+                         "note": (f"tcgen05 {precision}: every algorithmic MAC costs {tc_products} tensor-core MACs, so the tensor pipe does {tc_products}x `achieved`"
                                   if use_tc else "fp32 FFMA parity path: the tensor pipe is idle; fraction of the fp32-FFMA peak "
                                   "(148 SM x 128 lanes x 2 x clk) is reported as frac_ffma"),
                          "algorithmic_flop_per_launch": R * T_STEPS * FLOP_PER_CAND_STEP},

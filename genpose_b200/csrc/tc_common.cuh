@@ -163,6 +163,11 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16_f32(int M, int N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// the same with the operand formats chosen separately (kind::f16: 0 = fp16, 1 = bf16): e.g. bf16 activations against fp16 weights
+__host__ __device__ constexpr uint32_t make_idesc_f16kind_f32(int M, int N, uint32_t a_fmt, uint32_t b_fmt) {
+    return (1u << 4) | (a_fmt << 7) | (b_fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
 // D[tmem] (+)= A[smem] . B[smem]^T   — issued by ONE thread on behalf of the CTA
 __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, bool accumulate) {
     asm volatile(

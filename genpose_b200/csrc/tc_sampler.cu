@@ -52,10 +52,17 @@ constexpr int kTcRowWarps = 8;
 constexpr int kTcThreads = (kTcRowWarps + 2) * 32;
 constexpr uint32_t kSlotBytes = 16384;
 constexpr int kTeam = 4;                           // CTAs per tile
-constexpr int kCommonSlots = 1 + 16;               // P1 (both units) + P2 (2 units x 8 K-chunks); slot = hi image | lo image
-constexpr int kHeadSlots = 8 + 4;                  // head slice: 128-row unit (8 K-chunks) + 64-row unit (2 K-chunks per slot)
-constexpr int kSlotsPerCtaStep = kCommonSlots + kHeadSlots;      // 29 slots = 464 KiB per CTA and step
-constexpr int kSlotsPerStep = kCommonSlots + kTeam * kHeadSlots; // 65 slots in the global stream
+// Weight stream geometry.  kW16 = false (shipped, "bf16x3"): every weight block as bf16 hi image | lo image, three products per
+// K-step.  kW16 = true ("bf16x2", EXPERIMENTAL: emulated on the CPU in oracle/tc_emulation.py, not yet run on hardware): the
+// weights of layer 1 and of the heads as ONE fp16 image (11-bit mantissa), two products per K-step (Ahi.W + Alo.W) — the
+// activations keep their bf16 hi/lo split, which is what the parity bound needs — so a step streams 15 slots
+// instead of 29 and issues 2/3 of the MMAs.  Layer 0 (K = 16, ten small MMAs) keeps the bf16 hi | lo form in both.
+template <bool kW16> struct TcStream {
+    static constexpr int kCommonSlots = 1 + (kW16 ? 8 : 16);   // P1 (both units) + P2 (2 units x 8 K-chunks of 32; kW16: x 4 slots of K = 64)
+    static constexpr int kHeadSlots = kW16 ? 4 + 2 : 8 + 4;    // head slice: 128-row unit + 64-row unit (kW16: K = 64 / K = 128 per slot)
+    static constexpr int kSlotsPerCtaStep = kCommonSlots + kHeadSlots;        // 29 slots = 464 KiB per CTA and step (kW16: 15 = 240 KiB)
+    static constexpr int kSlotsPerStep = kCommonSlots + kTeam * kHeadSlots;   // 65 slots in the global stream (kW16: 33)
+};
 constexpr uint32_t kLboB64 = 1024;                 // 64-row operand images
 constexpr uint32_t kLboB = 2048, kSbo = 128;       // 128-row operand images
 constexpr int kMaxObjPerTile = 4;
@@ -90,7 +97,7 @@ struct TcOdeParams {
 
 struct TcPcParams {
     PcParams pc;
-    const uint8_t *wstream;   // kSlotsPerStep x 16 KiB of bf16 operand images (genpose_b200/weights.py::pack_trunk_tc)
+    const uint8_t *wstream;   // TcStream::kSlotsPerStep x 16 KiB of operand images (genpose_b200/weights.py::pack_trunk_tc / pack_trunk_tc16)
     TcOdeParams ode;          // used by tc_ode_sampler_kernel only
 };
 
@@ -132,8 +139,9 @@ __device__ __forceinline__ void relu_split32(const uint32_t (&v)[32], const floa
 // epilogues, team exchange) and differ in what the row warps do with the score and in how the trip count is known:
 // PC runs exactly T evaluations; the ODE solver's count depends on its step controller, so the row warps publish how many
 // evaluations are known to exist (s_allowed, always at least one ahead of every decision point) and when the last one is (s_final).
-template <bool kOde>
+template <bool kOde, bool kW16 = false>
 __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
+    using TS = TcStream<kW16>;
     const PcParams &p = tp.pc;
     extern __shared__ __align__(1024) uint8_t smem[];
     constexpr int kSlots = TcSmem<kOde>::kSlots;
@@ -201,6 +209,8 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
     cluster_sync_all();          // the team's mailbox barriers are initialised before anyone arrives remotely
     const uint32_t tmem_base = s_tmem_base;
     const uint32_t idesc128 = make_idesc_bf16_f32(128, 128), idesc64 = make_idesc_bf16_f32(128, 64);
+    // kW16: A = bf16 (tensor memory), B = fp16 (shared memory) in one kind::f16 instruction (separate format fields)
+    const uint32_t idesc128w = make_idesc_f16kind_f32(128, 128, 1, 0), idesc64w = make_idesc_f16kind_f32(128, 64, 1, 0);
     const bool dbg_cta = p.dbg != nullptr && (int)blockIdx.x == p.dbg_cta;
 
     if (warp == kTcRowWarps + 1) {
@@ -208,14 +218,14 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
         if (lane == 0) {
             auto produce = [&](uint32_t it) {
                 const uint32_t s = it % kSlots;
-                const uint32_t idx = it % kSlotsPerCtaStep;
-                const uint32_t src = idx < (uint32_t)kCommonSlots ? idx : idx + (uint32_t)(rank * kHeadSlots);
+                const uint32_t idx = it % TS::kSlotsPerCtaStep;
+                const uint32_t src = idx < (uint32_t)TS::kCommonSlots ? idx : idx + (uint32_t)(rank * TS::kHeadSlots);
                 mbar_wait(&bar_empty[s], ((it / kSlots) & 1u) ^ 1u);
                 mbar_arrive_expect_tx(&bar_full[s], kSlotBytes);
                 bulk_g2s(sRing + s * kSlotBytes, tp.wstream + (size_t)src * kSlotBytes, kSlotBytes, &bar_full[s]);
             };
             if constexpr (!kOde) {
-                const uint32_t total = (uint32_t)p.T * kSlotsPerCtaStep;
+                const uint32_t total = (uint32_t)p.T * TS::kSlotsPerCtaStep;
                 for (uint32_t it = 0; it < total; ++it) produce(it);
             } else {
                 // stream the weights of evaluation e only once it is known to exist; the row warps keep s_allowed one evaluation
@@ -229,7 +239,7 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
                         }
                     }
                     if (!more) break;
-                    for (uint32_t k = 0; k < (uint32_t)kSlotsPerCtaStep; ++k) produce((uint32_t)e * kSlotsPerCtaStep + k);
+                    for (uint32_t k = 0; k < (uint32_t)TS::kSlotsPerCtaStep; ++k) produce((uint32_t)e * TS::kSlotsPerCtaStep + k);
                 }
             }
         }
@@ -298,7 +308,7 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
                     // the MMA warp ~250 cycles even when the data is there (measured: groups of 2 slots, 7.45 -> 8.0 ms per launch), so
                     // groups are as large as the A-operand hand-off allows.  (Also measured without effect: a 10th ring slot, one private
                     // copy of the weight stream per tile team — the waits are not L2 hot-line contention — and one 8-slot wait for unit 0.)
-                    const int groups = split ? 2 : 1, per = split ? 4 : 8;   // (unit 1 in two groups of 4: slower, 7.26 -> 7.35 ms)
+                    const int groups = split ? 2 : 1, per = (split ? 4 : 8) / (kW16 ? 2 : 1);   // (unit 1 in two groups of 4: slower, 7.26 -> 7.35 ms)
                     for (int g = 0; g < groups; ++g) {
                         if (ds) tq = clock64();
                         wait_slots(per);                           // before the operand wait (see layer 0)
@@ -319,6 +329,7 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
                         const uint32_t s_first = it % kSlots;
                         const int kc0 = g * per;
                         if (elect_one_sync()) {
+                            if constexpr (!kW16) {
 #pragma unroll 4
                             for (int kk = 0; kk < per; ++kk) {
                                 const int kc = kc0 + kk;
@@ -336,6 +347,24 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
                                 }
                                 umma_commit(&bar_empty[s]);
                             }
+                            } else {
+                            // one fp16 image of K = 64 per slot: four K-steps, two products each (Ahi.W, Alo.W)
+#pragma unroll 2
+                            for (int kk = 0; kk < per; ++kk) {
+                                uint32_t s = s_first + (uint32_t)kk;
+                                s = s >= (uint32_t)kSlots ? s - (uint32_t)kSlots : s;
+                                const uint32_t sb = ring + s * kSlotBytes;
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    const uint64_t b_w = make_smem_desc(sb + 2u * j * kLboB, kLboB, kSbo);
+                                    const int ks = (kc0 + kk) * 4 + j;                      // K-step (16 inputs) of the unit
+                                    const uint32_t ac = (uint32_t)ks * 8u;                  // K index / 2
+                                    umma_bf16_ts(d, t_ahi + ac, b_w, idesc128w, ks != 0);
+                                    umma_bf16_ts(d, t_alo + ac, b_w, idesc128w, true);
+                                }
+                                umma_commit(&bar_empty[s]);
+                            }
+                            }
                             if (g == groups - 1) umma_commit(&bar_acc_full[b]);
                         }
                         __syncwarp();
@@ -344,13 +373,32 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
                     }
                 } else {
                     if (ds) tq = clock64();
-                    wait_slots(4);
+                    constexpr int kSmallSlots = kW16 ? 2 : 4;
+                    wait_slots(kSmallSlots);
                     if (ds) { w_full += clock64() - tq; tq = clock64(); }
                     mbar_wait(&bar_acc_empty[b], (n & 1u) ^ 1u);
                     tc_fence_after_sync();
                     if (ds) { w_acc += clock64() - tq; tq = clock64(); }
                     const uint32_t s_first = it % kSlots;
                     if (elect_one_sync()) {
+                        if constexpr (kW16) {
+                        // one fp16 image of K = 128 per slot (64 rows): eight K-steps, two products each
+#pragma unroll
+                        for (int sl = 0; sl < 2; ++sl) {
+                            uint32_t s = s_first + (uint32_t)sl;
+                            s = s >= (uint32_t)kSlots ? s - (uint32_t)kSlots : s;
+                            const uint32_t sb = ring + s * kSlotBytes;
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                const uint64_t b_w = make_smem_desc(sb + 2u * j * kLboB64, kLboB64, kSbo);
+                                const int ks = sl * 8 + j;
+                                const uint32_t ac = (uint32_t)ks * 8u;
+                                umma_bf16_ts(d, t_ahi + ac, b_w, idesc64w, ks != 0);
+                                umma_bf16_ts(d, t_alo + ac, b_w, idesc64w, true);
+                            }
+                            umma_commit(&bar_empty[s]);
+                        }
+                        } else {
 #pragma unroll
                         for (int sl = 0; sl < 4; ++sl) {
                             uint32_t s = s_first + (uint32_t)sl;
@@ -370,11 +418,12 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
                             }
                             umma_commit(&bar_empty[s]);
                         }
+                        }
                         umma_commit(&bar_acc_full[b]);
                     }
                     __syncwarp();
                     if (ds) w_issue += clock64() - tq;
-                    it += 4u;
+                    it += (uint32_t)kSmallSlots;
                 }
                 ++u;
             }
@@ -1181,6 +1230,15 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 tc_ode_sampler_kernel(TcPcParams tp) {
     tc_sampler_body<true>(tp);
 }
+// EXPERIMENTAL (see TcStream): fp16 weight images, two products per K-step
+__global__ void __launch_bounds__(kTcThreads, 1)
+tc_pc_sampler_w16_kernel(TcPcParams tp) {
+    tc_sampler_body<false, true>(tp);
+}
+__global__ void __launch_bounds__(kTcThreads, 1)
+tc_ode_sampler_w16_kernel(TcPcParams tp) {
+    tc_sampler_body<true, true>(tp);
+}
 
 // cluster (4 CTAs = one tile team, DSMEM) + cooperative (grid barrier => all CTAs must be co-resident) launch of either kernel
 static int launch_tc_sampler(void (*kernel)(TcPcParams), const char *what, const TcPcParams &tp, int n_tiles, uint32_t smem_bytes,
@@ -1216,7 +1274,8 @@ static int launch_tc_sampler(void (*kernel)(TcPcParams), const char *what, const
 
 using namespace gpb;
 
-extern "C" size_t gpb_trunk_tc_stream_bytes(void) { return (size_t)kSlotsPerStep * kSlotBytes; }
+extern "C" size_t gpb_trunk_tc_stream_bytes(void) { return (size_t)TcStream<false>::kSlotsPerStep * kSlotBytes; }
+extern "C" size_t gpb_trunk_tc16_stream_bytes(void) { return (size_t)TcStream<true>::kSlotsPerStep * kSlotBytes; }
 
 // Largest row count R the tensor-core samplers accept on the current device for K candidates per object (0 = not at all):
 // every 128-row tile needs one co-resident 4-CTA cluster, and a tile may span at most kMaxObjPerTile objects.
@@ -1246,10 +1305,10 @@ extern "C" int gpb_sampler_tc_max_rows(int K) {
     return cached * kTcRows;
 }
 
-extern "C" int gpb_sample_pc_tc_dbg(const float *x0, int R, int K, int num_steps, float snr, const float *obj_bias, const float *W,
-                                    const void *tc_stream, const float *pts_center, const float *step_noise, uint64_t seed,
-                                    const float *time_grid, float *mean_x, float *process, void *workspace, size_t workspace_bytes,
-                                    unsigned long long *dbg, void *stream) {
+static int sample_pc_tc_impl(bool w16, const float *x0, int R, int K, int num_steps, float snr, const float *obj_bias, const float *W,
+                             const void *tc_stream, const float *pts_center, const float *step_noise, uint64_t seed,
+                             const float *time_grid, float *mean_x, float *process, void *workspace, size_t workspace_bytes,
+                             unsigned long long *dbg, void *stream) {
     const int dbg_cta_sel = (int)(seed >> 56);   // profiling aid: the top byte of the seed selects the recording CTA when dbg != NULL
     GPB_REQUIRE(R >= 0 && K >= 1 && num_steps >= 2, "sample_pc_tc: need R >= 0, K >= 1, num_steps >= 2");
     if (R == 0) return GPB_OK;
@@ -1286,13 +1345,29 @@ extern "C" int gpb_sample_pc_tc_dbg(const float *x0, int R, int K, int num_steps
     p.mean_x = mean_x; p.process = process; p.tiles_per_cta = 1; p.dbg = dbg; p.dbg_cta = dbg ? dbg_cta_sel : 0;
     tp.wstream = reinterpret_cast<const uint8_t *>(tc_stream);
 
-    return launch_tc_sampler(tc_pc_sampler_kernel, "sample_pc_tc", tp, n_tiles, TcSmem<false>::kBytes, st);
+    return launch_tc_sampler(w16 ? tc_pc_sampler_w16_kernel : tc_pc_sampler_kernel, "sample_pc_tc", tp, n_tiles, TcSmem<false>::kBytes, st);
 }
 
-extern "C" int gpb_sample_ode_tc_dbg(const float *x0, int R, int K, float T0, float rtol, float atol, int denoise_steps,
-                                     const float *obj_bias, const float *W, const void *tc_stream, const float *pts_center, double *pose,
-                                     int *stats, void *workspace, size_t workspace_bytes, unsigned long long *dbg, int dbg_evals,
-                                     void *stream) {
+extern "C" int gpb_sample_pc_tc_dbg(const float *x0, int R, int K, int num_steps, float snr, const float *obj_bias, const float *W,
+                                    const void *tc_stream, const float *pts_center, const float *step_noise, uint64_t seed,
+                                    const float *time_grid, float *mean_x, float *process, void *workspace, size_t workspace_bytes,
+                                    unsigned long long *dbg, void *stream) {
+    return sample_pc_tc_impl(false, x0, R, K, num_steps, snr, obj_bias, W, tc_stream, pts_center, step_noise, seed, time_grid, mean_x,
+                             process, workspace, workspace_bytes, dbg, stream);
+}
+
+extern "C" int gpb_sample_pc_tc16(const float *x0, int R, int K, int num_steps, float snr, const float *obj_bias, const float *W,
+                                  const void *tc16_stream, const float *pts_center, const float *step_noise, uint64_t seed,
+                                  const float *time_grid, float *mean_x, float *process, void *workspace, size_t workspace_bytes,
+                                  unsigned long long *dbg, void *stream) {
+    return sample_pc_tc_impl(true, x0, R, K, num_steps, snr, obj_bias, W, tc16_stream, pts_center, step_noise, seed, time_grid, mean_x,
+                             process, workspace, workspace_bytes, dbg, stream);
+}
+
+static int sample_ode_tc_impl(bool w16, const float *x0, int R, int K, float T0, float rtol, float atol, int denoise_steps,
+                              const float *obj_bias, const float *W, const void *tc_stream, const float *pts_center, double *pose,
+                              int *stats, void *workspace, size_t workspace_bytes, unsigned long long *dbg, int dbg_evals,
+                              void *stream) {
     GPB_REQUIRE(R >= 0 && K >= 1, "sample_ode_tc: need R >= 0, K >= 1");
     if (R == 0) return GPB_OK;
     GPB_REQUIRE(x0 && obj_bias && W && tc_stream && pts_center && pose && workspace, "sample_ode_tc: NULL buffer");
@@ -1324,7 +1399,22 @@ extern "C" int gpb_sample_ode_tc_dbg(const float *x0, int R, int K, float T0, fl
     tp.ode.T0 = T0; tp.ode.rtol = rtol; tp.ode.atol = atol; tp.ode.denoise_steps = denoise_steps;
     tp.ode.Kst = w.Kst; tp.ode.partial = reinterpret_cast<double *>(w.partial); tp.ode.tb_cta = w.tb_cta;
     tp.ode.pose = pose; tp.ode.stats = stats;
-    return launch_tc_sampler(tc_ode_sampler_kernel, "sample_ode_tc", tp, n_tiles, TcSmem<true>::kBytes, st);
+    return launch_tc_sampler(w16 ? tc_ode_sampler_w16_kernel : tc_ode_sampler_kernel, "sample_ode_tc", tp, n_tiles, TcSmem<true>::kBytes, st);
+}
+
+extern "C" int gpb_sample_ode_tc_dbg(const float *x0, int R, int K, float T0, float rtol, float atol, int denoise_steps,
+                                     const float *obj_bias, const float *W, const void *tc_stream, const float *pts_center, double *pose,
+                                     int *stats, void *workspace, size_t workspace_bytes, unsigned long long *dbg, int dbg_evals,
+                                     void *stream) {
+    return sample_ode_tc_impl(false, x0, R, K, T0, rtol, atol, denoise_steps, obj_bias, W, tc_stream, pts_center, pose, stats, workspace,
+                              workspace_bytes, dbg, dbg_evals, stream);
+}
+
+extern "C" int gpb_sample_ode_tc16(const float *x0, int R, int K, float T0, float rtol, float atol, int denoise_steps,
+                                   const float *obj_bias, const float *W, const void *tc16_stream, const float *pts_center, double *pose,
+                                   int *stats, void *workspace, size_t workspace_bytes, void *stream) {
+    return sample_ode_tc_impl(true, x0, R, K, T0, rtol, atol, denoise_steps, obj_bias, W, tc16_stream, pts_center, pose, stats, workspace,
+                              workspace_bytes, nullptr, 0, stream);
 }
 
 extern "C" int gpb_sample_pc_tc(const float *x0, int R, int K, int num_steps, float snr, const float *obj_bias, const float *W,

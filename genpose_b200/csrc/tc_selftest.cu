@@ -89,7 +89,10 @@ umma_selftest_kernel(const float *__restrict__ A, const uint16_t *__restrict__ B
         tc_fence_after_sync();
         // swap_fields bit 1 (timing aid only, SS form): issue M = 64 instructions (half the rows; D is then NOT the product the
         // caller expects) to measure whether a 64-row tile costs half the tensor time of a 128-row one
-        const uint32_t idesc = make_idesc_bf16_f32((swap_fields & 2) ? 64 : 128, N);
+        // swap_fields bit 2: the B images hold fp16 (not bf16) values and only two products are formed, Ahi.B (term 0) and Alo.B
+        // (term 1) — the mixed-format instruction of the two-product samplers (A = bf16, B = fp16 in one kind::f16 MMA)
+        const bool w16 = (swap_fields & 4) != 0;
+        const uint32_t idesc = w16 ? make_idesc_f16kind_f32((swap_fields & 2) ? 64 : 128, N, 1, 0) : make_idesc_bf16_f32((swap_fields & 2) ? 64 : 128, N);
         const uint32_t ahi = smem_u32(sAhi), alo = smem_u32(sAlo), bhi = smem_u32(sBhi), blo = smem_u32(sBlo);
         bool acc = false;
         const unsigned long long t_start = clock64();
@@ -98,11 +101,12 @@ umma_selftest_kernel(const float *__restrict__ A, const uint16_t *__restrict__ B
             if (elect_one_sync()) {
                 for (int rep = 0; rep < repeat; ++rep)
                     for (int term = 0; term < n_terms; ++term) {
-                        const uint32_t a0 = term == 2 ? alo : ahi, b0 = term == 1 ? blo : bhi;
+                        const bool a_lo = w16 ? term == 1 : term == 2;
+                        const uint32_t a0 = a_lo ? alo : ahi, b0 = (!w16 && term == 1) ? blo : bhi;
                         for (int k16 = 0; k16 < K / 16; ++k16) {
                             const uint64_t ad = make_smem_desc(a0 + k16 * 2 * a_lbo, a_lbo, a_sbo);
                             const uint64_t bd = make_smem_desc(b0 + k16 * 2 * b_lbo, b_lbo, b_sbo);
-                            if (a_tmem) umma_bf16_ts(tmem_base, tmem_base + (term == 2 ? 384u : 256u) + (uint32_t)k16 * 8u, bd, idesc, acc);
+                            if (a_tmem) umma_bf16_ts(tmem_base, tmem_base + (a_lo ? 384u : 256u) + (uint32_t)k16 * 8u, bd, idesc, acc);
                             else umma_bf16(tmem_base, ad, bd, idesc, acc);
                             acc = true;
                         }
@@ -111,13 +115,14 @@ umma_selftest_kernel(const float *__restrict__ A, const uint16_t *__restrict__ B
             __syncwarp();
         } else
         for (int rep = 0; rep < repeat; ++rep)
-        for (int term = 0; term < n_terms; ++term) {   // 0: Ahi.Bhi  1: Ahi.Blo  2: Alo.Bhi
-            const uint32_t a0 = term == 2 ? alo : ahi, b0 = term == 1 ? blo : bhi;
+        for (int term = 0; term < n_terms; ++term) {   // 0: Ahi.Bhi  1: Ahi.Blo  2: Alo.Bhi   (w16: 0: Ahi.B  1: Alo.B)
+            const bool a_lo = w16 ? term == 1 : term == 2;
+            const uint32_t a0 = a_lo ? alo : ahi, b0 = (!w16 && term == 1) ? blo : bhi;
             for (int k16 = 0; k16 < K / 16; ++k16) {
                 const uint64_t ad = (swap_fields & 1) ? make_smem_desc(a0 + k16 * 2 * a_lbo, a_sbo, a_lbo) : make_smem_desc(a0 + k16 * 2 * a_lbo, a_lbo, a_sbo);
                 const uint64_t bd = (swap_fields & 1) ? make_smem_desc(b0 + k16 * 2 * b_lbo, b_sbo, b_lbo) : make_smem_desc(b0 + k16 * 2 * b_lbo, b_lbo, b_sbo);
                 if (elect_one_sync()) {
-                    if (a_tmem) umma_bf16_ts(tmem_base, tmem_base + (term == 2 ? 384u : 256u) + (uint32_t)k16 * 8u, bd, idesc, acc);
+                    if (a_tmem) umma_bf16_ts(tmem_base, tmem_base + (a_lo ? 384u : 256u) + (uint32_t)k16 * 8u, bd, idesc, acc);
                     else umma_bf16(tmem_base, ad, bd, idesc, acc);
                 }
                 __syncwarp();

@@ -96,6 +96,17 @@ class Engine:
             raise lib.GenPoseB200Error("tensor-core encoder image size disagrees with the library")
         self.enc_tc = etc.to(self.device)
         self._ws: Dict[Tuple[str, int], torch.Tensor] = {}
+        self._state_for_tc16 = state_dict
+        self._trunk_tc16: Optional[torch.Tensor] = None
+
+    def trunk_tc16(self) -> torch.Tensor:
+        """EXPERIMENTAL two-product stream (weights.pack_trunk_tc16), packed on first use of precision='bf16x2'."""
+        if self._trunk_tc16 is None:
+            tc = weights.pack_trunk_tc16(self._state_for_tc16)
+            if tc.numel() * 2 != lib.load().gpb_trunk_tc16_stream_bytes():
+                raise lib.GenPoseB200Error("two-product weight stream size disagrees with the library")
+            self._trunk_tc16 = tc.to(self.device)
+        return self._trunk_tc16
 
     def _workspace(self, kind: str, nbytes: int) -> torch.Tensor:
         ws = self._ws.get(kind)
@@ -108,7 +119,7 @@ class Engine:
     def encode(self, pts: torch.Tensor, return_fps: bool = False, precision: str = "auto"):
         """Pointnet2ClsMSG.forward: pts [B,1024,3] (raw camera frame) -> pts_feat [B,1024].
         precision 'fp32' = every level on FFMA; 'bf16x3' / 'auto' = set-abstraction level 3 on tcgen05 (bf16x3 split)."""
-        if precision not in ("auto", "bf16x3", "fp32"):
+        if precision not in ("auto", "bf16x3", "bf16x2", "fp32"):      # 'bf16x2' concerns the samplers only: tensor-core encoder as 'bf16x3'
             raise lib.GenPoseB200Error(f"encode: unknown precision {precision!r}")
         B, N, C = pts.shape
         if N != arch.NUM_POINTS or C != 3:
@@ -154,11 +165,12 @@ class Engine:
                   step_noise: Optional[torch.Tensor] = None, seed: int = 0, snr: float = arch.SNR,
                   return_process: bool = False, precision: str = "fp32"):
         """precision 'fp32' = FFMA parity kernel; 'bf16x3' = tcgen05 tensor-core kernel; 'auto' = tensor cores when
-        the shape allows."""
+        the shape allows; 'bf16x2' = EXPERIMENTAL two-product tensor-core kernel (fp16 weight images, include/genpose_b200.h),
+        never chosen by 'auto'."""
         R = x0.shape[0]
         if precision == "auto":
             precision = "bf16x3" if self.tc_supported(R, K) else "fp32"
-        if precision not in ("fp32", "bf16x3"):
+        if precision not in ("fp32", "bf16x3", "bf16x2"):
             raise lib.GenPoseB200Error(f"sample_pc: unknown precision {precision!r}")
         L = lib.load()
         ws = self._workspace("samp", L.gpb_sampler_workspace_bytes(R, num_steps))
@@ -175,6 +187,9 @@ class Engine:
         if precision == "bf16x3":
             lib.check(L.gpb_sample_pc_tc(*head, self.trunk_tc.data_ptr(), _chk(pts_center, torch.float32, "pts_center"), *common),
                       "sample_pc_tc")
+        elif precision == "bf16x2":
+            lib.check(L.gpb_sample_pc_tc16(*head, self.trunk_tc16().data_ptr(), _chk(pts_center, torch.float32, "pts_center"),
+                                           *common[:-1], 0, common[-1]), "sample_pc_tc16")
         else:
             lib.check(L.gpb_sample_pc(*head, _chk(pts_center, torch.float32, "pts_center"), *common), "sample_pc")
         return (mean_x, process) if return_process else mean_x
@@ -183,11 +198,12 @@ class Engine:
     def sample_ode(self, obj_bias: torch.Tensor, pts_center: torch.Tensor, x0: torch.Tensor, K: int, T0: float = 1.0,
                    rtol: float = 1e-5, atol: float = 1e-5, denoise_steps: int = 1000, precision: str = "fp32"):
         """cond_ode_sampler (samplers.py:163-227): RK45 with SciPy's controller on device -> (pose [R,9] float64, stats [4]).
-        precision 'fp32' = FFMA parity kernel; 'bf16x3' = tcgen05 kernel; 'auto' = tensor cores when the shape allows."""
+        precision 'fp32' = FFMA parity kernel; 'bf16x3' = tcgen05 kernel; 'auto' = tensor cores when the shape allows;
+        'bf16x2' = EXPERIMENTAL two-product tensor-core kernel, never chosen by 'auto'."""
         R = x0.shape[0]
         if precision == "auto":
             precision = "bf16x3" if self.tc_supported(R, K) else "fp32"
-        if precision not in ("fp32", "bf16x3"):
+        if precision not in ("fp32", "bf16x3", "bf16x2"):
             raise lib.GenPoseB200Error(f"sample_ode: unknown precision {precision!r}")
         L = lib.load()
         ws = self._workspace("samp", L.gpb_sampler_workspace_bytes(R, 1))
@@ -198,6 +214,8 @@ class Engine:
         tail = (_chk(pts_center, torch.float32, "pts_center"), pose.data_ptr(), stats.data_ptr(), ws.data_ptr(), ws.numel(), _stream())
         if precision == "bf16x3":
             lib.check(L.gpb_sample_ode_tc(*head, self.trunk_tc.data_ptr(), *tail), "sample_ode_tc")
+        elif precision == "bf16x2":
+            lib.check(L.gpb_sample_ode_tc16(*head, self.trunk_tc16().data_ptr(), *tail), "sample_ode_tc16")
         else:
             lib.check(L.gpb_sample_ode(*head, *tail), "sample_ode")
         return pose, stats

@@ -270,3 +270,37 @@ def pack_trunk_tc(sd: Dict[str, torch.Tensor], prefix: str = "pose_score_net") -
         slots += unit_slots(stacked[192 * r + 128: 192 * r + 192], 2)
     assert all(sl.numel() * 2 == 16384 for sl in slots) and len(slots) == 65, (len(slots), {sl.numel() for sl in slots})
     return torch.cat(slots).contiguous()
+
+
+FP16_MAX = 65504.0
+
+
+def pack_trunk_tc16(sd: Dict[str, torch.Tensor], prefix: str = "pose_score_net") -> torch.Tensor:
+    """EXPERIMENTAL weight stream of the two-product tensor-core samplers (tc_sampler.cu, TcStream<true>): 33 slots of 16 KiB
+    (int16 words), K-major no-swizzle operand blocks [K/8][rows][8] like pack_trunk_tc, but the weights of layer 1 and of the heads
+    as ONE fp16 image each (no lo image):
+         slot 0          : P1 exactly as in pack_trunk_tc (bf16 hi | lo per unit; layer 0 keeps its five products)
+         slots 1..8      : P2: for unit in ([0,128), [128,256)): 4 slots, slot q = inputs [64q, 64q+64) of the 128 rows (fp16)
+         slots 9+6r..    : head slice of team rank r: 4 slots (units [192r, 192r+128), K = 64 each), then 2 slots
+                           (units [192r+128, 192r+192), K = 128 each)
+    Weights beyond the fp16 range are refused (use the three-product stream)."""
+    g = lambda k: sd[f"{prefix}.{k}"].float()
+    slots = [pack_trunk_tc(sd, prefix)[:8192]]                                   # slot 0: 16 KiB = 8192 int16 words
+
+    def unit_slots16(w_rows, k_per_slot):
+        if float(w_rows.abs().max()) >= FP16_MAX:
+            raise ValueError("pack_trunk_tc16: a weight exceeds the fp16 range; use pack_trunk_tc (bf16x3)")
+        rows = w_rows.shape[0]
+        img = umma_image(w_rows.to(torch.float16).view(torch.int16).view(rows, -1).view(torch.bfloat16)).reshape(32, rows * 8)
+        return [img[k0 // 8: (k0 + k_per_slot) // 8].reshape(-1) for k0 in range(0, 256, k_per_slot)]
+
+    p2 = g("pose_encoder.2.weight")
+    for unit in range(2):
+        slots += unit_slots16(p2[128 * unit: 128 * unit + 128], 64)
+    off = arch.PTS_FEAT_DIM + arch.T_EMBED_DIM
+    stacked = torch.cat([g(f"fusion_tail_{h}.0.weight")[:, off:] for h in arch.HEADS], dim=0)      # [768, 256]
+    for r in range(4):
+        slots += unit_slots16(stacked[192 * r: 192 * r + 128], 64)
+        slots += unit_slots16(stacked[192 * r + 128: 192 * r + 192], 128)
+    assert all(sl.numel() * 2 == 16384 for sl in slots) and len(slots) == 33, (len(slots), {sl.numel() for sl in slots})
+    return torch.cat(slots).contiguous()

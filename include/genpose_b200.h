@@ -175,6 +175,22 @@ GPB_API int gpb_sample_ode_tc_dbg(const float *x0, int R, int K, float T0, float
                           double *pose, int *stats, void *workspace, size_t workspace_bytes, unsigned long long *dbg,
                           int dbg_evals, void *stream);
 
+/* EXPERIMENTAL — arithmetic emulated on the CPU (oracle/tc_emulation.py: within 0.5 of the parity bound on the shortest chains,
+ * 0.03 at T = 500), kernels not yet run on hardware; nothing selects them unless the caller asks for precision "bf16x2".
+ * gpb_sample_pc_tc / gpb_sample_ode_tc with TWO tensor-core products per K-step instead of three: the activations keep their
+ * bf16 hi/lo split (tensor memory), the weights of layer 1 and of the heads are ONE fp16 image (11-bit mantissa) — the
+ * dropped Ahi.Blo product only carried the weights' bits beyond bf16.  tc16_stream = gpb_trunk_tc16_stream_bytes() bytes
+ * from genpose_b200/weights.py::pack_trunk_tc16 (33 slots of 16 KiB; 15 per CTA and step instead of 29).  Same constraints,
+ * workspace and semantics as the functions they mirror; dbg as in gpb_sample_pc_tc_dbg (may be NULL). */
+GPB_API size_t gpb_trunk_tc16_stream_bytes(void);
+GPB_API int gpb_sample_pc_tc16(const float *x0, int R, int K, int num_steps, float snr, const float *obj_bias,
+                       const float *trunk_weights, const void *tc16_stream, const float *pts_center,
+                       const float *step_noise, uint64_t seed, const float *time_grid, float *mean_x, float *process,
+                       void *workspace, size_t workspace_bytes, unsigned long long *dbg, void *stream);
+GPB_API int gpb_sample_ode_tc16(const float *x0, int R, int K, float T0, float rtol, float atol, int denoise_steps,
+                        const float *obj_bias, const float *trunk_weights, const void *tc16_stream, const float *pts_center,
+                        double *pose, int *stats, void *workspace, size_t workspace_bytes, void *stream);
+
 /* replaces PoseNet.get_energy's arithmetic after the encoder (networks/posenet_agent.py:508-523 ->
  * PoseEnergyNet.get_energy energynet.py:143-198, 'IP' decoupled): energy [B,K,2] = (rot, trans). */
 GPB_API int gpb_energy(const float *pose, int R, int K, float t, const float *obj_bias, const float *trunk_weights,
@@ -200,7 +216,8 @@ GPB_API uint64_t gpb_launch_count(void);
  *     accumulate in TMEM).  A fp32 row-major; Bhi/Blo = bf16 operand images in the canonical K-major
  *     no-swizzle layout (genpose_b200/weights.py::umma_image).  variant/swap_fields select layout
  *     conventions under test (swap_fields bit 0 = LBO/SBO fields exchanged; bit 1 = issue M = 64 instructions, a timing aid
- *     whose D is not the product); n_terms 1..3 = how many of the bf16x3 products are accumulated; a_tmem = 1 feeds the
+ *     whose D is not the product; bit 2 = Bhi holds fp16 values and the products are Ahi.B, Alo.B — the mixed-format
+ *     instruction of the two-product samplers, n_terms <= 2); n_terms 1..3 = how many of the bf16x3 products are accumulated; a_tmem = 1 feeds the
  *     A operand from tensor memory (tcgen05.st + the TS form of tcgen05.mma) instead of shared memory; repeat > 1 re-issues
  *     the whole K loop (timing aid: cycles_out[0] = issue cycles, cycles_out[1] = cycles until completion; may be NULL).
  * ---------------------------------------------------------------------------------------------- */

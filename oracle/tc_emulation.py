@@ -7,8 +7,9 @@ pin DESIGN.md §5's precision claim in the CPU suite.  It restates what the kern
   * layer 0 from THREE bf16 pieces of the pose row (x1 + x2 + x3) against P1 hi | lo (five products, publish_x);
   * everything the kernel hoists out of the row loop in fp32: object bias A_pts.pts_feat + a, time bias A_t.relu(L_t.fourier(t)).
 
-`terms` selects how many products of the split are kept (3 = shipped, 1 = plain bf16) so that a test can show why the split is
-needed.  The score network it emulates is PoseScoreNet.forward (networks/gf_algorithms/scorenet.py:178-222)."""
+`terms` selects how many products of the split are kept (3 = shipped "bf16x3", 1 = plain bf16) so that a test can show why the
+split is needed; terms = "x2" is the experimental two-product mode (tc_sampler.cu, TcStream<true>): activations bf16 hi + lo,
+the weights of layer 1 and of the heads ONE fp16 value each, products Ahi.W + Alo.W (layer 0 keeps its five bf16 products).  The score network it emulates is PoseScoreNet.forward (networks/gf_algorithms/scorenet.py:178-222)."""
 from contextlib import contextmanager
 
 import numpy as np
@@ -24,9 +25,12 @@ def split_bf16(t: torch.Tensor):
     return hi, lo
 
 
-def mm_split(a: torch.Tensor, w: torch.Tensor, terms: int = 3) -> torch.Tensor:
+def mm_split(a: torch.Tensor, w: torch.Tensor, terms=3) -> torch.Tensor:
     """a [R,K] . w [N,K]^T with both operands split into bf16 hi + lo; products are exact in fp32, sums are fp32."""
     ah, al = split_bf16(a)
+    if terms == "x2":
+        w16 = w.float().to(torch.float16).float()
+        return ah @ w16.t() + al @ w16.t()
     wh, wl = split_bf16(w)
     out = ah @ wh.t()
     if terms >= 2:
@@ -36,7 +40,7 @@ def mm_split(a: torch.Tensor, w: torch.Tensor, terms: int = 3) -> torch.Tensor:
     return out
 
 
-def trunk_tc(sd, pts_feat, pose, t, terms: int = 3, prefix: str = "pose_score_net") -> torch.Tensor:
+def trunk_tc(sd, pts_feat, pose, t, terms=3, prefix: str = "pose_score_net") -> torch.Tensor:
     g = lambda k: sd[f"{prefix}.{k}"].float()
     tt = t.float().squeeze(1)
     x_proj = tt[:, None] * g("t_encoder.0.W")[None, :] * 2 * np.pi                      # scorenet.py:63
@@ -47,10 +51,11 @@ def trunk_tc(sd, pts_feat, pose, t, terms: int = 3, prefix: str = "pose_score_ne
     x2 = (x - x1).to(torch.bfloat16).float()
     x3 = (x - x1 - x2).to(torch.bfloat16).float()
     ph, pl = split_bf16(g("pose_encoder.0.weight"))
+    l0_terms = 3 if terms == "x2" else terms
     acc = x1 @ ph.t()
-    if terms >= 2:
+    if l0_terms >= 2:
         acc = acc + x2 @ ph.t() + x3 @ ph.t()
-    if terms >= 3:
+    if l0_terms >= 3:
         acc = acc + x1 @ pl.t() + x2 @ pl.t()
     h1 = torch.relu(acc + g("pose_encoder.0.bias"))
     pf = torch.relu(mm_split(h1, g("pose_encoder.2.weight"), terms) + g("pose_encoder.2.bias"))
@@ -66,7 +71,7 @@ def trunk_tc(sd, pts_feat, pose, t, terms: int = 3, prefix: str = "pose_score_ne
 
 
 @contextmanager
-def emulated_score(terms: int = 3):
+def emulated_score(terms=3):
     """Inside the block every sampler of the oracle evaluates the score network with the tensor-core arithmetic."""
     orig = O.score
 

@@ -32,6 +32,34 @@ def test_bf16x3_split_keeps_the_parity_bound(B, K, T):
     assert float(((bf - ref).abs() / tol).max()) > 3 * frac     # single bf16 is several times worse
 
 
+@pytest.mark.parametrize("B,K,T", [(2, 50, 30), (3, 50, 20), (1, 16, 100)])
+def test_two_product_mode_keeps_the_parity_bound(B, K, T):
+    """The experimental 'bf16x2' samplers (bf16 hi/lo activations x ONE fp16 weight): what the dropped Ahi.Blo product carried
+    is the weights' bits beyond bf16, and an fp16 weight keeps three of them.  Shortest chains are the worst case (measured
+    0.31-0.46 of the bound at T = 20..30, 0.05 at T = 100, 0.03 at T = 500); with bf16 weights the same two products are 3.7x over."""
+    sd, data, x0, sn, feat = _case(B, K, T, 50 + B)
+    ref, _ = O.pred_func_pc(sd, data, K, T, x0, sn, pts_feat=feat)
+    with E.emulated_score(terms="x2"):
+        tc, _ = O.pred_func_pc(sd, data, K, T, x0, sn, pts_feat=feat)
+    tol = 1e-3 + 5e-5 * ref.abs()
+    assert float(((tc - ref).abs() / tol).max()) < 0.7
+
+
+def test_two_product_mode_ode():
+    B, K, T0, seed = 3, 50, 0.55, 73
+    sd = synth.make_state_dict(seed, kappa=0.3)
+    data = synth.batch_from_clouds(synth.make_clouds(B, seed))
+    x0 = torch.from_numpy(synth.make_prior_noise(B * K, seed, sigma=float(O.sigma_of_t(torch.tensor(T0)))))
+    feat = O.encode(sd, data["pts"])
+    rep = feat.unsqueeze(1).repeat(1, K, 1).view(B * K, -1)
+    cen = data["pts_center"].unsqueeze(1).repeat(1, K, 1).view(B * K, -1)
+    ref, st = O.ode_sampler(sd, rep, cen, x0, T0=T0, return_stats=True)
+    with E.emulated_score(terms="x2"):
+        out, st2 = O.ode_sampler(sd, rep, cen, x0, T0=T0, return_stats=True)
+    assert st2["nfev"] == st["nfev"]
+    assert float(((out - ref).abs() / (1e-3 + 2e-4 * ref.abs())).max()) < 0.1
+
+
 def test_split_product_is_exact_to_2_pow_minus_16():
     g = torch.Generator().manual_seed(0)
     a, w = torch.randn(64, 256, generator=g), torch.randn(96, 256, generator=g)

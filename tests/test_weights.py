@@ -1,5 +1,6 @@
 """CPU: host-side weight packing (BN fold, head stacking, W1 column split) against the oracle."""
 import numpy as np
+import pytest
 import torch
 
 from genpose_b200 import arch, synth, weights
@@ -28,6 +29,34 @@ def test_bn_fold_reproduces_shared_mlp():
                 w, b = weights._fold(sd, f"pts_encoder.SA_modules.{l}.mlps.{s}.layer{j}")
                 h = torch.relu(h @ w.t() + b)
             np.testing.assert_allclose(h.float().numpy(), ref.numpy(), rtol=2e-5, atol=2e-5)
+
+
+def test_two_product_stream_layout():
+    """pack_trunk_tc16: every slot is the K-major no-swizzle image [K/8][rows][8] of the fp16-rounded weight block the kernel's
+    descriptors expect (tc_sampler.cu, TcStream<true>); slot 0 is the three-product stream's P1 slot."""
+    sd = synth.make_state_dict(3, kappa=0.3)
+    st = weights.pack_trunk_tc16(sd)
+    assert st.dtype == torch.int16 and st.numel() * 2 == 33 * 16384
+    assert torch.equal(st[:8192], weights.pack_trunk_tc(sd)[:8192])
+    slot = lambda i: st[i * 8192:(i + 1) * 8192].view(torch.float16)
+    r16 = lambda w: w.to(torch.float16).float()
+    p2 = sd["pose_score_net.pose_encoder.2.weight"].float()
+    for unit in range(2):
+        for q in range(4):
+            w = slot(1 + unit * 4 + q).reshape(8, 128, 8).permute(1, 0, 2).reshape(128, 64).float()
+            assert torch.equal(w, r16(p2[128 * unit:128 * unit + 128, 64 * q:64 * q + 64]))
+    stacked = torch.cat([sd[f"pose_score_net.fusion_tail_{h}.0.weight"].float()[:, 1152:] for h in ("rot_x", "rot_y", "trans")], 0)
+    for r in range(4):
+        for q in range(4):
+            w = slot(9 + 6 * r + q).reshape(8, 128, 8).permute(1, 0, 2).reshape(128, 64).float()
+            assert torch.equal(w, r16(stacked[192 * r:192 * r + 128, 64 * q:64 * q + 64]))
+        for q in range(2):
+            w = slot(13 + 6 * r + q).reshape(16, 64, 8).permute(1, 0, 2).reshape(64, 128).float()
+            assert torch.equal(w, r16(stacked[192 * r + 128:192 * r + 192, 128 * q:128 * q + 128]))
+    sd_big = dict(sd)
+    sd_big["pose_score_net.pose_encoder.2.weight"] = sd["pose_score_net.pose_encoder.2.weight"] * 1e6
+    with pytest.raises(ValueError):
+        weights.pack_trunk_tc16(sd_big)
 
 
 def test_trunk_pack_reproduces_score():

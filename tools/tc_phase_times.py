@@ -1,5 +1,5 @@
 """Decode the cycle stamps of gpb_sample_pc_tc_dbg: per-phase durations (cycles) of CTA 0, averaged over steps.
-    python tools/tc_phase_times.py [T]     (bench shape: 64 objects x 50 candidates)"""
+    python tools/tc_phase_times.py [T] [cta,cta,...] [bf16x3|bf16x2]     (bench shape: 64 objects x 50 candidates)"""
 import sys
 
 import numpy as np
@@ -10,6 +10,7 @@ from genpose_b200 import lib, ops, synth  # noqa: E402
 
 T = int(sys.argv[1]) if len(sys.argv) > 1 else 100
 CTAS = [int(c) for c in sys.argv[2].split(",")] if len(sys.argv) > 2 else [0]
+W16 = len(sys.argv) > 3 and sys.argv[3] == "bf16x2"
 B, K = 64, 50
 sd = synth.make_state_dict(0, kappa=synth.stable_kappa(T))
 eng = ops.Engine(sd)
@@ -27,7 +28,8 @@ dbg = torch.zeros(2, T, 16, dtype=torch.int64, device="cuda")
 
 def record(cta):
     for _ in range(2):
-        lib.check(L.gpb_sample_pc_tc_dbg(x0.data_ptr(), R, K, T, 0.16, ob.data_ptr(), eng.trunk_w.data_ptr(), eng.trunk_tc.data_ptr(),
+        fn, stream_w = (L.gpb_sample_pc_tc16, eng.trunk_tc16()) if W16 else (L.gpb_sample_pc_tc_dbg, eng.trunk_tc)
+        lib.check(fn(x0.data_ptr(), R, K, T, 0.16, ob.data_ptr(), eng.trunk_w.data_ptr(), stream_w.data_ptr(),
                                          center.data_ptr(), 0, (cta << 56) | 1, ts.data_ptr(), out.data_ptr(), 0, ws.data_ptr(), ws.numel(),
                                          dbg.data_ptr(), torch.cuda.current_stream().cuda_stream), "dbg")
     torch.cuda.synchronize()

@@ -1,6 +1,6 @@
 """Stress the tensor-core PC sampler at small grids (1-3 tile teams), where a step's tail is shortest and inter-warp skew largest:
 many repetitions, tc vs fp32 FFMA kernel on the same explicit noise, allocator memory dirtied with NaN bit patterns in between.
-    python tools/tc_stress.py [reps]        exits non-zero on the first disagreement; run under `timeout` (a hang is a failure)"""
+    python tools/tc_stress.py [reps] [precision]   exits non-zero on the first disagreement; run under `timeout` (a hang is a failure)"""
 import sys
 import time
 
@@ -11,6 +11,7 @@ sys.path.insert(0, ".")
 from genpose_b200 import ops, synth  # noqa: E402
 
 reps = int(sys.argv[1]) if len(sys.argv) > 1 else 50
+PRECISION = sys.argv[2] if len(sys.argv) > 2 else "bf16x3"
 SHAPES = [(3, 64, 100, True), (2, 50, 30, True), (5, 50, 60, False), (7, 50, 40, False), (1, 128, 25, True)]
 t0 = time.time()
 worst = 0.0
@@ -30,7 +31,7 @@ for (B, K, T, proc) in SHAPES:
         junk = torch.full((8 << 20,), float("nan"), device="cuda")     # dirty what the caching allocator hands out next
         del junk
         eng._ws.clear()                                                   # fresh (dirty) workspace every repetition
-        out = eng.sample_pc(ob, cen, x0, K, T, step_noise=sn, precision="bf16x3", return_process=proc)
+        out = eng.sample_pc(ob, cen, x0, K, T, step_noise=sn, precision=PRECISION, return_process=proc)
         pose = out[0] if proc else out
         torch.cuda.synchronize()
         d = float((pose - ref).abs().max())
