@@ -19,6 +19,24 @@ def default_cfg(sampler="pc", sampling_steps=500, posenet_mode="score", noise_mo
     return get_config(argv + list(extra))
 
 
+def poses_to_RTs(pred_pose: torch.Tensor):
+    """[B,K,9] poses (rx, ry, t) -> float64 numpy [B,K,4,4], the `RTs_all` that pred_pose_batch / pred_energy_batch build
+    (runners/evaluation_single.py:325-332, :346-353) with one get_rot_matrix call and two `.cpu().numpy()` copies PER CANDIDATE.
+    Here: all B*K candidates at once on the device the poses live on and ONE device->host copy.  Result formatting after the hot
+    path (the runner pickles it for compute_mAP); the columns are get_rot_matrix's (utils/misc.py:136: Gram-Schmidt b1, b2 and
+    b1 x b2 as matrix COLUMNS, F.normalize eps 1e-12)."""
+    import numpy as np
+    p = pred_pose.detach()
+    b1 = torch.nn.functional.normalize(p[..., 0:3], dim=-1)
+    a2 = p[..., 3:6]
+    b2 = torch.nn.functional.normalize(a2 - (b1 * a2).sum(-1, keepdim=True) * b1, dim=-1)
+    b3 = torch.cross(b1, b2, dim=-1)
+    rt = torch.zeros(*p.shape[:-1], 4, 4, dtype=p.dtype, device=p.device)
+    rt[..., :3, 0], rt[..., :3, 1], rt[..., :3, 2], rt[..., :3, 3] = b1, b2, b3, p[..., 6:9]
+    rt[..., 3, 3] = 1.0
+    return rt.cpu().numpy().astype(np.float64)
+
+
 class PosePipeline:
     def __init__(self, score_state_dict, energy_state_dict=None, sampler="pc", sampling_steps=500, noise_mode="philox",
                  precision="auto"):

@@ -130,3 +130,23 @@ def test_agent_end_to_end_on_gpu(tmp_path):
     sp, se = sort_poses_by_energy(pose, en)
     sp_ref, se_ref = O.sort_poses_by_energy(pose.cpu(), en.cpu())
     assert torch.equal(sp.cpu(), sp_ref) and torch.equal(se.cpu(), se_ref)
+
+
+def test_poses_to_RTs_is_the_runners_loop():
+    """pipeline.poses_to_RTs against the literal per-candidate loop of pred_pose_batch (runners/evaluation_single.py:325-332)."""
+    import numpy as np
+    from genpose_b200.pipeline import poses_to_RTs
+    from oracle import genpose_oracle as O
+    g = torch.Generator().manual_seed(4)
+    pred_pose = torch.randn(3, 7, 9, generator=g)
+    RTs_all = np.ones((3, 7, 4, 4))
+    for i in range(pred_pose.shape[1]):
+        R = O.get_rot_matrix(pred_pose[:, i, :-3])
+        T = pred_pose[:, i, -3:]
+        RTs = np.identity(4, dtype=float)[np.newaxis, ...].repeat(R.shape[0], 0)
+        RTs[:, :3, :3] = R.cpu().numpy()
+        RTs[:, :3, 3] = T.cpu().numpy()
+        RTs_all[:, i, :, :] = RTs
+    got = poses_to_RTs(pred_pose)
+    assert got.dtype == np.float64 and got.shape == (3, 7, 4, 4)
+    np.testing.assert_allclose(got, RTs_all, rtol=0, atol=1e-6)
