@@ -38,6 +38,7 @@ def test_abi_version_and_sizes(built):
     assert built.gpb_encoder_weights_floats() == weights.encoder_floats()
     assert built.gpb_trunk_weights_floats() == weights.trunk_floats()
     assert built.gpb_encode_workspace_bytes(64) > 0 and built.gpb_sampler_workspace_bytes(3200, 500) > 0
+    assert built.gpb_trunk_tc_stream_bytes() == 65 * 16384 and built.gpb_trunk_tc16_stream_bytes() == 33 * 16384
     assert built.gpb_launch_count() == 0
 
 
@@ -47,6 +48,11 @@ def test_argument_validation_without_gpu(built):
     assert b"m<=n" in built.gpb_last_error_string()
     assert built.gpb_rank_pool(None, None, 1, 500, 1, None, None, None, None) == -1
     assert built.gpb_encode(None, 0, None, None, None, 0, None, None, None, None) == 0      # empty batch is a no-op
+    # the samplers: empty batch is a no-op, a too-small K is refused by the tensor-core entries (three- and two-product alike)
+    for fn in (built.gpb_sample_pc_tc, built.gpb_sample_pc_tc16):
+        extra = (None,) if fn is built.gpb_sample_pc_tc16 else ()
+        assert fn(None, 0, 50, 500, 0.16, None, None, None, None, None, 0, None, None, None, None, 0, *extra, None) == 0
+    assert built.gpb_sample_ode_tc16(None, 0, 50, 0.55, 1e-5, 1e-5, 1000, None, None, None, None, None, None, None, 0, None) == 0
 
 
 def test_sass_is_sm100a_only():
