@@ -97,6 +97,7 @@ class Engine:
         self.enc_tc = etc.to(self.device)
         self._ws: Dict[Tuple[str, int], torch.Tensor] = {}
         self._state_for_tc16 = state_dict
+        self._time_grids: Dict[int, torch.Tensor] = {}
         self._trunk_tc16: Optional[torch.Tensor] = None
 
     def trunk_tc16(self) -> torch.Tensor:
@@ -174,7 +175,9 @@ class Engine:
             raise lib.GenPoseB200Error(f"sample_pc: unknown precision {precision!r}")
         L = lib.load()
         ws = self._workspace("samp", L.gpb_sampler_workspace_bytes(R, num_steps))
-        ts = time_grid(num_steps, self.device)
+        ts = self._time_grids.get(num_steps)         # built once per T: a pageable host->device copy per call would make the host
+        if ts is None:                               # wait for the encoder in front of it before it can enqueue the sampler
+            ts = self._time_grids[num_steps] = time_grid(num_steps, self.device)
         mean_x = torch.empty(R, 9, dtype=torch.float32, device=self.device)
         process = torch.empty(R, num_steps, 9, dtype=torch.float32, device=self.device) if return_process else None
         if step_noise is not None and tuple(step_noise.shape) != (num_steps, 2, R, 9):
