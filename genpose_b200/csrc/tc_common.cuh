@@ -223,5 +223,15 @@ __device__ __forceinline__ void split_bf16x2(float a, float b, uint32_t &hi, uin
     lo = *reinterpret_cast<const uint32_t *>(&l);
 }
 
+// ReLU fused into the split (EXPERIMENTAL, compiled in with -DGPB_EPI_RZ_RELU=1; emulated in oracle/tc_emulation.py): hi = bf16
+// TRUNCATION of max(x, 0) (cvt.rz.relu: for x >= 0 the residual x - hi is then >= 0, for x < 0 hi = 0 and the residual is x < 0),
+// lo = rn_bf16(max(residual, 0)) (cvt.rn.relu).  Saves the two FMNMX of every column pair; hi + lo still carries 16 mantissa bits.
+__device__ __forceinline__ void relu_split_bf16x2_rz(float a, float b, uint32_t &hi, uint32_t &lo) {
+    asm("cvt.rz.relu.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(b), "f"(a));          // d = {hi half: first source, lo half: second}
+    const float ra = a - __uint_as_float(hi << 16);
+    const float rb = b - __uint_as_float(hi & 0xffff0000u);
+    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(rb), "f"(ra));
+}
+
 }  // namespace tc
 }  // namespace gpb

@@ -130,7 +130,11 @@ __device__ __forceinline__ void relu_split32(const uint32_t (&v)[32], const floa
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
         const float2 bb = *reinterpret_cast<const float2 *>(bias + 2 * j);
+#if defined(GPB_EPI_RZ_RELU) && GPB_EPI_RZ_RELU
+        relu_split_bf16x2_rz(__uint_as_float(v[2 * j]) + bb.x, __uint_as_float(v[2 * j + 1]) + bb.y, hi[j], lo[j]);
+#else
         split_bf16x2(fmaxf(__uint_as_float(v[2 * j]) + bb.x, 0.f), fmaxf(__uint_as_float(v[2 * j + 1]) + bb.y, 0.f), hi[j], lo[j]);
+#endif
     }
 }
 

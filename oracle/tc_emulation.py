@@ -25,9 +25,24 @@ def split_bf16(t: torch.Tensor):
     return hi, lo
 
 
+ACT_SPLIT = "rn"          # "rz_relu": the experimental ReLU-fused activation split of tc_common.cuh (relu_split_bf16x2_rz)
+
+
+def split_act(a: torch.Tensor):
+    """hi/lo of a POST-ReLU activation.  'rn': hi = rn_bf16(a), lo = rn_bf16(a - hi) (shipped).  'rz_relu': hi = bf16 truncation
+    (cvt.rz.relu; a >= 0 so the residual is >= 0), lo = rn_bf16(max(residual, 0)) (cvt.rn.relu)."""
+    if ACT_SPLIT == "rn":
+        return split_bf16(a)
+    a = a.float()
+    hi = (a.view(torch.int32) & ~0xFFFF).view(torch.float32)
+    hi = torch.where(a > 0, hi, torch.zeros_like(hi))
+    return hi, torch.clamp(a - hi, min=0).to(torch.bfloat16).float()
+
+
 def mm_split(a: torch.Tensor, w: torch.Tensor, terms=3) -> torch.Tensor:
-    """a [R,K] . w [N,K]^T with both operands split into bf16 hi + lo; products are exact in fp32, sums are fp32."""
-    ah, al = split_bf16(a)
+    """a [R,K] . w [N,K]^T with both operands split into bf16 hi + lo; products are exact in fp32, sums are fp32.
+    a is a post-ReLU activation (split_act), w a weight block."""
+    ah, al = split_act(a)
     if terms == "x2":
         w16 = w.float().to(torch.float16).float()
         return ah @ w16.t() + al @ w16.t()

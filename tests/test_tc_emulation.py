@@ -45,6 +45,19 @@ def test_two_product_mode_keeps_the_parity_bound(B, K, T):
     assert float(((tc - ref).abs() / tol).max()) < 0.7
 
 
+def test_relu_fused_truncating_split_keeps_the_parity_bound(monkeypatch):
+    """The experimental epilogue split (GPB_EPI_RZ_RELU: hi truncated, ReLU inside both conversions) costs nothing in accuracy."""
+    B, K, T = 2, 50, 30
+    sd, data, x0, sn, feat = _case(B, K, T, 50 + B)
+    ref, _ = O.pred_func_pc(sd, data, K, T, x0, sn, pts_feat=feat)
+    tol = 1e-3 + 5e-5 * ref.abs()
+    monkeypatch.setattr(E, "ACT_SPLIT", "rz_relu")
+    for terms in (3, "x2"):
+        with E.emulated_score(terms=terms):
+            tc, _ = O.pred_func_pc(sd, data, K, T, x0, sn, pts_feat=feat)
+        assert float(((tc - ref).abs() / tol).max()) < 0.5
+
+
 def test_two_product_mode_ode():
     B, K, T0, seed = 3, 50, 0.55, 73
     sd = synth.make_state_dict(seed, kappa=0.3)
