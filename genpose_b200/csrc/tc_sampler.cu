@@ -706,6 +706,20 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
                     mbar_wait(&bar_acc_full[b], n & 1u);
                     if (ds) ds[1 + 2 * layer] = clock64();
                     tc_fence_after_sync();
+#if defined(GPB_EPI_LD2) && GPB_EPI_LD2
+                    {   // EXPERIMENTAL: both 32-column loads in flight together (one tensor-memory round trip per unit instead of two)
+                        // and the accumulator handed back before the conversion instead of in the middle of it
+                        uint32_t v0[32], v1[32];
+                        tmem_ld32(tm_row + kColD + b * 128u + (uint32_t)cs * 64u, v0);
+                        tmem_ld32(tm_row + kColD + b * 128u + (uint32_t)cs * 64u + 32u, v1);
+                        tmem_ld_wait();
+                        tc_fence_before_sync();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&bar_acc_empty[b]);
+                        relu_split32(v0, bias, hi, lo);
+                        relu_split32(v1, bias + 32, hi + 16, lo + 16);
+                    }
+#else
                     {
                         uint32_t v[32];
                         tmem_ld32(tm_row + kColD + b * 128u + (uint32_t)cs * 64u, v);
@@ -718,6 +732,7 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
                         if (lane == 0) mbar_arrive(&bar_acc_empty[b]);
                         relu_split32(v, bias + 32, hi + 16, lo + 16);
                     }
+#endif
                     ++u;
                 }
                 {   // unit b: once its accumulator is complete every MMA of the layer has consumed the old A
@@ -726,6 +741,23 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
                     tc_fence_after_sync();
                     tmem_st32(tm_row + kColAhi + (uint32_t)cs * 32u, hi);
                     tmem_st32(tm_row + kColAlo + (uint32_t)cs * 32u, lo);
+#if defined(GPB_EPI_LD2) && GPB_EPI_LD2
+                    {
+                        uint32_t v0[32], v1[32];
+                        tmem_ld32(tm_row + kColD + b * 128u + (uint32_t)cs * 64u, v0);
+                        tmem_ld32(tm_row + kColD + b * 128u + (uint32_t)cs * 64u + 32u, v1);
+                        tmem_ld_wait();
+                        tmem_st_wait();             // first half of the new A operand is in tensor memory; the accumulator is in registers
+                        tc_fence_before_sync();
+                        __syncwarp();
+                        if (lane == 0) {
+                            mbar_arrive(&bar_a_ready[0]);
+                            mbar_arrive(&bar_acc_empty[b]);
+                        }
+                        relu_split32(v0, bias + 128, hi, lo);
+                        relu_split32(v1, bias + 128 + 32, hi + 16, lo + 16);
+                    }
+#else
                     {
                         uint32_t v[32];
                         tmem_ld32(tm_row + kColD + b * 128u + (uint32_t)cs * 64u, v);
@@ -743,6 +775,7 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
                         if (lane == 0) mbar_arrive(&bar_acc_empty[b]);
                         relu_split32(v, bias + 128 + 32, hi + 16, lo + 16);
                     }
+#endif
                     tmem_st32(tm_row + kColAhi + 64u + (uint32_t)cs * 32u, hi);
                     tmem_st32(tm_row + kColAlo + 64u + (uint32_t)cs * 32u, lo);
                     tmem_st_wait();
