@@ -5,7 +5,8 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgenpose_b200.so")
+# GPB_LIB: an alternative build of the same library (experiment variants from `make -C csrc variant NAME=.. EXTRA=..`), in-tree
+LIB_PATH = os.environ.get("GPB_LIB") or os.path.join(_HERE, "libgenpose_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
 
 _vp, _i, _f, _sz, _u64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_size_t, ctypes.c_uint64
