@@ -27,3 +27,8 @@ def test_shipped_protocol_has_no_violation():
 
 def test_model_sees_the_old_a_ready_race():
     assert _violations(50, 2, old=True) > 0
+
+
+def test_team_exchange_and_grid_word_have_no_violation():
+    for seed in range(300):
+        sim.TeamSim(6, 3, random.Random(seed)).run()

@@ -215,6 +215,98 @@ class Sim:
             self.pipe_step()
 
 
+class TxBar:
+    """mbarrier with a transaction count: the phase completes when the pending arrivals AND the outstanding bytes reach zero."""
+
+    def __init__(self, name):
+        self.name, self.pending, self.tx, self.phase = name, 1, 0, 0
+
+    def _check(self):
+        if self.pending == 0 and self.tx == 0:
+            self.phase += 1
+            self.pending = 1
+
+    def arrive_expect_tx(self, n):
+        if self.pending == 0:
+            raise Violation(f"{self.name}: second arrival inside one phase")
+        self.tx += n
+        self.pending -= 1
+        self._check()
+
+    def complete_tx(self, n):
+        self.tx -= n
+        self._check()
+
+    def passed(self, parity):
+        return (self.phase & 1) != parity
+
+
+class TeamSim:
+    """The inter-CTA side: `teams` tile teams of four ranks.  Per step every rank sends its partial score to its three peers
+    (st.async: asynchronous delivery, completes bytes on the RECEIVER's bar_mail[step & 1]), waits for its own mailbox, reads the
+    four slots, the team leader adds the tile norm to the step's grid word, every rank polls the word, updates.  Checked: no
+    deadlock, every rank reads exactly this step's partials from every peer (no stale or future mail), the grid word of a step is
+    complete when read."""
+
+    def __init__(self, steps, teams, rng):
+        self.T, self.n, self.rng = steps, teams, rng
+        self.bar = {(tm, r, par): TxBar(f"mail[{tm},{r},{par}]") for tm in range(teams) for r in range(4) for par in range(2)}
+        self.mail = {(tm, r, par, src): None for tm in range(teams) for r in range(4) for par in range(2) for src in range(4)}
+        self.net = []                 # in flight: (team, dst, par, src, step)
+        self.word = {}
+
+    def rank(self, tm, r):
+        for t in range(self.T):
+            par, ph = t & 1, (t >> 1) & 1
+            for _ in range(self.rng.randrange(0, 5)):          # the score evaluation: arbitrary time
+                yield None
+            self.bar[(tm, r, par)].arrive_expect_tx(3)
+            yield None
+            self.mail[(tm, r, par, r)] = t                     # own slot
+            for d in range(1, 4):
+                self.net.append((tm, (r + d) & 3, par, r, t))
+                yield None
+            yield (lambda par=par, ph=ph: self.bar[(tm, r, par)].passed(ph))
+            for src in range(4):
+                if self.mail[(tm, r, par, src)] != t:
+                    raise Violation(f"team {tm} rank {r} step {t}: mailbox slot of rank {src} holds step {self.mail[(tm, r, par, src)]}")
+            yield None
+            if r == 0:
+                self.word[t] = self.word.get(t, 0) + 1
+                yield None
+            yield (lambda t=t: self.word.get(t, 0) >= self.n)
+            if self.word[t] != self.n:
+                raise Violation(f"grid word of step {t} read as {self.word[t]} of {self.n}")
+            for _ in range(self.rng.randrange(0, 3)):          # update
+                yield None
+
+    def deliver(self):
+        i = self.rng.randrange(len(self.net))                  # st.async completions are not ordered between senders
+        tm, dst, par, src, t = self.net.pop(i)
+        self.mail[(tm, dst, par, src)] = t
+        self.bar[(tm, dst, par)].complete_tx(1)
+
+    def run(self):
+        agents = {(tm, r): self.rank(tm, r) for tm in range(self.n) for r in range(4)}
+        waiting = {k: None for k in agents}
+        weights = {k: self.rng.choice([1, 1, 1, 5, 25]) for k in agents}
+        net_w = self.rng.choice([1, 3, 20])
+        live = set(agents)
+        while live:
+            runnable = [k for k in live if waiting[k] is None or waiting[k]()]
+            cands = runnable + (["net"] if self.net else [])
+            if not cands:
+                raise Violation(f"deadlock: ranks {sorted(live)} blocked")
+            k = self.rng.choices(cands, weights=[(1.0 / net_w if c == "net" else 1.0 / weights[c]) for c in cands])[0]
+            if k == "net":
+                self.deliver()
+                continue
+            try:
+                waiting[k] = next(agents[k])
+            except StopIteration:
+                live.discard(k)
+
+
 def main():
     args = [a for a in sys.argv[1:] if not a.startswith("--")]
     runs = int(args[0]) if args else 2000
@@ -230,7 +322,16 @@ def main():
                 print(f"schedule {seed}: {e}")
     print(f"{runs} random schedules x {steps} steps, protocol = {'single a_ready barrier (old)' if old else 'one a_ready barrier per half'}: "
           f"{bad} violations")
-    return 1 if (bad and not old) else 0
+    bad_team = 0
+    for seed in range(runs):
+        try:
+            TeamSim(steps + 3, 3, random.Random(seed)).run()
+        except Violation as e:
+            bad_team += 1
+            if bad_team <= 3:
+                print(f"team schedule {seed}: {e}")
+    print(f"{runs} random schedules x {steps + 3} steps, team exchange + grid word (3 teams of 4 ranks): {bad_team} violations")
+    return 1 if ((bad and not old) or bad_team) else 0
 
 
 if __name__ == "__main__":
