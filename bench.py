@@ -200,8 +200,8 @@ def run_ode_line(args, rank, world, local_rank):
     torch.manual_seed(rank)
     x0_dev = ve_prior((R, 9), T=T0).to(dev).contiguous()
     precision = "bf16x3" if args.precision == "bf16x3" or (args.precision == "auto" and eng.tc_supported(R, K_CAND)) else "fp32"
-    if args.precision == "bf16x2":
-        precision = "bf16x2"
+    if args.precision == "f16x2":
+        precision = "f16x2"
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
     out_host = torch.empty(B_PER_GPU, K_CAND, 9, dtype=torch.float64).pin_memory()
     stats_box = {}
@@ -276,9 +276,9 @@ def main():
     ap.add_argument("--sampler", default="pc", choices=["pc", "ode"],
                     help="pc = BASELINE.json's metric (T=500 predictor-corrector steps, the default and the headline); ode = the "
                          "reference's shipped recipe (scripts/eval_single.sh: RK45 probability-flow ODE, T0=0.55) as an extra line")
-    ap.add_argument("--precision", default="auto", choices=["auto", "bf16x3", "fp32", "bf16x2"],
+    ap.add_argument("--precision", default="auto", choices=["auto", "bf16x3", "fp32", "f16x2"],
                     help="dense layers of the sampler: tcgen05 bf16x3 (auto when the shape allows) or the fp32 FFMA parity kernel; "
-                         "bf16x2 = EXPERIMENTAL two-product tensor-core kernel (fp16 weight images), never chosen by auto")
+                         "f16x2 = EXPERIMENTAL two-product tensor-core kernel (fp16 weight images), never chosen by auto")
     args = ap.parse_args()
 
     from genpose_b200 import distributed as D
@@ -315,9 +315,9 @@ def main():
     clouds_dev = clouds_host.to(dev)
     center_dev = clouds_dev.mean(dim=1).contiguous()
     R = B_PER_GPU * K_CAND
-    use_tc = args.precision in ("bf16x3", "bf16x2") or (args.precision == "auto" and eng.tc_supported(R, K_CAND))
-    precision = args.precision if args.precision in ("bf16x3", "bf16x2") else ("bf16x3" if use_tc else "fp32")
-    tc_products = 2 if precision == "bf16x2" else 3
+    use_tc = args.precision in ("bf16x3", "f16x2") or (args.precision == "auto" and eng.tc_supported(R, K_CAND))
+    precision = args.precision if args.precision in ("bf16x3", "f16x2") else ("bf16x3" if use_tc else "fp32")
+    tc_products = 2 if precision == "f16x2" else 3
     x0_dev = torch.from_numpy(synth.make_prior_noise(R, seed)).to(dev)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
     gathered = torch.empty(world * B_PER_GPU, K_CAND, 9, device=dev) if world > 1 else None
@@ -471,13 +471,13 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": total_ms[0] / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": ("bf16x3 (bf16 tensor-core operands, error-compensated split, fp32 accumulate)" if precision == "bf16x3" else
-                      "bf16x2 (bf16 hi/lo activations x fp16 weights, fp32 accumulate; experimental)") if use_tc else "f32",
+                      "f16x2 (bf16 hi/lo activations x fp16 weights, fp32 accumulate; experimental)") if use_tc else "f32",
             "data": "synthetic", "config": workload_config(args, world),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(clouds_host.numel() * 4 + R * 9 * 4),
                     "d2h_bytes_per_step": int(out_host.numel() * 4), "ms_per_step": total_ms[1] / args.steps,
                     "api": "PoseNet.pred_func(data, repeat_num=50)" + (" + PoseNet.get_energy + rank_pool" if args.config == 3 else "")},
             "gpu_launches": int(launches),
-            "roofline": {"kernel": (("tc_pc_sampler_w16_kernel" if precision == "bf16x2" else "tc_pc_sampler_kernel") if use_tc
+            "roofline": {"kernel": (("tc_pc_sampler_kernel<w16>" if precision == "f16x2" else "tc_pc_sampler_kernel") if use_tc
                                     else "pc_sampler_kernel") + " (+ time_bias_table_kernel)",
                          "bound": "tensor", "achieved": ach, "peak": peak,
                          "unit": "TFLOP/s", "frac": ach / peak,

@@ -440,7 +440,7 @@ pc_sampler_kernel(PcParams p) {
 struct OdeParams {
     const float *x0;   // [R,9]
     int R, K;
-    float T0, rtol, atol;
+    double T0, rtol, atol;     // Python floats in the reference (samplers.py:178, posenet.py:94): float64 through the ABI
     int denoise_steps;         // 1000 when num_steps is None (samplers.py:217); 0 = no denoise
     const float *obj_bias, *W, *pts_center;
     double *y;                 // [R,9]   workspace
@@ -802,13 +802,13 @@ extern "C" int gpb_sample_pc(const float *x0, int R, int K, int num_steps, float
     return GPB_OK;
 }
 
-extern "C" int gpb_sample_ode(const float *x0, int R, int K, float T0, float rtol, float atol, int denoise_steps,
+extern "C" int gpb_sample_ode(const float *x0, int R, int K, double T0, double rtol, double atol, int denoise_steps,
                               const float *obj_bias, const float *W, const float *pts_center, double *pose, int *stats,
                               void *workspace, size_t workspace_bytes, void *stream) {
     GPB_REQUIRE(R >= 0 && K >= 1, "sample_ode: need R >= 0, K >= 1");
     if (R == 0) return GPB_OK;
     GPB_REQUIRE(x0 && obj_bias && W && pts_center && pose && workspace, "sample_ode: NULL buffer");
-    GPB_REQUIRE(T0 > 1e-5f && rtol > 0 && atol > 0, "sample_ode: need T0 > eps and positive tolerances");
+    GPB_REQUIRE(T0 > 1e-5 && rtol > 0 && atol > 0, "sample_ode: need T0 > eps and positive tolerances");
     GPB_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "sample_ode: workspace must be 256-byte aligned");
     SamplerWs w = carve_sampler(workspace, R, 1);
     if (workspace_bytes < w.bytes) {

@@ -11,6 +11,7 @@
 // 16-byte words => row-per-thread epilogues write the A operand with conflict-free STS.128.
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 
 namespace gpb {
@@ -223,14 +224,14 @@ __device__ __forceinline__ void split_bf16x2(float a, float b, uint32_t &hi, uin
     lo = *reinterpret_cast<const uint32_t *>(&l);
 }
 
-// ReLU fused into the split (EXPERIMENTAL, compiled in with -DGPB_EPI_RZ_RELU=1; emulated in oracle/tc_emulation.py): hi = bf16
-// TRUNCATION of max(x, 0) (cvt.rz.relu: for x >= 0 the residual x - hi is then >= 0, for x < 0 hi = 0 and the residual is x < 0),
-// lo = rn_bf16(max(residual, 0)) (cvt.rn.relu).  Saves the two FMNMX of every column pair; hi + lo still carries 16 mantissa bits.
-__device__ __forceinline__ void relu_split_bf16x2_rz(float a, float b, uint32_t &hi, uint32_t &lo) {
-    asm("cvt.rz.relu.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(b), "f"(a));          // d = {hi half: first source, lo half: second}
-    const float ra = a - __uint_as_float(hi << 16);
-    const float rb = b - __uint_as_float(hi & 0xffff0000u);
-    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(rb), "f"(ra));
+// fp16 halves of a ReLU'd activation for the two-product layers (A = hi + lo, both fp16, against ONE fp16 weight image):
+// hi = fp16 TRUNCATION of max(x, 0) (cvt.rz.relu: for x >= 0 the residual x - hi is then >= 0; for x < 0 hi = 0 and the residual
+// x < 0 is removed by the second relu), lo = rn_fp16(max(residual, 0)) (cvt.rn.relu); hi + lo carries 21 mantissa bits.
+// .satfinite clamps an activation beyond the fp16 range (65504) instead of producing inf.
+__device__ __forceinline__ void relu_split_f16x2(float a, float b, uint32_t &hi, uint32_t &lo) {
+    asm("cvt.rz.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(b), "f"(a));      // d = {upper half: first source, lower half: second}
+    const float2 h = __half22float2(*reinterpret_cast<const __half2 *>(&hi));
+    asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(b - h.y), "f"(a - h.x));
 }
 
 }  // namespace tc

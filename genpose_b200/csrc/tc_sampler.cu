@@ -38,6 +38,7 @@
 // History (3200 rows x 500 steps, one B200): A in shared memory + 2-deep weight ring 18.2 ms; A in TMEM, deep ring,
 // warp-uniform issue, one issue group per unit 12.6 ms (one CTA per tile, all three heads); this version: see DESIGN.md §5.
 #include <cstdlib>
+#include <initializer_list>
 #include <type_traits>
 
 #include "common.cuh"
@@ -51,22 +52,38 @@ constexpr int kTcRows = 128;
 constexpr int kTcRowWarps = 8;
 constexpr int kTcThreads = (kTcRowWarps + 2) * 32;
 constexpr uint32_t kSlotBytes = 16384;
-constexpr int kTeam = 4;                           // CTAs per tile
-// Weight stream geometry.  kW16 = false (shipped, "bf16x3"): every weight block as bf16 hi image | lo image, three products per
-// K-step.  kW16 = true ("bf16x2", EXPERIMENTAL: emulated on the CPU in oracle/tc_emulation.py, not yet run on hardware): the
-// weights of layer 1 and of the heads as ONE fp16 image (11-bit mantissa), two products per K-step (Ahi.W + Alo.W) — the
-// activations keep their bf16 hi/lo split, which is what the parity bound needs — so a step streams 15 slots
-// instead of 29 and issues 2/3 of the MMAs.  Layer 0 (K = 16, ten small MMAs) keeps the bf16 hi | lo form in both.
-template <bool kW16> struct TcStream {
+// Weight stream geometry.  A 128-row tile of candidates is owned by a TEAM of kTeam CTAs (4, 2 or 1; the team is a thread-block
+// cluster) for all steps: every rank runs layers 0 and 1 and then ITS kCols = 768 / kTeam of the 768 stacked head units.  The team
+// size is chosen from the row count (launch_tc_sampler): 4 while one 4-CTA cluster per tile fits the device (<= 33 tiles on a
+// B200: short dependent chain per step), 2 up to 66 tiles, 1 beyond (one tile per SM, no redundant layer 1, no exchange: the
+// throughput configuration, 148 tiles = 18,944 rows).
+// kW16 = false ("bf16x3"): every weight block as bf16 hi image | lo image, three products per K-step.  kW16 = true ("f16x2"): the
+// weights of layer 1 and of the heads as ONE fp16 image (11-bit mantissa) against fp16 hi/lo activations, two products per K-step
+// (Ahi.W + Alo.W), so a step streams 33 slots instead of 65 and issues 2/3 of the MMAs.  (kind::f16 takes ONE format for both
+// operands on this part: bf16 activations against fp16 weights raise an illegal-instruction fault, measured in round 2.)
+// Layer 0 (K = 16, ten small MMAs) keeps the bf16 hi | lo form in both.
+template <bool kW16, int kTeam> struct TcStream {
+    static_assert(kTeam == 1 || kTeam == 2 || kTeam == 4, "team size");
+    static constexpr int kCols = 768 / kTeam;                   // head columns of one rank
+    static constexpr int kFullUnits = kCols / 128;              // N = 128 accumulator units of the head slice (1, 3, 6)
+    static constexpr bool kSmallUnit = (kCols % 128) != 0;      // team 4: one more unit of N = 64
+    static constexpr int kHeadUnits = kFullUnits + (kSmallUnit ? 1 : 0);
     static constexpr int kCommonSlots = 1 + (kW16 ? 8 : 16);   // P1 (both units) + P2 (2 units x 8 K-chunks of 32; kW16: x 4 slots of K = 64)
-    static constexpr int kHeadSlots = kW16 ? 4 + 2 : 8 + 4;    // head slice: 128-row unit + 64-row unit (kW16: K = 64 / K = 128 per slot)
-    static constexpr int kSlotsPerCtaStep = kCommonSlots + kHeadSlots;        // 29 slots = 464 KiB per CTA and step (kW16: 15 = 240 KiB)
-    static constexpr int kSlotsPerStep = kCommonSlots + kTeam * kHeadSlots;   // 65 slots in the global stream (kW16: 33)
+    static constexpr int kHeadSlots = kFullUnits * (kW16 ? 4 : 8) + (kSmallUnit ? (kW16 ? 2 : 4) : 0);
+    static constexpr int kSlotsPerCtaStep = kCommonSlots + kHeadSlots;        // team 4: 29 slots = 464 KiB per CTA and step (kW16: 15)
+    static constexpr int kSlotsPerStep = kCommonSlots + kTeam * kHeadSlots;   // 65 slots in the global stream (kW16: 33), any team
+    // the stream buffer holds two layouts back to back: A (team 4: per rank a 128-unit and a 64-unit) then B (teams 2 and 1: six
+    // 128-units in column order)  (genpose_b200/weights.py::pack_trunk_tc / pack_trunk_tc16)
+    static constexpr int kLayoutSlot0 = kTeam == 4 ? 0 : kSlotsPerStep;
 };
 constexpr uint32_t kLboB64 = 1024;                 // 64-row operand images
 constexpr uint32_t kLboB = 2048, kSbo = 128;       // 128-row operand images
 constexpr int kMaxObjPerTile = 4;
 constexpr uint32_t kColD = 0, kColAhi = 256, kColAlo = 384;
+// per-step grid reduction word of the PC kernel: [63:56] arrived tiles, [55:48] poisoned tiles, [47:0] sum of the tile sums as
+// 22.18 fixed point of (tile sum x min(sigma(t), 1)) x up to 255 tiles (a tile sum is 128 row norms |f| / sigma: the limit 2^22 is
+// 32,768 per row on average at sigma >= 1 and 3.3 M per row at sigma = 0.01)
+constexpr float kNormSumLimit = 4194304.f, kNormSumScale = 262144.f;
 using TL = TrunkLayout;
 
 // dynamic shared memory map (bytes)
@@ -75,18 +92,21 @@ constexpr uint32_t kOffOw = kOffObt + kMaxObjPerTile * 768 * 4;       // [9][256
 constexpr uint32_t kOffBias = kOffOw + (9 * 256 + 16) * 4;            // p1_b [256] | p2_b [256]
 constexpr uint32_t kOffFpart = kOffBias + 512 * 4;                    // [128][12] fp32 partial scores of column sub-half 1
 constexpr uint32_t kOffMail = kOffFpart + 128 * 12 * 4;               // [2 parities][4 ranks][128][8] fp32: the team's partial sums (DSMEM)
-constexpr uint32_t kOffOdeY = kOffMail + 2 * 4 * 128 * 8 * 4;         // ODE only: y [9][128] | y_new [9][128] float64
-// the weight ring takes what is left: 10 slots for the PC kernel, 9 for the ODE kernel (which keeps its float64 state in smem)
-template <bool kOde> struct TcSmem {
-    static constexpr int kSlots = kOde ? 9 : 10;
-    static constexpr uint32_t kOffRing = ((kOde ? kOffOdeY + 2 * 9 * 128 * 8 : kOffOdeY) + 1023u) & ~1023u;
+// then: the team's mailboxes (teams of 2 and 4), the ODE kernel's float64 state y [9][128] | y_new [9][128], and the weight ring,
+// which takes what is left (team 4: 10 slots PC / 9 ODE; team 1: 12 / 11)
+template <bool kOde, int kTeam> struct TcSmem {
+    static constexpr uint32_t kMailBytes = kTeam > 1 ? 2u * kTeam * 128u * 8u * 4u : 0u;
+    static constexpr uint32_t kOffOdeY = kOffMail + kMailBytes;
+    static constexpr uint32_t kOffRing = ((kOffOdeY + (kOde ? 2u * 9u * 128u * 8u : 0u)) + 1023u) & ~1023u;
+    static constexpr int kSlots = (int)((227u * 1024u - 1280u - kOffRing) / kSlotBytes);
     static constexpr uint32_t kBytes = kOffRing + kSlots * kSlotBytes;
 };
-static_assert(TcSmem<false>::kBytes <= 227 * 1024 - 1280 && TcSmem<true>::kBytes <= 227 * 1024 - 1280, "tc sampler shared memory budget");
+static_assert(TcSmem<false, 4>::kSlots == 10 && TcSmem<true, 4>::kSlots == 9 && TcSmem<false, 1>::kSlots == 12 && TcSmem<true, 1>::kSlots == 11,
+              "tc sampler shared memory budget");
 
 // probability-flow ODE mode (cond_ode_sampler, samplers.py:163-227): everything PcParams does not already carry
 struct TcOdeParams {
-    float T0, rtol, atol;
+    double T0, rtol, atol;
     int denoise_steps;
     double *Kst;        // [4 ranks][7 stages][R,9] float64 stage derivatives, one private copy per tile-team rank
     double *partial;    // [4 slots][n_tiles][2] per-tile partial sums of the step controller's norms
@@ -125,16 +145,15 @@ __device__ __forceinline__ void red_relaxed_add_u64(unsigned long long *p, unsig
 }
 
 
-// bias + ReLU + bf16 hi/lo split of 32 accumulator columns -> 16 + 16 packed words (column pairs)
+// bias + ReLU + hi/lo split of 32 accumulator columns -> 16 + 16 packed words (column pairs); kF16: fp16 halves (the A operand
+// of the two-product layers), else bf16 halves
+template <bool kF16>
 __device__ __forceinline__ void relu_split32(const uint32_t (&v)[32], const float *bias, uint32_t *hi, uint32_t *lo) {
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
         const float2 bb = *reinterpret_cast<const float2 *>(bias + 2 * j);
-#if defined(GPB_EPI_RZ_RELU) && GPB_EPI_RZ_RELU
-        relu_split_bf16x2_rz(__uint_as_float(v[2 * j]) + bb.x, __uint_as_float(v[2 * j + 1]) + bb.y, hi[j], lo[j]);
-#else
-        split_bf16x2(fmaxf(__uint_as_float(v[2 * j]) + bb.x, 0.f), fmaxf(__uint_as_float(v[2 * j + 1]) + bb.y, 0.f), hi[j], lo[j]);
-#endif
+        if constexpr (kF16) relu_split_f16x2(__uint_as_float(v[2 * j]) + bb.x, __uint_as_float(v[2 * j + 1]) + bb.y, hi[j], lo[j]);
+        else split_bf16x2(fmaxf(__uint_as_float(v[2 * j]) + bb.x, 0.f), fmaxf(__uint_as_float(v[2 * j + 1]) + bb.y, 0.f), hi[j], lo[j]);
     }
 }
 
@@ -143,13 +162,15 @@ __device__ __forceinline__ void relu_split32(const uint32_t (&v)[32], const floa
 // epilogues, team exchange) and differ in what the row warps do with the score and in how the trip count is known:
 // PC runs exactly T evaluations; the ODE solver's count depends on its step controller, so the row warps publish how many
 // evaluations are known to exist (s_allowed, always at least one ahead of every decision point) and when the last one is (s_final).
-template <bool kOde, bool kW16 = false>
+template <bool kOde, bool kW16, int kTeam>
 __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
-    using TS = TcStream<kW16>;
+    using TS = TcStream<kW16, kTeam>;
+    using SM = TcSmem<kOde, kTeam>;
+    constexpr int kCols = TS::kCols;
     const PcParams &p = tp.pc;
     extern __shared__ __align__(1024) uint8_t smem[];
-    constexpr int kSlots = TcSmem<kOde>::kSlots;
-    uint8_t *sRing = smem + TcSmem<kOde>::kOffRing;
+    constexpr int kSlots = SM::kSlots;
+    uint8_t *sRing = smem + SM::kOffRing;
     float *sObt = reinterpret_cast<float *>(smem + kOffObt);
     float *sOw = reinterpret_cast<float *>(smem + kOffOw);
     float *sBias = reinterpret_cast<float *>(smem + kOffBias);
@@ -165,14 +186,14 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
     __shared__ double s_redd[12];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int tile = blockIdx.x / kTeam, rank = (int)cluster_ctarank();   // cluster = tile team (launch: cluster dims 4x1x1); rank 0 leads
+    const int tile = blockIdx.x / kTeam, rank = kTeam > 1 ? (int)cluster_ctarank() : 0;   // cluster = tile team (launch: cluster dims kTeam x 1 x 1); rank 0 leads
     const int n_tiles = gridDim.x / kTeam;
     const int row0 = tile * kTcRows;
     const int obj_lo = row0 / p.K;
     const int n_obj = (min(row0 + kTcRows, p.R) - 1) / p.K - obj_lo + 1;
     const float *W = p.W;
-    const int n_lo = rank * 192;                  // this rank's slice [n_lo, n_lo + 192) of the 768 stacked head units
-    const int hA = n_lo / 256, hB = (n_lo + 191) / 256;   // the (at most two) heads the slice touches
+    const int n_lo = rank * kCols;                // this rank's slice [n_lo, n_lo + kCols) of the 768 stacked head units
+    const int hA = n_lo / 256;                    // first head the slice touches (teams 2 and 4: at most two heads, hA and hA + 1)
 
     if (tid == 0) {
         for (int s = 0; s < kSlots; ++s) {
@@ -195,7 +216,7 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
             s_allowed = 2 + 6 + 1;     // f0, f1 (select_initial_step), the first RK45 attempt, and whatever follows it
             s_final = 0;
             s_gn = 1;
-            s_times[0] = tp.ode.T0;
+            s_times[0] = (float)tp.ode.T0;
         }
     }
     if (warp == kTcRowWarps) tmem_alloc(&s_tmem_base, 512);
@@ -210,11 +231,11 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
-    cluster_sync_all();          // the team's mailbox barriers are initialised before anyone arrives remotely
+    if constexpr (kTeam > 1) cluster_sync_all();          // the team's mailbox barriers are initialised before anyone arrives remotely
     const uint32_t tmem_base = s_tmem_base;
     const uint32_t idesc128 = make_idesc_bf16_f32(128, 128), idesc64 = make_idesc_bf16_f32(128, 64);
-    // kW16: A = bf16 (tensor memory), B = fp16 (shared memory) in one kind::f16 instruction (separate format fields)
-    const uint32_t idesc128w = make_idesc_f16kind_f32(128, 128, 1, 0), idesc64w = make_idesc_f16kind_f32(128, 64, 1, 0);
+    // kW16: A = fp16 hi / lo (tensor memory), B = fp16 (shared memory)
+    const uint32_t idesc128w = make_idesc_f16kind_f32(128, 128, 0, 0), idesc64w = make_idesc_f16kind_f32(128, 64, 0, 0);
     const bool dbg_cta = p.dbg != nullptr && (int)blockIdx.x == p.dbg_cta;
 
     if (warp == kTcRowWarps + 1) {
@@ -223,7 +244,7 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
             auto produce = [&](uint32_t it) {
                 const uint32_t s = it % kSlots;
                 const uint32_t idx = it % TS::kSlotsPerCtaStep;
-                const uint32_t src = idx < (uint32_t)TS::kCommonSlots ? idx : idx + (uint32_t)(rank * TS::kHeadSlots);
+                const uint32_t src = (uint32_t)TS::kLayoutSlot0 + (idx < (uint32_t)TS::kCommonSlots ? idx : idx + (uint32_t)(rank * TS::kHeadSlots));
                 mbar_wait(&bar_empty[s], ((it / kSlots) & 1u) ^ 1u);
                 mbar_arrive_expect_tx(&bar_full[s], kSlotBytes);
                 bulk_g2s(sRing + s * kSlotBytes, tp.wstream + (size_t)src * kSlotBytes, kSlotBytes, &bar_full[s]);
@@ -298,7 +319,7 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
                 ++it;
             }
             // ---- units with K = 256: layer 1 (P2: two 128-column units) and this rank's head slice (128 + 64 columns) ----
-            for (int unit = 0; unit < 4; ++unit) {
+            for (int unit = 0; unit < 2 + TS::kHeadUnits; ++unit) {
                 if (ds) tq = clock64();
                 // Units 0 and 2 are the first consumers of a freshly written A operand (h1 / pf).  The row warps publish it in
                 // two halves (K columns [0,128) as soon as the first accumulator unit is converted, [128,256) after the second),
@@ -306,7 +327,7 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
                 const bool split = unit == 0 || unit == 2;
                 const uint32_t b = u & 1u, n = u >> 1;
                 const uint32_t d = tmem_base + kColD + b * 128u;
-                const bool small = unit == 3;                      // the 64-column unit: 2 K-chunks per slot
+                const bool small = TS::kSmallUnit && unit == 2 + TS::kHeadUnits - 1;   // the 64-column unit (team 4): 2 K-chunks per slot
                 if (!small) {
                     // 8 slots = 16 K-steps, issued as one group (unit 1) or two groups of 4 slots (units 0, 2).  Every slot wait costs
                     // the MMA warp ~250 cycles even when the data is there (measured: groups of 2 slots, 7.45 -> 8.0 ms per launch), so
@@ -493,11 +514,11 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
         // ================= ODE mode: helpers and solver state (dead code in the PC instantiation) =================
         const TcOdeParams &od = tp.ode;
         const int rt = tid;                                                   // 0..255 over the eight row warps
-        float *tb_mine = od.tb_cta + (size_t)blockIdx.x * 6 * 192;           // this CTA's [6][192] time biases (its head columns)
-        double *sY = reinterpret_cast<double *>(smem + kOffOdeY);             // [9][128]
+        float *tb_mine = od.tb_cta + (size_t)blockIdx.x * 6 * kCols;         // this CTA's [6][kCols] time biases (its head columns)
+        double *sY = reinterpret_cast<double *>(smem + SM::kOffOdeY);             // [9][128]
         double *sYn = sY + 9 * 128;                                           // [9][128]
         // t_bias(t_j) for the gn times in s_times (scorenet.py:63-64, :195; same operation order as compute_time_bias in scorenet.cu),
-        // restricted to THIS rank's 192 head columns [n_lo, n_lo + 192) — the only ones its head epilogue reads.  All eight row
+        // restricted to THIS rank's kCols head columns [n_lo, n_lo + kCols) — the only ones its head epilogue reads.  All eight row
         // warps; scratch = sFpart (free between the team exchange and the next head epilogue).  The weights come from L2: every
         // thread keeps a batch of 32 loads in flight while it works on the previous batch.
         auto time_biases = [&](auto GN) {
@@ -545,47 +566,57 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
                     if (j0 + jj < gn) te[(j0 + jj) * 128 + n] = fmaxf(acc[jj], 0.f);
             }
             named_bar_sync(5, 256);
-            if (rt < 192) {   // tb[j][n_lo + rt] = A_t[:, n] . te[j]
-                float acc[gn];
+            {   // tb[j][n_lo + c] = A_t[:, n_lo + c] . te[j]: thread rt owns columns c = rt + 256 i (i < kCpt) of the rank's kCols
+                constexpr int kCpt = (kCols + 255) / 256;
+                float acc[kCpt][gn];
 #pragma unroll
-                for (int j = 0; j < gn; ++j) acc[j] = 0.f;
-                const float *w = W + TL::a_t + n_lo + rt;
-                float wa[32], wb[32];
+                for (int i = 0; i < kCpt; ++i)
 #pragma unroll
-                for (int k = 0; k < 32; ++k) wa[k] = __ldg(w + k * 768);
+                    for (int j = 0; j < gn; ++j) acc[i][j] = 0.f;
+                const float *w = W + TL::a_t + n_lo + (rt < kCols ? rt : 0);
+                constexpr int kBatch = kCpt == 1 ? 32 : 16;                   // k values per batch of loads in flight
+                float wa[kCpt][kBatch], wb[kCpt][kBatch];
+                auto load = [&](float (&dst)[kCpt][kBatch], int k0) {
 #pragma unroll
-                for (int half = 0; half < 2; ++half) {
+                    for (int i = 0; i < kCpt; ++i) {
+                        const int off = (256 * i + rt < kCols) ? 256 * i : 0;   // out-of-slice columns re-read a valid one; discarded below
 #pragma unroll
-                    for (int k = 0; k < 32; ++k) wb[k] = __ldg(w + (64 * half + 32 + k) * 768);
-#pragma unroll
-                    for (int k4 = 0; k4 < 32; k4 += 4)
-#pragma unroll
-                        for (int j = 0; j < gn; ++j) {
-                            const float4 e = *reinterpret_cast<const float4 *>(te + j * 128 + 64 * half + k4);
-                            acc[j] = fmaf(e.w, wa[k4 + 3], fmaf(e.z, wa[k4 + 2], fmaf(e.y, wa[k4 + 1], fmaf(e.x, wa[k4], acc[j]))));
-                        }
-                    if (half == 0) {
-#pragma unroll
-                        for (int k = 0; k < 32; ++k) wa[k] = __ldg(w + (64 + k) * 768);
+                        for (int k = 0; k < kBatch; ++k) dst[i][k] = __ldg(w + off + (size_t)(k0 + k) * 768);
                     }
+                };
+                auto mac = [&](const float (&src)[kCpt][kBatch], int k0) {
 #pragma unroll
-                    for (int k4 = 0; k4 < 32; k4 += 4)
+                    for (int k4 = 0; k4 < kBatch; k4 += 4)
 #pragma unroll
                         for (int j = 0; j < gn; ++j) {
-                            const float4 e = *reinterpret_cast<const float4 *>(te + j * 128 + 64 * half + 32 + k4);
-                            acc[j] = fmaf(e.w, wb[k4 + 3], fmaf(e.z, wb[k4 + 2], fmaf(e.y, wb[k4 + 1], fmaf(e.x, wb[k4], acc[j]))));
+                            const float4 e = *reinterpret_cast<const float4 *>(te + j * 128 + k0 + k4);
+#pragma unroll
+                            for (int i = 0; i < kCpt; ++i)
+                                acc[i][j] = fmaf(e.w, src[i][k4 + 3], fmaf(e.z, src[i][k4 + 2], fmaf(e.y, src[i][k4 + 1], fmaf(e.x, src[i][k4], acc[i][j]))));
                         }
+                };
+                load(wa, 0);
+#pragma unroll 1
+                for (int k0 = 0; k0 < 128; k0 += 2 * kBatch) {
+                    load(wb, k0 + kBatch);
+                    mac(wa, k0);
+                    if (k0 + 2 * kBatch < 128) load(wa, k0 + 2 * kBatch);
+                    mac(wb, k0 + kBatch);
                 }
 #pragma unroll
-                for (int j = 0; j < gn; ++j) __stcg(tb_mine + j * 192 + rt, acc[j]);
+                for (int i = 0; i < kCpt; ++i)
+                    if (256 * i + rt < kCols) {
+#pragma unroll
+                        for (int j = 0; j < gn; ++j) __stcg(tb_mine + j * kCols + 256 * i + rt, acc[i][j]);
+                    }
             }
             named_bar_sync(5, 256);
         };
         // (object bias + time bias of evaluation `gi` of the group) -> this rank's column slice of sObt, by `nthr` threads from `t0`
         auto fill_obt = [&](int gi, int t0, int nthr) {
-            for (int i = tid - t0; i < n_obj * 192; i += nthr) {
-                const int o = i / 192, cc = n_lo + i % 192;
-                sObt[o * 768 + cc] = __ldg(p.obj_bias + (size_t)(obj_lo + o) * 768 + cc) + __ldcg(tb_mine + gi * 192 + i % 192);
+            for (int i = tid - t0; i < n_obj * kCols; i += nthr) {
+                const int o = i / kCols, cc = n_lo + i % kCols;
+                sObt[o * 768 + cc] = __ldg(p.obj_bias + (size_t)(obj_lo + o) * 768 + cc) + __ldcg(tb_mine + gi * kCols + i % kCols);
             }
         };
         // solver state, replicated bit-identically in every row thread of every rank (scipy/integrate/_ivp/rk.py, common.py)
@@ -706,33 +737,18 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
                     mbar_wait(&bar_acc_full[b], n & 1u);
                     if (ds) ds[1 + 2 * layer] = clock64();
                     tc_fence_after_sync();
-#if defined(GPB_EPI_LD2) && GPB_EPI_LD2
-                    {   // EXPERIMENTAL: both 32-column loads in flight together (one tensor-memory round trip per unit instead of two)
-                        // and the accumulator handed back before the conversion instead of in the middle of it
-                        uint32_t v0[32], v1[32];
-                        tmem_ld32(tm_row + kColD + b * 128u + (uint32_t)cs * 64u, v0);
-                        tmem_ld32(tm_row + kColD + b * 128u + (uint32_t)cs * 64u + 32u, v1);
-                        tmem_ld_wait();
-                        tc_fence_before_sync();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&bar_acc_empty[b]);
-                        relu_split32(v0, bias, hi, lo);
-                        relu_split32(v1, bias + 32, hi + 16, lo + 16);
-                    }
-#else
                     {
                         uint32_t v[32];
                         tmem_ld32(tm_row + kColD + b * 128u + (uint32_t)cs * 64u, v);
                         tmem_ld_wait();
-                        relu_split32(v, bias, hi, lo);
+                        relu_split32<kW16>(v, bias, hi, lo);
                         tmem_ld32(tm_row + kColD + b * 128u + (uint32_t)cs * 64u + 32u, v);
                         tmem_ld_wait();
                         tc_fence_before_sync();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&bar_acc_empty[b]);
-                        relu_split32(v, bias + 32, hi + 16, lo + 16);
+                        relu_split32<kW16>(v, bias + 32, hi + 16, lo + 16);
                     }
-#endif
                     ++u;
                 }
                 {   // unit b: once its accumulator is complete every MMA of the layer has consumed the old A
@@ -741,23 +757,6 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
                     tc_fence_after_sync();
                     tmem_st32(tm_row + kColAhi + (uint32_t)cs * 32u, hi);
                     tmem_st32(tm_row + kColAlo + (uint32_t)cs * 32u, lo);
-#if defined(GPB_EPI_LD2) && GPB_EPI_LD2
-                    {
-                        uint32_t v0[32], v1[32];
-                        tmem_ld32(tm_row + kColD + b * 128u + (uint32_t)cs * 64u, v0);
-                        tmem_ld32(tm_row + kColD + b * 128u + (uint32_t)cs * 64u + 32u, v1);
-                        tmem_ld_wait();
-                        tmem_st_wait();             // first half of the new A operand is in tensor memory; the accumulator is in registers
-                        tc_fence_before_sync();
-                        __syncwarp();
-                        if (lane == 0) {
-                            mbar_arrive(&bar_a_ready[0]);
-                            mbar_arrive(&bar_acc_empty[b]);
-                        }
-                        relu_split32(v0, bias + 128, hi, lo);
-                        relu_split32(v1, bias + 128 + 32, hi + 16, lo + 16);
-                    }
-#else
                     {
                         uint32_t v[32];
                         tmem_ld32(tm_row + kColD + b * 128u + (uint32_t)cs * 64u, v);
@@ -767,15 +766,14 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
                         tc_fence_before_sync();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&bar_a_ready[0]);
-                        relu_split32(v, bias + 128, hi, lo);
+                        relu_split32<kW16>(v, bias + 128, hi, lo);
                         tmem_ld32(tm_row + kColD + b * 128u + (uint32_t)cs * 64u + 32u, v);
                         tmem_ld_wait();
                         tc_fence_before_sync();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&bar_acc_empty[b]);
-                        relu_split32(v, bias + 128 + 32, hi + 16, lo + 16);
+                        relu_split32<kW16>(v, bias + 128 + 32, hi + 16, lo + 16);
                     }
-#endif
                     tmem_st32(tm_row + kColAhi + 64u + (uint32_t)cs * 32u, hi);
                     tmem_st32(tm_row + kColAlo + 64u + (uint32_t)cs * 32u, lo);
                     tmem_st_wait();
@@ -824,49 +822,55 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
                 }
             }
             named_bar_sync(3, kTcRowWarps * 32);      // sObt holds obj_bias + t_bias of THIS step (written by warps 4-7)
-            // ---- head slice: relu(acc + obj_bias + t_bias) . O, partial sums per touched head (oA: head hA, oB: head hB) ----
-            float oA[3] = {0.f, 0.f, 0.f}, oB[3] = {0.f, 0.f, 0.f};
-            {   // 128-column unit: this thread's columns [cs*64, +64) of the slice
+            // ---- head slice: relu(acc + obj_bias + t_bias) . O, partial sums per touched head: o[h - hA] (teams 2 and 4 touch two
+            //      heads, team 1 all three) ----
+            float o[3][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
+            auto head_cols = [&](const uint32_t (&v)[32], int nn) {          // 32 columns starting at stacked unit nn (one head per block)
+                const int sel = (nn >> 8) - hA;                              // team 1: a compile-time constant after unrolling
+                if (sel == 0) head_block(v, nn, o[0][0], o[0][1], o[0][2]);
+                else if (kTeam > 1 || sel == 1) head_block(v, nn, o[1][0], o[1][1], o[1][2]);
+                else head_block(v, nn, o[2][0], o[2][1], o[2][2]);
+            };
+#pragma unroll
+            for (int hu = 0; hu < TS::kHeadUnits; ++hu) {
                 const uint32_t b = u & 1u, n = u >> 1;
                 mbar_wait(&bar_acc_full[b], n & 1u);
-                if (ds) ds[5] = clock64();
+                if (ds && hu == 0) ds[5] = clock64();
+                if (ds && hu == TS::kHeadUnits - 1) ds[7] = clock64();
                 tc_fence_after_sync();
+                if (!(TS::kSmallUnit && hu == TS::kHeadUnits - 1)) {
+                    // 128-column unit: this thread's columns [cs*64, +64) of the unit
 #pragma unroll 1
-                for (int blk = 0; blk < 2; ++blk) {
+                    for (int blk = 0; blk < 2; ++blk) {
+                        uint32_t v[32];
+                        tmem_ld32(tm_row + kColD + b * 128u + (uint32_t)(cs * 64 + blk * 32), v);
+                        tmem_ld_wait();
+                        head_cols(v, n_lo + hu * 128 + cs * 64 + blk * 32);
+                    }
+                    tc_fence_before_sync();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&bar_acc_empty[b]);
+                } else {
+                    // 64-column unit (team 4): this thread's columns [cs*32, +32) of the unit
                     uint32_t v[32];
-                    tmem_ld32(tm_row + kColD + b * 128u + (uint32_t)(cs * 64 + blk * 32), v);
+                    tmem_ld32(tm_row + kColD + b * 128u + (uint32_t)(cs * 32), v);
                     tmem_ld_wait();
-                    const int nn = n_lo + cs * 64 + blk * 32;
-                    if ((nn >> 8) == hA) head_block(v, nn, oA[0], oA[1], oA[2]);
-                    else head_block(v, nn, oB[0], oB[1], oB[2]);
+                    tc_fence_before_sync();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&bar_acc_empty[b]);
+                    head_cols(v, n_lo + hu * 128 + cs * 32);
                 }
-                tc_fence_before_sync();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&bar_acc_empty[b]);
                 ++u;
-                if (ds) ds[6] = clock64();
+                if (ds && hu == 0) ds[6] = clock64();
+                if (ds && hu == TS::kHeadUnits - 1) ds[8] = clock64();
             }
-            {   // 64-column unit: this thread's columns [128 + cs*32, +32) of the slice
-                const uint32_t b = u & 1u, n = u >> 1;
-                mbar_wait(&bar_acc_full[b], n & 1u);
-                if (ds) ds[7] = clock64();
-                tc_fence_after_sync();
-                uint32_t v[32];
-                tmem_ld32(tm_row + kColD + b * 128u + (uint32_t)(cs * 32), v);
-                tmem_ld_wait();
-                tc_fence_before_sync();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&bar_acc_empty[b]);
-                const int nn = n_lo + 128 + cs * 32;
-                if ((nn >> 8) == hA) head_block(v, nn, oA[0], oA[1], oA[2]);
-                else head_block(v, nn, oB[0], oB[1], oB[2]);
-                ++u;
-                if (ds) ds[8] = clock64();
-            }
-            // column sub-half 1 hands its partial sums (oA: head hA, oB: head hB) to sub-half 0
+            // column sub-half 1 hands its partial sums to sub-half 0
+            constexpr int kTouched = kTeam == 1 ? 3 : 2;
             if (cs == 1) {
-                sFpart[r * 12 + 0] = oA[0]; sFpart[r * 12 + 1] = oA[1]; sFpart[r * 12 + 2] = oA[2];
-                sFpart[r * 12 + 3] = oB[0]; sFpart[r * 12 + 4] = oB[1]; sFpart[r * 12 + 5] = oB[2];
+#pragma unroll
+                for (int hh = 0; hh < kTouched; ++hh)
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) sFpart[r * 12 + 3 * hh + c] = o[hh][c];
             }
             named_bar_sync(1, kTcRowWarps * 32);      // sub-half 1 partials are in sFpart; everyone is done with sObt
             if (ds) ds[9] = clock64();
@@ -889,27 +893,30 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
                 }
             }
 #pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                oA[c] += sFpart[r * 12 + c];
-                oB[c] += sFpart[r * 12 + 3 + c];
-            }
-            // ---- all-to-all inside the tile team through distributed shared memory: 6 floats per row and rank (its two heads),
-            //      summed by every rank in the same fixed rank order ----
+            for (int hh = 0; hh < kTouched; ++hh)
+#pragma unroll
+                for (int c = 0; c < 3; ++c) o[hh][c] += sFpart[r * 12 + 3 * hh + c];
             float f[9];
-            {
+            if constexpr (kTeam == 1) {
+#pragma unroll
+                for (int c = 0; c < 9; ++c) f[c] = o[c / 3][c % 3];
+                if (ds) ds[11] = ds[10] = clock64();
+            } else {
+                // ---- all-to-all inside the tile team through distributed shared memory: 6 floats per row and rank (its two heads),
+                //      summed by every rank in the same fixed rank order ----
                 const uint32_t par = (uint32_t)step & 1u;
                 float *my_slot = sMail + (((size_t)par * kTeam + rank) * 128 + r) * 8;
                 const uint32_t mail_off = smem_u32(my_slot);
                 const uint32_t bar_off = smem_u32(&bar_mail[par]);
-                if (tid == 0) mbar_arrive_expect_tx(&bar_mail[par], (uint32_t)(kTeam - 1) * 128u * 24u);   // 3 peers x 128 rows x 24 B
-                *reinterpret_cast<float4 *>(my_slot) = make_float4(oA[0], oA[1], oA[2], oB[0]);   // own slot: read back by this same thread
-                *reinterpret_cast<float2 *>(my_slot + 4) = make_float2(oB[1], oB[2]);
+                if (tid == 0) mbar_arrive_expect_tx(&bar_mail[par], (uint32_t)(kTeam - 1) * 128u * 24u);   // peers x 128 rows x 24 B
+                *reinterpret_cast<float4 *>(my_slot) = make_float4(o[0][0], o[0][1], o[0][2], o[1][0]);   // own slot: read back by this same thread
+                *reinterpret_cast<float2 *>(my_slot + 4) = make_float2(o[1][1], o[1][2]);
 #pragma unroll
                 for (uint32_t d = 1; d < (uint32_t)kTeam; ++d) {
                     const uint32_t dst = ((uint32_t)rank + d) & (uint32_t)(kTeam - 1);
                     const uint32_t ra = mapa_shared(mail_off, dst), rb = mapa_shared(bar_off, dst);
-                    st_async_f4(ra, oA[0], oA[1], oA[2], oB[0], rb);
-                    st_async_f2(ra + 16u, oB[1], oB[2], rb);
+                    st_async_f4(ra, o[0][0], o[0][1], o[0][2], o[1][0], rb);
+                    st_async_f2(ra + 16u, o[1][1], o[1][2], rb);
                 }
                 if (ds) ds[11] = clock64();
                 mbar_wait_cluster(&bar_mail[par], ((uint32_t)step >> 1) & 1u);
@@ -918,10 +925,10 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
 #pragma unroll
                 for (int c = 0; c < 9; ++c) f[c] = 0.f;
 #pragma unroll
-                for (int pr = 0; pr < kTeam; ++pr) {     // rank pr covers stacked units [192 pr, 192 pr + 192): heads (192 pr)/256 and (192 pr + 191)/256
+                for (int pr = 0; pr < kTeam; ++pr) {     // rank pr covers stacked units [kCols pr, kCols pr + kCols): heads ha and (if it crosses a boundary) ha + 1
                     const float4 a = *reinterpret_cast<const float4 *>(mb + (size_t)pr * 128 * 8);
                     const float2 b = *reinterpret_cast<const float2 *>(mb + (size_t)pr * 128 * 8 + 4);
-                    const int ha = (192 * pr) / 256, hb = (192 * pr + 191) / 256;
+                    const int ha = (kCols * pr) / 256, hb = (kCols * pr + kCols - 1) / 256;
                     f[3 * ha + 0] += a.x; f[3 * ha + 1] += a.y; f[3 * ha + 2] += a.z;
                     if (hb != ha) { f[3 * hb + 0] += a.w; f[3 * hb + 1] += b.x; f[3 * hb + 2] += b.y; }
                 }
@@ -1174,19 +1181,21 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
                     n2 = fmaf(gr[c], gr[c], n2);
                 }
                 // ---- batch-mean gradient norm = ONE 64-bit word per step: the leader of every tile adds
-                //          (1 << 58 | poisoned << 52 | tile sum as 32.20 fixed point)
+                //          (1 << 56 | poisoned << 48 | tile sum as 22.18 fixed point)      [up to 255 tiles]
                 //      with a single relaxed RED; thread 0 of every CTA polls the word until the arrival count reaches n_tiles and then
                 //      holds the count AND the sum.  Integer addition is associative, so the total is independent of arrival order
-                //      (bitwise reproducible, identical in every CTA) and exact to 2^-20 per tile; no payload travels beside the word, so
+                //      (bitwise reproducible, identical in every CTA) and exact to 2^-19 per tile; no payload travels beside the word, so
                 //      no release/acquire pair and no second round trip for the partials.  (Measured predecessors: partial array +
                 //      RED.release counter + acquire poll + __ldcg of the partials, 2.8 k + 0.9 k cycles per step; per-warp tagged words
                 //      polled by every warp 8.2 k; tagged tile sums polled by one warp per CTA 4.4 k.)  A tile whose sum is NaN or
-                //      >= 2^26 marks the word poisoned and the step's norm becomes NaN, as it would be (or diverge) in the reference.
+                //      >= 2^22 marks the word poisoned and the step's norm becomes NaN, as it would be (or diverge) in the reference.
                 // the step's constants and the predictor drift (0 - g^2 s) dt do not depend on the batch norm: before the grid wait
                 const float g_sde = sigma * kGCoef, g2_sde = g_sde * g_sde, g_sqrt_step = g_sde * sqrt_step;   // ve_sde diffusion (sde.py:20-24)
                 float pd[9];
 #pragma unroll
                 for (int c = 0; c < 9; ++c) pd[c] = (0.0f - g2_sde * gr[c]) * step_size;
+                // fixed-point scale of the step's reduction word: score norms grow like 1 / sigma(t), so the scale follows min(sigma, 1)
+                const float nsum_scale = kNormSumScale * fminf(sigma, 1.0f);
                 if (leader) {
                     const float wsum = warp_sum(valid ? sqrtf(n2) : 0.f);
                     if (lane == 0) s_red[q] = wsum;
@@ -1194,18 +1203,19 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
                     if (tid == 0) {
                         if (ds) ds[14] = clock64();
                         const float tile_sum = (s_red[0] + s_red[1]) + (s_red[2] + s_red[3]);
-                        const bool ok = tile_sum >= 0.f && tile_sum < 67108864.f;                  // false for NaN
-                        const unsigned long long fx = ok ? __float2ull_rn(tile_sum * 1048576.f) : 0ull;
-                        red_relaxed_add_u64(p.acc + step, (1ull << 58) | (ok ? 0ull : (1ull << 52)) | fx);
+                        const float scaled = tile_sum * nsum_scale;
+                        const bool ok = scaled >= 0.f && scaled < kNormSumLimit * kNormSumScale;   // false for NaN
+                        const unsigned long long fx = ok ? __float2ull_rn(scaled) : 0ull;
+                        red_relaxed_add_u64(p.acc + step, (1ull << 56) | (ok ? 0ull : (1ull << 48)) | fx);
                     }
                 }
                 if (tid == 0) {
                     unsigned long long v;
                     do {
                         v = ld_relaxed_gpu_u64(p.acc + step);
-                    } while ((unsigned)(v >> 58) < (unsigned)n_tiles);
-                    const bool poisoned = ((v >> 52) & 63ull) != 0ull;
-                    s_red[4] = poisoned ? __int_as_float(0x7fc00000) : (float)((double)(v & ((1ull << 52) - 1ull)) * (1.0 / 1048576.0));
+                    } while ((unsigned)(v >> 56) < (unsigned)n_tiles);
+                    const bool poisoned = ((v >> 48) & 255ull) != 0ull;
+                    s_red[4] = poisoned ? __int_as_float(0x7fc00000) : (float)((double)(v & ((1ull << 48) - 1ull)) / (double)nsum_scale);
                     if (ds) ds[15] = clock64();
                 }
                 named_bar_sync(2, 128);
@@ -1255,54 +1265,129 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
     }
     tc_fence_before_sync();
     __syncthreads();
-    cluster_sync_all();          // nobody leaves while a team mate may still write into its mailbox
+    if constexpr (kTeam > 1) cluster_sync_all();          // nobody leaves while a team mate may still write into its mailbox
     if (warp == kTcRowWarps) tmem_dealloc(tmem_base, 512);
 }
 
+template <bool kW16, int kTeam>
 __global__ void __launch_bounds__(kTcThreads, 1)   // 10 warps are allocated as 12 (granularity 4): <= 168 registers per thread
 tc_pc_sampler_kernel(TcPcParams tp) {
-    tc_sampler_body<false>(tp);
+    tc_sampler_body<false, kW16, kTeam>(tp);
 }
+template <bool kW16, int kTeam>
 __global__ void __launch_bounds__(kTcThreads, 1)
 tc_ode_sampler_kernel(TcPcParams tp) {
-    tc_sampler_body<true>(tp);
-}
-// EXPERIMENTAL (see TcStream): fp16 weight images, two products per K-step
-__global__ void __launch_bounds__(kTcThreads, 1)
-tc_pc_sampler_w16_kernel(TcPcParams tp) {
-    tc_sampler_body<false, true>(tp);
-}
-__global__ void __launch_bounds__(kTcThreads, 1)
-tc_ode_sampler_w16_kernel(TcPcParams tp) {
-    tc_sampler_body<true, true>(tp);
+    tc_sampler_body<true, kW16, kTeam>(tp);
 }
 
-// cluster (4 CTAs = one tile team, DSMEM) + cooperative (grid barrier => all CTAs must be co-resident) launch of either kernel
-static int launch_tc_sampler(void (*kernel)(TcPcParams), const char *what, const TcPcParams &tp, int n_tiles, uint32_t smem_bytes,
-                             cudaStream_t st) {
-    GPB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(n_tiles * kTeam);
+// ---- the 12 instantiations (sampler x arithmetic x team size) and how one is chosen ----
+using TcKernel = void (*)(TcPcParams);
+struct TcVariant {
+    TcKernel fn;
+    int team;
+    uint32_t smem;
+    int max_tiles;     // co-resident tiles on the current device model (-1 = not asked yet); per process
+};
+template <bool kOde, bool kW16, int kTeam> static TcVariant make_variant() {
+    TcKernel fn;
+    if constexpr (kOde) fn = tc_ode_sampler_kernel<kW16, kTeam>;
+    else fn = tc_pc_sampler_kernel<kW16, kTeam>;
+    return TcVariant{fn, kTeam, TcSmem<kOde, kTeam>::kBytes, -1};
+}
+static TcVariant g_variants[2][2][3] = {
+    {{make_variant<false, false, 1>(), make_variant<false, false, 2>(), make_variant<false, false, 4>()},
+     {make_variant<false, true, 1>(), make_variant<false, true, 2>(), make_variant<false, true, 4>()}},
+    {{make_variant<true, false, 1>(), make_variant<true, false, 2>(), make_variant<true, false, 4>()},
+     {make_variant<true, true, 1>(), make_variant<true, true, 2>(), make_variant<true, true, 4>()}}};
+static std::atomic<int> g_forced_team{0};
+
+// Nsight Compute cannot launch a kernel that is both clustered and cooperative (every replay mode ends in LaunchFailed,
+// profiles/README): under a profiler (its injection environment, or GPB_PROFILE_NO_COOP=1) the cooperative attribute is dropped.
+// Co-residency, which the grid barrier needs, is still established by the occupancy check (1 CTA per SM, grid <= what fits, and a
+// profiler serialises kernels, so the device is idle).
+static bool profiler_attached() {
+    static const bool attached = [] {
+        const char *no_coop = getenv("GPB_PROFILE_NO_COOP");
+        if (no_coop) return no_coop[0] == '1';
+        for (const char *name : {"NV_NSIGHT_INJECTION_TRANSPORT_TYPE", "NV_NSIGHT_INJECTION_PORT_BASE", "NV_COMPUTE_PROFILER_PERFWORKS_DIR",
+                                 "NV_TPS_LAUNCH_TOKEN", "CUDA_INJECTION64_PATH", "NVTX_INJECTION64_PATH"})
+            if (const char *v = getenv(name); v && v[0]) return true;
+        return false;
+    }();
+    return attached;
+}
+
+static void fill_launch_config(const TcVariant &v, int n_tiles, cudaStream_t st, bool cooperative, cudaLaunchConfig_t &cfg,
+                               cudaLaunchAttribute (&attrs)[2]) {
+    cfg = cudaLaunchConfig_t{};
+    cfg.gridDim = dim3(n_tiles * v.team);
     cfg.blockDim = dim3(kTcThreads);
-    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.dynamicSmemBytes = v.smem;
     cfg.stream = st;
-    cudaLaunchAttribute attrs[2];
-    attrs[0].id = cudaLaunchAttributeClusterDimension;
-    attrs[0].val.clusterDim.x = kTeam;
-    attrs[0].val.clusterDim.y = 1;
-    attrs[0].val.clusterDim.z = 1;
-    attrs[1].id = cudaLaunchAttributeCooperative;
-    attrs[1].val.cooperative = 1;
+    int n = 0;
+    if (v.team > 1) {
+        attrs[n].id = cudaLaunchAttributeClusterDimension;
+        attrs[n].val.clusterDim.x = v.team;
+        attrs[n].val.clusterDim.y = 1;
+        attrs[n].val.clusterDim.z = 1;
+        ++n;
+    }
+    if (cooperative) {
+        attrs[n].id = cudaLaunchAttributeCooperative;
+        attrs[n].val.cooperative = 1;
+        ++n;
+    }
     cfg.attrs = attrs;
-    // Nsight Compute cannot launch a kernel that is both clustered and cooperative (every replay mode ends in LaunchFailed,
-    // profiles/README): GPB_PROFILE_NO_COOP=1 drops the cooperative attribute for profiling runs only.  Co-residency, which the
-    // grid barrier needs, is still established by the occupancy check below (1 CTA per SM, grid <= #SMs, idle device).
-    const char *no_coop = getenv("GPB_PROFILE_NO_COOP");
-    cfg.numAttrs = (no_coop && no_coop[0] == '1') ? 1 : 2;
-    int max_clusters = 0;
-    GPB_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, kernel, &cfg));
-    GPB_REQUIRE(max_clusters >= n_tiles, "%s: only %d co-resident 4-CTA clusters fit, %d needed; split the batch", what, max_clusters, n_tiles);
-    GPB_CUDA(cudaLaunchKernelEx(&cfg, kernel, tp));
+    cfg.numAttrs = n;
+}
+
+// how many 128-row tiles this variant can hold co-resident (one team per tile, one CTA per SM); 0 on error
+static int variant_max_tiles(TcVariant &v) {
+    if (v.max_tiles >= 0) return v.max_tiles;
+    int n = 0;
+    if (cudaFuncSetAttribute(v.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v.smem) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    if (v.team > 1) {
+        cudaLaunchConfig_t cfg;
+        cudaLaunchAttribute attrs[2];
+        fill_launch_config(v, 64, nullptr, false, cfg, attrs);
+        if (cudaOccupancyMaxActiveClusters(&n, v.fn, &cfg) != cudaSuccess) {
+            cudaGetLastError();
+            return 0;
+        }
+    } else {
+        int dev = 0, sms = 0, per_sm = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, v.fn, kTcThreads, v.smem) != cudaSuccess) {
+            cudaGetLastError();
+            return 0;
+        }
+        n = sms * per_sm;
+    }
+    v.max_tiles = n < 255 ? n : 255;               // the PC kernel's reduction word counts at most 255 tiles
+    return v.max_tiles;
+}
+
+// team size for n_tiles tiles: the largest team (shortest per-step dependent chain) whose clusters are all co-resident
+static TcVariant *pick_variant(bool ode, bool w16, int n_tiles) {
+    const int forced = g_forced_team.load();
+    for (int ti = 2; ti >= 0; --ti) {
+        TcVariant &v = g_variants[ode][w16][ti];
+        if (forced && v.team != forced) continue;
+        if (n_tiles <= variant_max_tiles(v)) return &v;
+    }
+    return nullptr;
+}
+
+// cluster (the tile team, DSMEM) + cooperative (grid barrier => all CTAs must be co-resident) launch
+static int launch_tc_sampler(TcVariant &v, const char *what, const TcPcParams &tp, int n_tiles, cudaStream_t st) {
+    GPB_CUDA(cudaFuncSetAttribute(v.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v.smem));
+    cudaLaunchConfig_t cfg;
+    cudaLaunchAttribute attrs[2];
+    fill_launch_config(v, n_tiles, st, !profiler_attached(), cfg, attrs);
+    GPB_CUDA(cudaLaunchKernelEx(&cfg, v.fn, tp));
     g_launches.fetch_add(1);
     return GPB_OK;
 }
@@ -1311,35 +1396,29 @@ static int launch_tc_sampler(void (*kernel)(TcPcParams), const char *what, const
 
 using namespace gpb;
 
-extern "C" size_t gpb_trunk_tc_stream_bytes(void) { return (size_t)TcStream<false>::kSlotsPerStep * kSlotBytes; }
-extern "C" size_t gpb_trunk_tc16_stream_bytes(void) { return (size_t)TcStream<true>::kSlotsPerStep * kSlotBytes; }
+extern "C" size_t gpb_trunk_tc_stream_bytes(void) { return (size_t)2 * TcStream<false, 4>::kSlotsPerStep * kSlotBytes; }
+extern "C" size_t gpb_trunk_tc16_stream_bytes(void) { return (size_t)2 * TcStream<true, 4>::kSlotsPerStep * kSlotBytes; }
+
+// Tuning / test knob: force the tile-team size of the tensor-core samplers (1, 2 or 4; 0 = chosen from the row count).
+extern "C" int gpb_set_tc_team(int team) {
+    GPB_REQUIRE(team == 0 || team == 1 || team == 2 || team == 4, "set_tc_team: team must be 0 (auto), 1, 2 or 4");
+    g_forced_team.store(team);
+    return GPB_OK;
+}
 
 // Largest row count R the tensor-core samplers accept on the current device for K candidates per object (0 = not at all):
-// every 128-row tile needs one co-resident 4-CTA cluster, and a tile may span at most kMaxObjPerTile objects.
+// every 128-row tile needs one co-resident CTA (team of 1: one tile per SM), and a tile may span at most kMaxObjPerTile objects.
 extern "C" int gpb_sampler_tc_max_rows(int K) {
     if (K < 1 || 127 / K + 2 > kMaxObjPerTile) return 0;
-    static int cached = -1;                       // per process; the answer depends on the device model only
-    if (cached < 0) {
-        cudaLaunchConfig_t cfg{};
-        cfg.gridDim = dim3(kTeam * 64);
-        cfg.blockDim = dim3(kTcThreads);
-        cfg.dynamicSmemBytes = TcSmem<true>::kBytes;
-        cudaLaunchAttribute attr{};
-        attr.id = cudaLaunchAttributeClusterDimension;
-        attr.val.clusterDim.x = kTeam;
-        attr.val.clusterDim.y = 1;
-        attr.val.clusterDim.z = 1;
-        cfg.attrs = &attr;
-        cfg.numAttrs = 1;
-        int n = 0;
-        if (cudaFuncSetAttribute(tc_ode_sampler_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcSmem<true>::kBytes) != cudaSuccess ||
-            cudaOccupancyMaxActiveClusters(&n, tc_ode_sampler_kernel, &cfg) != cudaSuccess) {
-            cudaGetLastError();
-            return 0;
-        }
-        cached = n < 63 ? n : 63;
+    const int forced = g_forced_team.load();
+    int best = 0;
+    for (int ti = 0; ti < 3; ++ti) {
+        if (forced && g_variants[1][0][ti].team != forced) continue;
+        const int a = variant_max_tiles(g_variants[1][0][ti]), b = variant_max_tiles(g_variants[1][1][ti]);   // the ODE kernels: the larger footprint
+        const int n = a < b ? a : b;
+        best = n > best ? n : best;
     }
-    return cached * kTcRows;
+    return best * kTcRows;
 }
 
 static int sample_pc_tc_impl(bool w16, const float *x0, int R, int K, int num_steps, float snr, const float *obj_bias, const float *W,
@@ -1360,13 +1439,10 @@ static int sample_pc_tc_impl(bool w16, const float *x0, int R, int K, int num_st
         return GPB_EWORKSPACE;
     }
     cudaStream_t st = (cudaStream_t)stream;
-    int dev = 0, sms = 0;
-    GPB_CUDA(cudaGetDevice(&dev));
-    GPB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     const int n_tiles = (R + kTcRows - 1) / kTcRows;
-    const int grid = n_tiles * kTeam;
-    GPB_REQUIRE(n_tiles < 64, "sample_pc_tc: R=%d is %d tiles; the per-step reduction word counts at most 63", R, n_tiles);
-    GPB_REQUIRE(grid <= sms, "sample_pc_tc: R=%d needs %d co-resident CTAs but the device has %d SMs; split the batch", R, grid, sms);
+    TcVariant *v = pick_variant(false, w16, n_tiles);
+    GPB_REQUIRE(v != nullptr, "sample_pc_tc: R=%d is %d tiles of 128 rows; more than fit co-resident on this device (%d); use gpb_sample_pc",
+                R, n_tiles, variant_max_tiles(g_variants[0][w16][0]));
 
     SamplerWs w = carve_sampler(workspace, R, num_steps);
     GPB_CUDA(cudaMemsetAsync(w.barrier, 0, 256, st));
@@ -1381,8 +1457,7 @@ static int sample_pc_tc_impl(bool w16, const float *x0, int R, int K, int num_st
     p.ts = time_grid; p.tb_table = w.tb_table; p.partial = w.partial; p.barrier = w.barrier; p.acc = w.acc;
     p.mean_x = mean_x; p.process = process; p.tiles_per_cta = 1; p.dbg = dbg; p.dbg_cta = dbg ? dbg_cta_sel : 0;
     tp.wstream = reinterpret_cast<const uint8_t *>(tc_stream);
-
-    return launch_tc_sampler(w16 ? tc_pc_sampler_w16_kernel : tc_pc_sampler_kernel, "sample_pc_tc", tp, n_tiles, TcSmem<false>::kBytes, st);
+    return launch_tc_sampler(*v, "sample_pc_tc", tp, n_tiles, st);
 }
 
 extern "C" int gpb_sample_pc_tc_dbg(const float *x0, int R, int K, int num_steps, float snr, const float *obj_bias, const float *W,
@@ -1401,14 +1476,14 @@ extern "C" int gpb_sample_pc_tc16(const float *x0, int R, int K, int num_steps, 
                              process, workspace, workspace_bytes, dbg, stream);
 }
 
-static int sample_ode_tc_impl(bool w16, const float *x0, int R, int K, float T0, float rtol, float atol, int denoise_steps,
+static int sample_ode_tc_impl(bool w16, const float *x0, int R, int K, double T0, double rtol, double atol, int denoise_steps,
                               const float *obj_bias, const float *W, const void *tc_stream, const float *pts_center, double *pose,
                               int *stats, void *workspace, size_t workspace_bytes, unsigned long long *dbg, int dbg_evals,
                               void *stream) {
     GPB_REQUIRE(R >= 0 && K >= 1, "sample_ode_tc: need R >= 0, K >= 1");
     if (R == 0) return GPB_OK;
     GPB_REQUIRE(x0 && obj_bias && W && tc_stream && pts_center && pose && workspace, "sample_ode_tc: NULL buffer");
-    GPB_REQUIRE(T0 > 1e-5f && rtol > 0 && atol > 0, "sample_ode_tc: need T0 > eps and positive tolerances");
+    GPB_REQUIRE(T0 > 1e-5 && rtol > 0 && atol > 0, "sample_ode_tc: need T0 > eps and positive tolerances");
     GPB_REQUIRE(127 / K + 2 <= kMaxObjPerTile, "sample_ode_tc: K=%d too small (a 128-row tile may span at most %d objects); "
                 "use gpb_sample_ode", K, kMaxObjPerTile);
     GPB_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0 && (reinterpret_cast<uintptr_t>(tc_stream) & 15) == 0,
@@ -1419,12 +1494,10 @@ static int sample_ode_tc_impl(bool w16, const float *x0, int R, int K, float T0,
         return GPB_EWORKSPACE;
     }
     cudaStream_t st = (cudaStream_t)stream;
-    int dev = 0, sms = 0;
-    GPB_CUDA(cudaGetDevice(&dev));
-    GPB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     const int n_tiles = (R + kTcRows - 1) / kTcRows;
-    GPB_REQUIRE(n_tiles * kTeam <= sms && n_tiles * kTeam <= 160, "sample_ode_tc: R=%d needs %d co-resident CTAs but the device has %d SMs; "
-                "split the batch", R, n_tiles * kTeam, sms);
+    TcVariant *v = pick_variant(true, w16, n_tiles);
+    GPB_REQUIRE(v != nullptr && n_tiles * v->team <= 160, "sample_ode_tc: R=%d is %d tiles of 128 rows; more than fit co-resident on this "
+                "device (%d); use gpb_sample_ode", R, n_tiles, variant_max_tiles(g_variants[1][w16][0]));
     GPB_CUDA(cudaMemsetAsync(w.barrier, 0, 256, st));
 
     TcPcParams tp{};
@@ -1436,10 +1509,10 @@ static int sample_ode_tc_impl(bool w16, const float *x0, int R, int K, float T0,
     tp.ode.T0 = T0; tp.ode.rtol = rtol; tp.ode.atol = atol; tp.ode.denoise_steps = denoise_steps;
     tp.ode.Kst = w.Kst; tp.ode.partial = reinterpret_cast<double *>(w.partial); tp.ode.tb_cta = w.tb_cta;
     tp.ode.pose = pose; tp.ode.stats = stats;
-    return launch_tc_sampler(w16 ? tc_ode_sampler_w16_kernel : tc_ode_sampler_kernel, "sample_ode_tc", tp, n_tiles, TcSmem<true>::kBytes, st);
+    return launch_tc_sampler(*v, "sample_ode_tc", tp, n_tiles, st);
 }
 
-extern "C" int gpb_sample_ode_tc_dbg(const float *x0, int R, int K, float T0, float rtol, float atol, int denoise_steps,
+extern "C" int gpb_sample_ode_tc_dbg(const float *x0, int R, int K, double T0, double rtol, double atol, int denoise_steps,
                                      const float *obj_bias, const float *W, const void *tc_stream, const float *pts_center, double *pose,
                                      int *stats, void *workspace, size_t workspace_bytes, unsigned long long *dbg, int dbg_evals,
                                      void *stream) {
@@ -1447,7 +1520,7 @@ extern "C" int gpb_sample_ode_tc_dbg(const float *x0, int R, int K, float T0, fl
                               workspace_bytes, dbg, dbg_evals, stream);
 }
 
-extern "C" int gpb_sample_ode_tc16(const float *x0, int R, int K, float T0, float rtol, float atol, int denoise_steps,
+extern "C" int gpb_sample_ode_tc16(const float *x0, int R, int K, double T0, double rtol, double atol, int denoise_steps,
                                    const float *obj_bias, const float *W, const void *tc16_stream, const float *pts_center, double *pose,
                                    int *stats, void *workspace, size_t workspace_bytes, void *stream) {
     return sample_ode_tc_impl(true, x0, R, K, T0, rtol, atol, denoise_steps, obj_bias, W, tc16_stream, pts_center, pose, stats, workspace,
@@ -1462,7 +1535,7 @@ extern "C" int gpb_sample_pc_tc(const float *x0, int R, int K, int num_steps, fl
                                 process, workspace, workspace_bytes, nullptr, stream);
 }
 
-extern "C" int gpb_sample_ode_tc(const float *x0, int R, int K, float T0, float rtol, float atol, int denoise_steps,
+extern "C" int gpb_sample_ode_tc(const float *x0, int R, int K, double T0, double rtol, double atol, int denoise_steps,
                                  const float *obj_bias, const float *W, const void *tc_stream, const float *pts_center, double *pose,
                                  int *stats, void *workspace, size_t workspace_bytes, void *stream) {
     return gpb_sample_ode_tc_dbg(x0, R, K, T0, rtol, atol, denoise_steps, obj_bias, W, tc_stream, pts_center, pose, stats, workspace,

@@ -46,12 +46,17 @@ umma_selftest_kernel(const float *__restrict__ A, const uint16_t *__restrict__ B
             bulk_g2s(sBlo + off, reinterpret_cast<const uint8_t *>(Blo) + off, n, &bar_b);
         }
     }
+    const bool a_f16 = (swap_fields & 4) != 0;    // two-product mode: A as fp16 hi/lo (relu_split_f16x2: A must be >= 0)
     if (warp < 4) {   // row threads: split A row `tid` into bf16 hi/lo and write the operand images
         const int r = tid;
         for (int k8 = 0; k8 < K / 8; ++k8) {
             uint32_t hi[4], lo[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
+                if (a_f16) {
+                    relu_split_f16x2(A[(size_t)r * K + k8 * 8 + 2 * j], A[(size_t)r * K + k8 * 8 + 2 * j + 1], hi[j], lo[j]);
+                    continue;
+                }
                 __nv_bfloat16 h0, l0, h1, l1;
                 split_bf16(A[(size_t)r * K + k8 * 8 + 2 * j], h0, l0);
                 split_bf16(A[(size_t)r * K + k8 * 8 + 2 * j + 1], h1, l1);
@@ -68,6 +73,10 @@ umma_selftest_kernel(const float *__restrict__ A, const uint16_t *__restrict__ B
                 uint32_t hi[8], lo[8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
+                    if (a_f16) {
+                        relu_split_f16x2(A[(size_t)r * K + 2 * (c0 + j)], A[(size_t)r * K + 2 * (c0 + j) + 1], hi[j], lo[j]);
+                        continue;
+                    }
                     __nv_bfloat16 h0, l0, h1, l1;
                     split_bf16(A[(size_t)r * K + 2 * (c0 + j)], h0, l0);
                     split_bf16(A[(size_t)r * K + 2 * (c0 + j) + 1], h1, l1);
@@ -89,10 +98,11 @@ umma_selftest_kernel(const float *__restrict__ A, const uint16_t *__restrict__ B
         tc_fence_after_sync();
         // swap_fields bit 1 (timing aid only, SS form): issue M = 64 instructions (half the rows; D is then NOT the product the
         // caller expects) to measure whether a 64-row tile costs half the tensor time of a 128-row one
-        // swap_fields bit 2: the B images hold fp16 (not bf16) values and only two products are formed, Ahi.B (term 0) and Alo.B
-        // (term 1) — the mixed-format instruction of the two-product samplers (A = bf16, B = fp16 in one kind::f16 MMA)
+        // swap_fields bit 2: the B images hold fp16 (not bf16) values, A is split into fp16 hi/lo and only two products are formed,
+        // Ahi.B (term 0) and Alo.B (term 1) — the arithmetic of the two-product samplers.  (swap_fields bit 3 additionally keeps A
+        // in bf16: the mixed-format kind::f16 instruction, which this part refuses with an illegal-instruction fault.)
         const bool w16 = (swap_fields & 4) != 0;
-        const uint32_t idesc = w16 ? make_idesc_f16kind_f32((swap_fields & 2) ? 64 : 128, N, 1, 0) : make_idesc_bf16_f32((swap_fields & 2) ? 64 : 128, N);
+        const uint32_t idesc = w16 ? make_idesc_f16kind_f32((swap_fields & 2) ? 64 : 128, N, 0, 0) : make_idesc_bf16_f32((swap_fields & 2) ? 64 : 128, N);
         const uint32_t ahi = smem_u32(sAhi), alo = smem_u32(sAlo), bhi = smem_u32(sBhi), blo = smem_u32(sBlo);
         bool acc = false;
         const unsigned long long t_start = clock64();

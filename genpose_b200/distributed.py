@@ -6,6 +6,7 @@ NVSwitch).  ~115 KB per rank at 64x50x9 fp32 => latency-bound, so there is nothi
 Parity caveat: the PC sampler couples all candidates of a launch through the batch-mean
 gradient norm (samplers.py:130) and the ODE sampler through one RK45 error norm (samplers.py:205).  A
 sharded run therefore reproduces the reference executed on the same SHARD, not on the global batch."""
+import math
 import os
 from typing import Callable, Dict, List, Tuple
 
@@ -18,6 +19,10 @@ def init_from_env(backend: str = None) -> Tuple[int, int, int]:
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if torch.cuda.is_available() and (backend or "nccl") == "nccl":
+        # One process per GPU: the C ABI launches on the CUDA *current* device and PoseNet's cfg.device is plain 'cuda', so the
+        # rank's device must be current before anything is allocated (and before NCCL picks its device).
+        torch.cuda.set_device(local_rank % torch.cuda.device_count())
     if world > 1 and not dist.is_initialized():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("MASTER_PORT", "29511")
@@ -56,17 +61,34 @@ def all_gather_objects_dim0(local: torch.Tensor, n_objects: int, world: int, ran
 
 def run_sharded(local_fn: Callable[[int, int], Dict[str, torch.Tensor]], n_objects: int, keys=("pred_pose",)) -> Dict[str, torch.Tensor]:
     """local_fn(lo, hi) computes this rank's objects [lo, hi) and returns tensors with dim 0 = hi - lo.
-    The selected keys are packed into ONE buffer and all-gathered once."""
+    The selected keys are packed into ONE buffer (in the widest dtype among them, so the ODE sampler's float64 poses
+    survive) and all-gathered once.  A rank whose shard is empty (fewer objects than ranks: common in per-frame
+    evaluation) does not call local_fn; it still joins the collective, with the shapes and dtypes the other ranks' results
+    have, learnt from rank 0 through one small metadata broadcast (only taken when n_objects < world_size)."""
     rank = dist.get_rank() if dist.is_initialized() else 0
     world = dist.get_world_size() if dist.is_initialized() else 1
     lo, hi = shard_bounds(n_objects, world)[rank]
-    local = local_fn(lo, hi)
-    flat = [local[k].reshape(hi - lo, -1).float() for k in keys]
-    widths = [f.shape[1] for f in flat]
-    packed = torch.cat(flat, dim=1).contiguous()
+    local = local_fn(lo, hi) if hi > lo else None
+    meta = None if local is None else {k: (tuple(local[k].shape[1:]), local[k].dtype, local[k].device) for k in keys}
+    if world > 1 and n_objects < world:
+        # some shards are empty: their ranks learn shapes / dtypes from rank 0 (the first rank always owns an object)
+        box = [None if meta is None else {k: (m[0], m[1]) for k, m in meta.items()}]
+        dist.broadcast_object_list(box, src=0)
+        if meta is None:
+            dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+            meta = {k: (tuple(box[0][k][0]), box[0][k][1], dev) for k in keys}
+    if meta is None:
+        raise ValueError("run_sharded: no objects at all")
+    wide = torch.float64 if any(m[1] == torch.float64 for m in meta.values()) else torch.float32
+    widths = [int(math.prod(meta[k][0])) for k in keys]
+    device = next(iter(meta.values()))[2]
+    if local is None:
+        packed = torch.zeros(0, sum(widths), dtype=wide, device=device)
+    else:
+        packed = torch.cat([local[k].reshape(hi - lo, w).to(wide) for k, w in zip(keys, widths)], dim=1).contiguous()
     full = all_gather_objects_dim0(packed, n_objects, world, rank)
     out, col = {}, 0
     for k, w in zip(keys, widths):
-        out[k] = full[:, col: col + w].reshape((n_objects,) + tuple(local[k].shape[1:]))
+        out[k] = full[:, col: col + w].reshape((n_objects,) + meta[k][0]).to(meta[k][1])
         col += w
     return out

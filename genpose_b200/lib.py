@@ -9,7 +9,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("GPB_LIB") or os.path.join(_HERE, "libgenpose_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
 
-_vp, _i, _f, _sz, _u64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_size_t, ctypes.c_uint64
+_vp, _i, _f, _d, _sz, _u64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_double, ctypes.c_size_t, ctypes.c_uint64
 
 # name -> (restype, argtypes); mirrors include/genpose_b200.h one to one
 SIGNATURES = {
@@ -33,13 +33,14 @@ SIGNATURES = {
     "gpb_encode_tc": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _sz, _vp, _vp, _vp, _vp]),
     "gpb_sample_pc_tc": (_i, [_vp, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _u64, _vp, _vp, _vp, _vp, _sz, _vp]),
     "gpb_sample_pc_tc_dbg": (_i, [_vp, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _u64, _vp, _vp, _vp, _vp, _sz, _vp, _vp]),
-    "gpb_sample_ode": (_i, [_vp, _i, _i, _f, _f, _f, _i, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "gpb_sample_ode": (_i, [_vp, _i, _i, _d, _d, _d, _i, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "gpb_sampler_tc_max_rows": (_i, [_i]),
-    "gpb_sample_ode_tc": (_i, [_vp, _i, _i, _f, _f, _f, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
-    "gpb_sample_ode_tc_dbg": (_i, [_vp, _i, _i, _f, _f, _f, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _i, _vp]),
+    "gpb_set_tc_team": (_i, [_i]),
+    "gpb_sample_ode_tc": (_i, [_vp, _i, _i, _d, _d, _d, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "gpb_sample_ode_tc_dbg": (_i, [_vp, _i, _i, _d, _d, _d, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _i, _vp]),
     "gpb_trunk_tc16_stream_bytes": (_sz, []),
     "gpb_sample_pc_tc16": (_i, [_vp, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _u64, _vp, _vp, _vp, _vp, _sz, _vp, _vp]),
-    "gpb_sample_ode_tc16": (_i, [_vp, _i, _i, _f, _f, _f, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "gpb_sample_ode_tc16": (_i, [_vp, _i, _i, _d, _d, _d, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "gpb_energy": (_i, [_vp, _i, _i, _f, _vp, _vp, _vp, _vp, _vp]),
     "gpb_rank_pool": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "gpb_prepare_clouds": (_i, [_vp, _vp, ctypes.c_longlong, ctypes.c_longlong, _i, _i, _i, _vp, ctypes.POINTER(ctypes.c_float), _vp, _u64,

@@ -8,6 +8,9 @@ import torch
 
 from . import arch, lib, weights
 
+# what precision="auto" means for the samplers when the tensor-core kernels accept the shape
+AUTO_TC_PRECISION = "bf16x3"
+
 
 def _chk(t: torch.Tensor, dtype, name: str) -> int:
     if not isinstance(t, torch.Tensor) or not t.is_cuda:
@@ -101,7 +104,7 @@ class Engine:
         self._trunk_tc16: Optional[torch.Tensor] = None
 
     def trunk_tc16(self) -> torch.Tensor:
-        """EXPERIMENTAL two-product stream (weights.pack_trunk_tc16), packed on first use of precision='bf16x2'."""
+        """Two-product stream (weights.pack_trunk_tc16), packed on first use of precision='f16x2'."""
         if self._trunk_tc16 is None:
             tc = weights.pack_trunk_tc16(self._state_for_tc16)
             if tc.numel() * 2 != lib.load().gpb_trunk_tc16_stream_bytes():
@@ -120,7 +123,7 @@ class Engine:
     def encode(self, pts: torch.Tensor, return_fps: bool = False, precision: str = "auto"):
         """Pointnet2ClsMSG.forward: pts [B,1024,3] (raw camera frame) -> pts_feat [B,1024].
         precision 'fp32' = every level on FFMA; 'bf16x3' / 'auto' = set-abstraction level 3 on tcgen05 (bf16x3 split)."""
-        if precision not in ("auto", "bf16x3", "bf16x2", "fp32"):      # 'bf16x2' concerns the samplers only: tensor-core encoder as 'bf16x3'
+        if precision not in ("auto", "bf16x3", "f16x2", "fp32"):      # 'f16x2' concerns the samplers only: tensor-core encoder as 'bf16x3'
             raise lib.GenPoseB200Error(f"encode: unknown precision {precision!r}")
         B, N, C = pts.shape
         if N != arch.NUM_POINTS or C != 3:
@@ -159,20 +162,25 @@ class Engine:
     @staticmethod
     def tc_supported(R: int, K: int) -> bool:
         """tcgen05 sampler constraints (asked of the library): a 128-row tile spans <= 4 objects (K >= 43) and every tile
-        needs one co-resident 4-CTA cluster (33 tiles = 4224 rows on a B200)."""
+        needs one co-resident team of CTAs — 4 per tile up to 33 tiles, 2 up to 66, 1 up to one tile per SM (148 tiles =
+        18,944 rows = 378 objects x 50 candidates on a B200)."""
         return 0 < R <= lib.load().gpb_sampler_tc_max_rows(int(K))
+
+    def _resolve_precision(self, what: str, precision: str, R: int, K: int) -> str:
+        if precision == "auto":
+            precision = AUTO_TC_PRECISION if self.tc_supported(R, K) else "fp32"
+        if precision not in ("fp32", "bf16x3", "f16x2"):
+            raise lib.GenPoseB200Error(f"{what}: unknown precision {precision!r}")
+        return precision
 
     def sample_pc(self, obj_bias: torch.Tensor, pts_center: torch.Tensor, x0: torch.Tensor, K: int, num_steps: int,
                   step_noise: Optional[torch.Tensor] = None, seed: int = 0, snr: float = arch.SNR,
-                  return_process: bool = False, precision: str = "fp32"):
-        """precision 'fp32' = FFMA parity kernel; 'bf16x3' = tcgen05 tensor-core kernel; 'auto' = tensor cores when
-        the shape allows; 'bf16x2' = EXPERIMENTAL two-product tensor-core kernel (fp16 weight images, include/genpose_b200.h),
-        never chosen by 'auto'."""
+                  return_process: bool = False, precision: str = "fp32", team: int = 0):
+        """precision 'fp32' = FFMA parity kernel; 'bf16x3' = tcgen05 kernel, three products per K-step (bf16 hi/lo operands);
+        'f16x2' = tcgen05 kernel, two products (fp16 hi/lo activations x one fp16 weight image); 'auto' = tensor cores
+        (AUTO_TC_PRECISION) when the shape allows.  team: 0 = tile-team size chosen from the row count, 1 / 2 / 4 force it."""
         R = x0.shape[0]
-        if precision == "auto":
-            precision = "bf16x3" if self.tc_supported(R, K) else "fp32"
-        if precision not in ("fp32", "bf16x3", "bf16x2"):
-            raise lib.GenPoseB200Error(f"sample_pc: unknown precision {precision!r}")
+        precision = self._resolve_precision("sample_pc", precision, R, K)
         L = lib.load()
         ws = self._workspace("samp", L.gpb_sampler_workspace_bytes(R, num_steps))
         ts = self._time_grids.get(num_steps)         # built once per T: a pageable host->device copy per call would make the host
@@ -187,10 +195,12 @@ class Engine:
                   _stream())
         head = (_chk(x0, torch.float32, "x0"), R, K, num_steps, float(snr), _chk(obj_bias, torch.float32, "obj_bias"),
                 self.trunk_w.data_ptr())
+        if precision != "fp32":
+            lib.check(L.gpb_set_tc_team(int(team)), "set_tc_team")
         if precision == "bf16x3":
             lib.check(L.gpb_sample_pc_tc(*head, self.trunk_tc.data_ptr(), _chk(pts_center, torch.float32, "pts_center"), *common),
                       "sample_pc_tc")
-        elif precision == "bf16x2":
+        elif precision == "f16x2":
             lib.check(L.gpb_sample_pc_tc16(*head, self.trunk_tc16().data_ptr(), _chk(pts_center, torch.float32, "pts_center"),
                                            *common[:-1], 0, common[-1]), "sample_pc_tc16")
         else:
@@ -199,15 +209,11 @@ class Engine:
 
     # ---- a10: ODE sampler --------------------------------------------------------------------------------
     def sample_ode(self, obj_bias: torch.Tensor, pts_center: torch.Tensor, x0: torch.Tensor, K: int, T0: float = 1.0,
-                   rtol: float = 1e-5, atol: float = 1e-5, denoise_steps: int = 1000, precision: str = "fp32"):
+                   rtol: float = 1e-5, atol: float = 1e-5, denoise_steps: int = 1000, precision: str = "fp32", team: int = 0):
         """cond_ode_sampler (samplers.py:163-227): RK45 with SciPy's controller on device -> (pose [R,9] float64, stats [4]).
-        precision 'fp32' = FFMA parity kernel; 'bf16x3' = tcgen05 kernel; 'auto' = tensor cores when the shape allows;
-        'bf16x2' = EXPERIMENTAL two-product tensor-core kernel, never chosen by 'auto'."""
+        precision and team as in sample_pc."""
         R = x0.shape[0]
-        if precision == "auto":
-            precision = "bf16x3" if self.tc_supported(R, K) else "fp32"
-        if precision not in ("fp32", "bf16x3", "bf16x2"):
-            raise lib.GenPoseB200Error(f"sample_ode: unknown precision {precision!r}")
+        precision = self._resolve_precision("sample_ode", precision, R, K)
         L = lib.load()
         ws = self._workspace("samp", L.gpb_sampler_workspace_bytes(R, 1))
         pose = torch.empty(R, 9, dtype=torch.float64, device=self.device)
@@ -215,9 +221,11 @@ class Engine:
         head = (_chk(x0, torch.float32, "x0"), R, K, float(T0), float(rtol), float(atol), int(denoise_steps),
                 _chk(obj_bias, torch.float32, "obj_bias"), self.trunk_w.data_ptr())
         tail = (_chk(pts_center, torch.float32, "pts_center"), pose.data_ptr(), stats.data_ptr(), ws.data_ptr(), ws.numel(), _stream())
+        if precision != "fp32":
+            lib.check(L.gpb_set_tc_team(int(team)), "set_tc_team")
         if precision == "bf16x3":
             lib.check(L.gpb_sample_ode_tc(*head, self.trunk_tc.data_ptr(), *tail), "sample_ode_tc")
-        elif precision == "bf16x2":
+        elif precision == "f16x2":
             lib.check(L.gpb_sample_ode_tc16(*head, self.trunk_tc16().data_ptr(), *tail), "sample_ode_tc16")
         else:
             lib.check(L.gpb_sample_ode(*head, *tail), "sample_ode")

@@ -228,27 +228,43 @@ def pack_encoder_tc(sd: Dict[str, torch.Tensor], prefix: str = "pts_encoder") ->
     return torch.cat([consts.view(torch.uint8)] + streams).contiguous()
 
 
+def _trunk_tc_layouts(sd, prefix, common_slots, unit_slots):
+    """Both head layouts of the tensor-core weight stream (tc_sampler.cu TcStream): A = team of 4 (per rank r the stacked head
+    units [192r, 192r+128) as a 128-row unit, then [192r+128, 192r+192) as a 64-row unit), then B = teams of 2 and 1 (six 128-row
+    units in column order; rank r of a team of 2 streams units 3r..3r+2).  Each layout starts with the common slots (P1, P2)."""
+    g = lambda k: sd[f"{prefix}.{k}"].float()
+    off = arch.PTS_FEAT_DIM + arch.T_EMBED_DIM
+    stacked = torch.cat([g(f"fusion_tail_{h}.0.weight")[:, off:] for h in arch.HEADS], dim=0)      # [768, 256] (scorenet.py:204)
+    lay_a, lay_b = list(common_slots), list(common_slots)
+    for r in range(4):
+        lay_a += unit_slots(stacked[192 * r: 192 * r + 128], False)
+        lay_a += unit_slots(stacked[192 * r + 128: 192 * r + 192], True)
+    for u in range(6):
+        lay_b += unit_slots(stacked[128 * u: 128 * u + 128], False)
+    assert len(lay_a) == len(lay_b) and all(sl.numel() * 2 == 16384 for sl in lay_a + lay_b), (len(lay_a), len(lay_b))
+    return torch.cat(lay_a + lay_b).contiguous()
+
+
 def pack_trunk_tc(sd: Dict[str, torch.Tensor], prefix: str = "pose_score_net") -> torch.Tensor:
-    """The weight stream of tc_pc_sampler_kernel: 65 slots of 16 KiB (int16 words), each a pair `hi image | lo image` of
-    K-major no-swizzle operand blocks [K/8][rows][8]:
+    """The weight stream of the three-product tensor-core samplers: 2 layouts x 65 slots of 16 KiB (int16 words), each slot a pair
+    `hi image | lo image` of K-major no-swizzle operand blocks [K/8][rows][8]:
          slot 0         : P1 (K padded 9 -> 16), output neurons [0,128): hi (4 KiB) | lo (4 KiB), then [128,256): hi | lo
          slots 1..16    : P2: for unit in ([0,128), [128,256)): for K-chunk kc in 0..7 (32 inputs): 128-row hi (8 KiB) | lo (8 KiB)
-         slots 17+12r.. : head slice of team rank r = stacked hidden units [192r, 192r+192) of the three heads
-                          (rows h*256 + j of fusion_tail_{rot_x,rot_y,trans}.0.weight[:, 1152:1408], scorenet.py:204):
-                            8 slots : units [192r, 192r+128), K-chunk kc: 128-row hi (8 KiB) | lo (8 KiB)
-                            4 slots : units [192r+128, 192r+192), two K-chunks per slot: 64-row hi (4 KiB) | lo (4 KiB), twice
-    Every CTA streams slots 0..16 plus its rank's 12 slots each step."""
+         slots 17..64   : the pose block of the three stacked heads (rows h*256 + j of fusion_tail_{rot_x,rot_y,trans}.0.weight[:, 1152:1408]):
+                          128-row units, K-chunk kc: hi (8 KiB) | lo (8 KiB), 8 slots each; 64-row units (layout A), two K-chunks
+                          per slot: hi (4 KiB) | lo (4 KiB), twice, 4 slots each; order per layout: _trunk_tc_layouts.
+    Every CTA streams slots 0..16 plus its rank's head slots each step."""
     g = lambda k: sd[f"{prefix}.{k}"].float()
-    slots = []
     p1 = torch.zeros(256, 16)
     p1[:, :9] = g("pose_encoder.0.weight")
     parts = []
     for unit in range(2):
         hi, lo = split_bf16(p1[128 * unit: 128 * unit + 128])
         parts += [umma_image(hi), umma_image(lo)]
-    slots.append(torch.cat(parts))
+    common = [torch.cat(parts)]
 
-    def unit_slots(w_rows, chunks_per_slot):
+    def unit_slots(w_rows, small):
+        chunks_per_slot = 2 if small else 1
         rows = w_rows.shape[0]
         hi, lo = split_bf16(w_rows)
         ih, il = umma_image(hi).reshape(32, rows * 8), umma_image(lo).reshape(32, rows * 8)
@@ -262,32 +278,28 @@ def pack_trunk_tc(sd: Dict[str, torch.Tensor], prefix: str = "pose_score_net") -
 
     p2 = g("pose_encoder.2.weight")
     for unit in range(2):
-        slots += unit_slots(p2[128 * unit: 128 * unit + 128], 1)
-    off = arch.PTS_FEAT_DIM + arch.T_EMBED_DIM
-    stacked = torch.cat([g(f"fusion_tail_{h}.0.weight")[:, off:] for h in arch.HEADS], dim=0)      # [768, 256]
-    for r in range(4):
-        slots += unit_slots(stacked[192 * r: 192 * r + 128], 1)
-        slots += unit_slots(stacked[192 * r + 128: 192 * r + 192], 2)
-    assert all(sl.numel() * 2 == 16384 for sl in slots) and len(slots) == 65, (len(slots), {sl.numel() for sl in slots})
-    return torch.cat(slots).contiguous()
+        common += unit_slots(p2[128 * unit: 128 * unit + 128], False)
+    out = _trunk_tc_layouts(sd, prefix, common, unit_slots)
+    assert out.numel() * 2 == 2 * 65 * 16384
+    return out
 
 
 FP16_MAX = 65504.0
 
 
 def pack_trunk_tc16(sd: Dict[str, torch.Tensor], prefix: str = "pose_score_net") -> torch.Tensor:
-    """EXPERIMENTAL weight stream of the two-product tensor-core samplers (tc_sampler.cu, TcStream<true>): 33 slots of 16 KiB
+    """Weight stream of the two-product tensor-core samplers (tc_sampler.cu, TcStream<true, .>): 2 layouts x 33 slots of 16 KiB
     (int16 words), K-major no-swizzle operand blocks [K/8][rows][8] like pack_trunk_tc, but the weights of layer 1 and of the heads
     as ONE fp16 image each (no lo image):
          slot 0          : P1 exactly as in pack_trunk_tc (bf16 hi | lo per unit; layer 0 keeps its five products)
          slots 1..8      : P2: for unit in ([0,128), [128,256)): 4 slots, slot q = inputs [64q, 64q+64) of the 128 rows (fp16)
-         slots 9+6r..    : head slice of team rank r: 4 slots (units [192r, 192r+128), K = 64 each), then 2 slots
-                           (units [192r+128, 192r+192), K = 128 each)
+         slots 9..32     : head units: 128-row units 4 slots (K = 64 each), 64-row units (layout A) 2 slots (K = 128 each)
     Weights beyond the fp16 range are refused (use the three-product stream)."""
     g = lambda k: sd[f"{prefix}.{k}"].float()
-    slots = [pack_trunk_tc(sd, prefix)[:8192]]                                   # slot 0: 16 KiB = 8192 int16 words
+    common = [pack_trunk_tc(sd, prefix)[:8192]]                                   # slot 0: 16 KiB = 8192 int16 words
 
-    def unit_slots16(w_rows, k_per_slot):
+    def unit_slots16(w_rows, small):
+        k_per_slot = 128 if small else 64
         if float(w_rows.abs().max()) >= FP16_MAX:
             raise ValueError("pack_trunk_tc16: a weight exceeds the fp16 range; use pack_trunk_tc (bf16x3)")
         rows = w_rows.shape[0]
@@ -296,11 +308,7 @@ def pack_trunk_tc16(sd: Dict[str, torch.Tensor], prefix: str = "pose_score_net")
 
     p2 = g("pose_encoder.2.weight")
     for unit in range(2):
-        slots += unit_slots16(p2[128 * unit: 128 * unit + 128], 64)
-    off = arch.PTS_FEAT_DIM + arch.T_EMBED_DIM
-    stacked = torch.cat([g(f"fusion_tail_{h}.0.weight")[:, off:] for h in arch.HEADS], dim=0)      # [768, 256]
-    for r in range(4):
-        slots += unit_slots16(stacked[192 * r: 192 * r + 128], 64)
-        slots += unit_slots16(stacked[192 * r + 128: 192 * r + 192], 128)
-    assert all(sl.numel() * 2 == 16384 for sl in slots) and len(slots) == 33, (len(slots), {sl.numel() for sl in slots})
-    return torch.cat(slots).contiguous()
+        common += unit_slots16(p2[128 * unit: 128 * unit + 128], False)
+    out = _trunk_tc_layouts(sd, prefix, common, unit_slots16)
+    assert out.numel() * 2 == 2 * 33 * 16384
+    return out

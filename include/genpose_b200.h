@@ -150,44 +150,52 @@ GPB_API int gpb_sample_pc_tc_dbg(const float *x0, int R, int K, int num_steps, f
  * Dormand-Prince 5(4) with SciPy's step controller, float64 state, fp32 score, one error norm over the
  * whole [R*9] state, followed by the reference's Euler "denoise" step (:209-218).
  *   x0 [R,9] f32        already-noised start (sigma(T0)*randn, plus init_x when tracking, :180)
+ *   T0, rtol, atol      float64, as the Python floats the reference hands to solve_ivp (samplers.py:178, :205)
  *   pose [R,9] f64 out  (the reference returns float64, :206-207)
  *   stats [4] i32 out   optional: nfev, accepted, rejected, status */
-GPB_API int gpb_sample_ode(const float *x0, int R, int K, float T0, float rtol, float atol, int denoise_steps,
+GPB_API int gpb_sample_ode(const float *x0, int R, int K, double T0, double rtol, double atol, int denoise_steps,
                    const float *obj_bias, const float *trunk_weights, const float *pts_center, double *pose,
                    int *stats, void *workspace, size_t workspace_bytes, void *stream);
 
 /* largest R gpb_sample_pc_tc / gpb_sample_ode_tc accept on the current device for K candidates per object (0 = K too
- * small or no device): one co-resident 4-CTA cluster per 128-row tile. */
+ * small or no device): every 128-row tile needs one co-resident team of CTAs, and a team may be a single CTA, so
+ * one tile per SM (148 tiles = 18,944 rows on a B200). */
 GPB_API int gpb_sampler_tc_max_rows(int K);
+
+/* Tuning / test knob: the tensor-core samplers give every 128-row tile to a TEAM of 4, 2 or 1 CTAs (a thread-block
+ * cluster; the head layer is split over the ranks).  By default the largest team whose clusters are all co-resident
+ * is used (4 up to 33 tiles, 2 up to 66, 1 up to 148 on a B200); team = 1, 2 or 4 forces one, 0 restores the default.
+ * Process-wide; results of different team sizes agree to the summation order of the head partials (~1e-6). */
+GPB_API int gpb_set_tc_team(int team);
 
 /* gpb_sample_ode on the tensor cores: the same solver (same controller, float64 state, one error norm over the whole
  * batch) with the score network's dense layers evaluated by tcgen05.mma (bf16x3 split, fp32 accumulation in tensor
- * memory), four CTAs (one thread-block cluster) per 128-row tile as in gpb_sample_pc_tc.  tc_stream as there.
- * Constraints: K >= 43, 4*ceil(R/128) <= #SMs; otherwise use gpb_sample_ode. */
-GPB_API int gpb_sample_ode_tc(const float *x0, int R, int K, float T0, float rtol, float atol, int denoise_steps,
+ * memory), one team of CTAs per 128-row tile as in gpb_sample_pc_tc.  tc_stream as there.
+ * Constraints: K >= 43, R <= gpb_sampler_tc_max_rows(K); otherwise use gpb_sample_ode. */
+GPB_API int gpb_sample_ode_tc(const float *x0, int R, int K, double T0, double rtol, double atol, int denoise_steps,
                       const float *obj_bias, const float *trunk_weights, const void *tc_stream, const float *pts_center,
                       double *pose, int *stats, void *workspace, size_t workspace_bytes, void *stream);
 
 /* profiling aid: as gpb_sample_ode_tc, additionally records clock64 stamps of CTA 0 for the first dbg_evals evaluations
  * into dbg [2][dbg_evals][16] (row thread 0 | MMA warp); see tools/tc_ode_phase_times.py. */
-GPB_API int gpb_sample_ode_tc_dbg(const float *x0, int R, int K, float T0, float rtol, float atol, int denoise_steps,
+GPB_API int gpb_sample_ode_tc_dbg(const float *x0, int R, int K, double T0, double rtol, double atol, int denoise_steps,
                           const float *obj_bias, const float *trunk_weights, const void *tc_stream, const float *pts_center,
                           double *pose, int *stats, void *workspace, size_t workspace_bytes, unsigned long long *dbg,
                           int dbg_evals, void *stream);
 
-/* EXPERIMENTAL — arithmetic emulated on the CPU (oracle/tc_emulation.py: within 0.5 of the parity bound on the shortest chains,
- * 0.03 at T = 500), kernels not yet run on hardware; nothing selects them unless the caller asks for precision "bf16x2".
- * gpb_sample_pc_tc / gpb_sample_ode_tc with TWO tensor-core products per K-step instead of three: the activations keep their
- * bf16 hi/lo split (tensor memory), the weights of layer 1 and of the heads are ONE fp16 image (11-bit mantissa) — the
- * dropped Ahi.Blo product only carried the weights' bits beyond bf16.  tc16_stream = gpb_trunk_tc16_stream_bytes() bytes
- * from genpose_b200/weights.py::pack_trunk_tc16 (33 slots of 16 KiB; 15 per CTA and step instead of 29).  Same constraints,
- * workspace and semantics as the functions they mirror; dbg as in gpb_sample_pc_tc_dbg (may be NULL). */
+/* gpb_sample_pc_tc / gpb_sample_ode_tc with TWO tensor-core products per K-step instead of three ("f16x2"): the activations
+ * of layer 1 and of the heads are split into fp16 hi + lo (tensor memory, 21 mantissa bits), their weights are ONE fp16 image
+ * (11-bit mantissa) — the dropped Ahi.Blo product only carried the weights' bits beyond the first image.  (kind::f16 wants
+ * one format for both operands: bf16 activations against fp16 weights fault.)  Weights beyond the fp16 range are refused by the
+ * packer; activations beyond it saturate.  tc16_stream = gpb_trunk_tc16_stream_bytes() bytes from
+ * genpose_b200/weights.py::pack_trunk_tc16 (2 layouts x 33 slots of 16 KiB).  Same constraints, workspace and semantics as
+ * the functions they mirror; dbg as in gpb_sample_pc_tc_dbg (may be NULL). */
 GPB_API size_t gpb_trunk_tc16_stream_bytes(void);
 GPB_API int gpb_sample_pc_tc16(const float *x0, int R, int K, int num_steps, float snr, const float *obj_bias,
                        const float *trunk_weights, const void *tc16_stream, const float *pts_center,
                        const float *step_noise, uint64_t seed, const float *time_grid, float *mean_x, float *process,
                        void *workspace, size_t workspace_bytes, unsigned long long *dbg, void *stream);
-GPB_API int gpb_sample_ode_tc16(const float *x0, int R, int K, float T0, float rtol, float atol, int denoise_steps,
+GPB_API int gpb_sample_ode_tc16(const float *x0, int R, int K, double T0, double rtol, double atol, int denoise_steps,
                         const float *obj_bias, const float *trunk_weights, const void *tc16_stream, const float *pts_center,
                         double *pose, int *stats, void *workspace, size_t workspace_bytes, void *stream);
 
@@ -205,7 +213,7 @@ GPB_API int gpb_rank_pool(const float *pose, const float *energy, int B, int K, 
                   float *sorted_energy, float *pooled_RT, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
- * (3) HOST-BUFFER CONVENIENCE — one call from host clouds to host poses (what bench.py's `e2e` times).
+ * (3) BOOK-KEEPING
  * ---------------------------------------------------------------------------------------------- */
 /* Kernel launch counter (for bench.py's gpu_launches claim): number of kernels this library has
  * launched since load, across all threads. */

@@ -7,9 +7,10 @@ pin DESIGN.md §5's precision claim in the CPU suite.  It restates what the kern
   * layer 0 from THREE bf16 pieces of the pose row (x1 + x2 + x3) against P1 hi | lo (five products, publish_x);
   * everything the kernel hoists out of the row loop in fp32: object bias A_pts.pts_feat + a, time bias A_t.relu(L_t.fourier(t)).
 
-`terms` selects how many products of the split are kept (3 = shipped "bf16x3", 1 = plain bf16) so that a test can show why the
-split is needed; terms = "x2" is the experimental two-product mode (tc_sampler.cu, TcStream<true>): activations bf16 hi + lo,
-the weights of layer 1 and of the heads ONE fp16 value each, products Ahi.W + Alo.W (layer 0 keeps its five bf16 products).  The score network it emulates is PoseScoreNet.forward (networks/gf_algorithms/scorenet.py:178-222)."""
+`terms` selects how many products of the split are kept (3 = "bf16x3", 1 = plain bf16) so that a test can show why the
+split is needed; terms = "x2" is the two-product mode "f16x2" (tc_sampler.cu, TcStream<true, .>): activations fp16 hi + lo
+(hi = truncation, lo = rounded residual, both through a ReLU; tc_common.cuh relu_split_f16x2), the weights of layer 1 and of the
+heads ONE fp16 value each, products Ahi.W + Alo.W (layer 0 keeps its five bf16 products).  The score network it emulates is PoseScoreNet.forward (networks/gf_algorithms/scorenet.py:178-222)."""
 from contextlib import contextmanager
 
 import numpy as np
@@ -25,27 +26,28 @@ def split_bf16(t: torch.Tensor):
     return hi, lo
 
 
-ACT_SPLIT = "rn"          # "rz_relu": the experimental ReLU-fused activation split of tc_common.cuh (relu_split_bf16x2_rz)
+FP16_MAX = 65504.0
 
 
-def split_act(a: torch.Tensor):
-    """hi/lo of a POST-ReLU activation.  'rn': hi = rn_bf16(a), lo = rn_bf16(a - hi) (shipped).  'rz_relu': hi = bf16 truncation
-    (cvt.rz.relu; a >= 0 so the residual is >= 0), lo = rn_bf16(max(residual, 0)) (cvt.rn.relu)."""
-    if ACT_SPLIT == "rn":
-        return split_bf16(a)
-    a = a.float()
-    hi = (a.view(torch.int32) & ~0xFFFF).view(torch.float32)
-    hi = torch.where(a > 0, hi, torch.zeros_like(hi))
-    return hi, torch.clamp(a - hi, min=0).to(torch.bfloat16).float()
+def split_act_f16(a: torch.Tensor):
+    """relu_split_f16x2 (tc_common.cuh): hi = fp16 TRUNCATION of max(a, 0) saturated at 65504 (cvt.rz.relu.satfinite), lo =
+    rn_fp16(max(a - hi, 0)) (cvt.rn.relu.satfinite)."""
+    a = torch.clamp(a.float(), min=0.0)
+    normal = (a.view(torch.int32) & ~0x1FFF).view(torch.float32)             # keep 10 mantissa bits (fp16 normal range)
+    sub = torch.floor(a * 2.0 ** 24) * 2.0 ** -24                              # below 2^-14: multiples of the fp16 subnormal step
+    hi = torch.clamp(torch.where(a >= 2.0 ** -14, normal, sub), max=FP16_MAX)
+    lo = torch.clamp(a - hi, min=0.0, max=FP16_MAX).to(torch.float16).float()
+    return hi, lo
 
 
 def mm_split(a: torch.Tensor, w: torch.Tensor, terms=3) -> torch.Tensor:
     """a [R,K] . w [N,K]^T with both operands split into bf16 hi + lo; products are exact in fp32, sums are fp32.
-    a is a post-ReLU activation (split_act), w a weight block."""
-    ah, al = split_act(a)
+    a is a post-ReLU activation, w a weight block.  terms = "x2": fp16 hi/lo activations against ONE fp16 weight."""
     if terms == "x2":
+        ah, al = split_act_f16(a)
         w16 = w.float().to(torch.float16).float()
         return ah @ w16.t() + al @ w16.t()
+    ah, al = split_bf16(a)
     wh, wl = split_bf16(w)
     out = ah @ wh.t()
     if terms >= 2:

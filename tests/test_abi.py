@@ -38,7 +38,7 @@ def test_abi_version_and_sizes(built):
     assert built.gpb_encoder_weights_floats() == weights.encoder_floats()
     assert built.gpb_trunk_weights_floats() == weights.trunk_floats()
     assert built.gpb_encode_workspace_bytes(64) > 0 and built.gpb_sampler_workspace_bytes(3200, 500) > 0
-    assert built.gpb_trunk_tc_stream_bytes() == 65 * 16384 and built.gpb_trunk_tc16_stream_bytes() == 33 * 16384
+    assert built.gpb_trunk_tc_stream_bytes() == 2 * 65 * 16384 and built.gpb_trunk_tc16_stream_bytes() == 2 * 33 * 16384
     assert built.gpb_launch_count() == 0
 
 

@@ -37,19 +37,19 @@ def _worker(rank, world, port, n_objects, ret):
         ids = torch.arange(lo, hi, dtype=torch.float32)
         pose = ids[:, None, None] * 100 + torch.arange(5)[None, :, None] * 10 + torch.arange(9)[None, None, :]
         energy = ids[:, None, None] + torch.zeros(hi - lo, 5, 2)
-        return {"pred_pose": pose, "energy": energy}
+        assert hi > lo, "local_fn must not be called for an empty shard"
+        return {"pred_pose": pose.double() + 1e-9, "energy": energy}          # float64 poses (ODE sampler) must survive the gather
 
     out = D.run_sharded(local_fn, n_objects, keys=("pred_pose", "energy"))
     ref = local_fn(0, n_objects)
-    ok = all(torch.equal(out[k], ref[k]) for k in ref)
+    ok = all(torch.equal(out[k], ref[k]) and out[k].dtype == ref[k].dtype for k in ref)
     ret[rank] = bool(ok)
     dist.barrier()
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("n_objects", [8, 7])
-def test_run_sharded_world2_gloo(n_objects):
-    world = 2
+@pytest.mark.parametrize("n_objects,world", [(8, 2), (7, 2), (1, 2), (2, 3)])
+def test_run_sharded_gloo(n_objects, world):
     ctx = mp.get_context("spawn")
     ret = ctx.Manager().dict()
     port = _free_port()

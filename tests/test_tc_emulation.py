@@ -34,28 +34,16 @@ def test_bf16x3_split_keeps_the_parity_bound(B, K, T):
 
 @pytest.mark.parametrize("B,K,T", [(2, 50, 30), (3, 50, 20), (1, 16, 100)])
 def test_two_product_mode_keeps_the_parity_bound(B, K, T):
-    """The experimental 'bf16x2' samplers (bf16 hi/lo activations x ONE fp16 weight): what the dropped Ahi.Blo product carried
-    is the weights' bits beyond bf16, and an fp16 weight keeps three of them.  Shortest chains are the worst case (measured
-    0.31-0.46 of the bound at T = 20..30, 0.05 at T = 100, 0.03 at T = 500); with bf16 weights the same two products are 3.7x over."""
+    """The 'f16x2' samplers (fp16 hi/lo activations x ONE fp16 weight): what the dropped Ahi.Blo product carried is the weights'
+    bits beyond the first image, and an fp16 weight keeps three more of them than a bf16 one.  Shortest chains are the worst case
+    (measured ~0.3-0.5 of the bound at T = 20..30, 0.05 at T = 100, 0.03 at T = 500); with bf16 weights the same two products
+    are 3.7x over."""
     sd, data, x0, sn, feat = _case(B, K, T, 50 + B)
     ref, _ = O.pred_func_pc(sd, data, K, T, x0, sn, pts_feat=feat)
     with E.emulated_score(terms="x2"):
         tc, _ = O.pred_func_pc(sd, data, K, T, x0, sn, pts_feat=feat)
     tol = 1e-3 + 5e-5 * ref.abs()
     assert float(((tc - ref).abs() / tol).max()) < 0.7
-
-
-def test_relu_fused_truncating_split_keeps_the_parity_bound(monkeypatch):
-    """The experimental epilogue split (GPB_EPI_RZ_RELU: hi truncated, ReLU inside both conversions) costs nothing in accuracy."""
-    B, K, T = 2, 50, 30
-    sd, data, x0, sn, feat = _case(B, K, T, 50 + B)
-    ref, _ = O.pred_func_pc(sd, data, K, T, x0, sn, pts_feat=feat)
-    tol = 1e-3 + 5e-5 * ref.abs()
-    monkeypatch.setattr(E, "ACT_SPLIT", "rz_relu")
-    for terms in (3, "x2"):
-        with E.emulated_score(terms=terms):
-            tc, _ = O.pred_func_pc(sd, data, K, T, x0, sn, pts_feat=feat)
-        assert float(((tc - ref).abs() / tol).max()) < 0.5
 
 
 def test_two_product_mode_ode():
@@ -80,3 +68,15 @@ def test_split_product_is_exact_to_2_pow_minus_16():
     scale = float((a.abs().double() @ w.abs().double().t()).max())
     assert float((E.mm_split(a, w, 3).double() - exact).abs().max()) <= 2.0 ** -15 * scale
     assert float((E.mm_split(a, w, 1).double() - exact).abs().max()) > 2.0 ** -12 * scale * 0.1
+
+
+def test_f16_activation_split_matches_its_definition():
+    """split_act_f16 = truncation to fp16 + rounded residual: hi is an fp16 value <= a, hi + lo carries >= 20 mantissa bits."""
+    g = torch.Generator().manual_seed(1)
+    a = torch.rand(4096, generator=g) * torch.tensor([1e-6, 1e-3, 1.0, 300.0]).repeat(1024)
+    hi, lo = E.split_act_f16(a)
+    assert torch.equal(hi, hi.to(torch.float16).float()) and bool((hi <= a).all()) and bool((lo >= 0).all())
+    big = a >= 1e-3
+    assert float(((hi + lo - a).abs()[big] / a[big]).max()) <= 2.0 ** -20
+    assert float((hi + lo - a).abs().max()) <= 2.0 ** -20 * 300 + 2.0 ** -25
+    assert float(E.split_act_f16(torch.tensor([1e6, -3.0]))[0][0]) == E.FP16_MAX and float(E.split_act_f16(torch.tensor([-3.0]))[0][0]) == 0.0

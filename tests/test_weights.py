@@ -33,10 +33,11 @@ def test_bn_fold_reproduces_shared_mlp():
 
 def test_two_product_stream_layout():
     """pack_trunk_tc16: every slot is the K-major no-swizzle image [K/8][rows][8] of the fp16-rounded weight block the kernel's
-    descriptors expect (tc_sampler.cu, TcStream<true>); slot 0 is the three-product stream's P1 slot."""
+    descriptors expect (tc_sampler.cu, TcStream<true, .>); slot 0 is the three-product stream's P1 slot; two layouts back to back:
+    A (team of 4: per rank a 128-row and a 64-row head unit) and B (teams of 2 and 1: six 128-row head units)."""
     sd = synth.make_state_dict(3, kappa=0.3)
     st = weights.pack_trunk_tc16(sd)
-    assert st.dtype == torch.int16 and st.numel() * 2 == 33 * 16384
+    assert st.dtype == torch.int16 and st.numel() * 2 == 2 * 33 * 16384
     assert torch.equal(st[:8192], weights.pack_trunk_tc(sd)[:8192])
     slot = lambda i: st[i * 8192:(i + 1) * 8192].view(torch.float16)
     r16 = lambda w: w.to(torch.float16).float()
@@ -53,10 +54,39 @@ def test_two_product_stream_layout():
         for q in range(2):
             w = slot(13 + 6 * r + q).reshape(16, 64, 8).permute(1, 0, 2).reshape(64, 128).float()
             assert torch.equal(w, r16(stacked[192 * r + 128:192 * r + 192, 128 * q:128 * q + 128]))
+    assert torch.equal(st[33 * 8192: 42 * 8192], st[: 9 * 8192])              # layout B starts with the same common slots
+    for u in range(6):
+        for q in range(4):
+            w = slot(33 + 9 + 4 * u + q).reshape(8, 128, 8).permute(1, 0, 2).reshape(128, 64).float()
+            assert torch.equal(w, r16(stacked[128 * u:128 * u + 128, 64 * q:64 * q + 64]))
     sd_big = dict(sd)
     sd_big["pose_score_net.pose_encoder.2.weight"] = sd["pose_score_net.pose_encoder.2.weight"] * 1e6
     with pytest.raises(ValueError):
         weights.pack_trunk_tc16(sd_big)
+
+
+def test_three_product_stream_layouts():
+    """pack_trunk_tc: layout A then layout B, 65 slots each; a head slot = 128-row hi image (8 KiB) | lo image of one 32-input K-chunk."""
+    sd = synth.make_state_dict(4, kappa=0.3)
+    st = weights.pack_trunk_tc(sd)
+    assert st.dtype == torch.int16 and st.numel() * 2 == 2 * 65 * 16384
+    assert torch.equal(st[65 * 8192: 82 * 8192], st[: 17 * 8192])
+    stacked = torch.cat([sd[f"pose_score_net.fusion_tail_{h}.0.weight"].float()[:, 1152:] for h in ("rot_x", "rot_y", "trans")], 0)
+    slot = lambda i: st[i * 8192:(i + 1) * 8192].view(torch.bfloat16)
+    for u in range(6):
+        for kc in range(8):
+            sl = slot(65 + 17 + 8 * u + kc).float()
+            hi = sl[:4096].reshape(4, 128, 8).permute(1, 0, 2).reshape(128, 32)
+            lo = sl[4096:].reshape(4, 128, 8).permute(1, 0, 2).reshape(128, 32)
+            w = stacked[128 * u:128 * u + 128, 32 * kc:32 * kc + 32]
+            wh, wl = weights.split_bf16(w)
+            assert torch.equal(hi, wh.float()) and torch.equal(lo, wl.float())
+    # layout A, rank 1, 64-row unit, slot 2: K-chunks 4 and 5
+    sl = slot(17 + 12 * 1 + 8 + 2).float()
+    for c in range(2):
+        hi = sl[c * 4096: c * 4096 + 2048].reshape(4, 64, 8).permute(1, 0, 2).reshape(64, 32)
+        wh, _ = weights.split_bf16(stacked[192 + 128:192 + 192, 32 * (4 + c):32 * (5 + c)])
+        assert torch.equal(hi, wh.float())
 
 
 def test_trunk_pack_reproduces_score():

@@ -1,5 +1,5 @@
 """Decode the cycle stamps of gpb_sample_pc_tc_dbg: per-phase durations (cycles) of CTA 0, averaged over steps.
-    python tools/tc_phase_times.py [T] [cta,cta,...] [bf16x3|bf16x2]     (bench shape: 64 objects x 50 candidates)"""
+    python tools/tc_phase_times.py [T] [cta,cta,...] [bf16x3|f16x2] [team 0|1|2|4] [objects]     (default: the bench shape, 64 objects x 50 candidates)"""
 import sys
 
 import numpy as np
@@ -10,8 +10,9 @@ from genpose_b200 import lib, ops, synth  # noqa: E402
 
 T = int(sys.argv[1]) if len(sys.argv) > 1 else 100
 CTAS = [int(c) for c in sys.argv[2].split(",")] if len(sys.argv) > 2 else [0]
-W16 = len(sys.argv) > 3 and sys.argv[3] == "bf16x2"
-B, K = 64, 50
+W16 = len(sys.argv) > 3 and sys.argv[3] == "f16x2"
+TEAM = int(sys.argv[4]) if len(sys.argv) > 4 else 0
+B, K = (int(sys.argv[5]) if len(sys.argv) > 5 else 64), 50
 sd = synth.make_state_dict(0, kappa=synth.stable_kappa(T))
 eng = ops.Engine(sd)
 pts = torch.from_numpy(synth.make_clouds(B, 100)).cuda()
@@ -20,6 +21,7 @@ R = B * K
 x0 = torch.from_numpy(synth.make_prior_noise(R, 100)).cuda()
 ob = eng.object_bias(eng.encode(pts))
 L = lib.load()
+lib.check(L.gpb_set_tc_team(TEAM), "set_tc_team")
 ws = torch.empty(L.gpb_sampler_workspace_bytes(R, T), dtype=torch.uint8, device="cuda")
 ts = ops.time_grid(T, "cuda")
 out = torch.empty(R, 9, device="cuda")
