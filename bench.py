@@ -199,9 +199,8 @@ def run_ode_line(args, rank, world, local_rank):
     R = B_PER_GPU * K_CAND
     torch.manual_seed(rank)
     x0_dev = ve_prior((R, 9), T=T0).to(dev).contiguous()
-    precision = "bf16x3" if args.precision == "bf16x3" or (args.precision == "auto" and eng.tc_supported(R, K_CAND)) else "fp32"
-    if args.precision == "f16x2":
-        precision = "f16x2"
+    from genpose_b200 import ops
+    precision = (ops.AUTO_TC_PRECISION if eng.tc_supported(R, K_CAND) else "fp32") if args.precision == "auto" else args.precision
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
     out_host = torch.empty(B_PER_GPU, K_CAND, 9, dtype=torch.float64).pin_memory()
     stats_box = {}
@@ -264,6 +263,87 @@ def run_ode_line(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+def profiled_traffic(kernel_substr, precision, rows, steps):
+    """roofline.traffic = dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel from the newest
+    `ncu --set full` summary committed under profiles/ (tools/summarize_ncu.py; the summary's companion .meta.json names the shape
+    and the commit it was captured at).  None when no capture of this kernel at this shape exists."""
+    import glob
+    best = None
+    for meta_path in glob.glob(os.path.join(ROOT, "profiles", "*_ncu_*.meta.json")):
+        try:
+            meta = json.load(open(meta_path))
+            if kernel_substr not in meta.get("kernel", "") or meta.get("precision") != precision or meta.get("rows") != rows \
+                    or meta.get("steps") != steps:
+                continue
+            if best is None or meta.get("order", 0) > best.get("order", 0):
+                best = meta
+        except Exception:
+            continue
+    if best is None:
+        return None, None
+    return best.get("dram_bytes"), {k: best.get(k) for k in ("file", "commit", "kernel", "tensor_pipe_active_pct", "duration_ms")}
+
+
+def gpu_torch_baseline(sd, clouds_dev, x0_dev, K, T, steps, seed=0):
+    """Context, never the target: the reference's algorithm as plain PyTorch on THIS GPU — the oracle port with its
+    tensors on cuda (cuBLAS / cuDNN-free eager ops, TF32 off), the reference's own compiled pointnet2 CUDA kernels (oracle/_ref, built
+    from the reference's sources) for furthest-point sampling and ball query — on the same batch.  Outside the product path."""
+    from oracle import build_ref
+    from oracle import genpose_oracle as O
+    ref_ext = build_ref.load_ref()
+    if ref_ext is None:
+        return {"unavailable": "oracle/_ref/pointnet2_cuda_ref.so not built (needs /root/reference at build time)"}
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    dev = clouds_dev.device
+    sd_dev = {k: v.to(dev) for k, v in sd.items()}
+    fps_cpu, bq_cpu = O.furthest_point_sample, O.ball_query
+
+    def fps_gpu(xyz, npoint):
+        xyz = xyz.float().contiguous()
+        idx = torch.zeros(xyz.shape[0], npoint, dtype=torch.int32, device=xyz.device)
+        temp = torch.full(xyz.shape[:2], 1e10, dtype=torch.float32, device=xyz.device)
+        ref_ext.furthest_point_sampling_wrapper(xyz.shape[0], xyz.shape[1], npoint, xyz, temp, idx)
+        return idx
+
+    def bq_gpu(radius, nsample, xyz, new_xyz):
+        xyz, new_xyz = xyz.float().contiguous(), new_xyz.float().contiguous()
+        idx = torch.zeros(xyz.shape[0], new_xyz.shape[1], nsample, dtype=torch.int32, device=xyz.device)
+        ref_ext.ball_query_wrapper(xyz.shape[0], xyz.shape[1], new_xyz.shape[1], radius, nsample, new_xyz, xyz, idx)
+        return idx
+
+    B = clouds_dev.shape[0]
+    R = B * K
+    center = clouds_dev.mean(dim=1)
+    noise = torch.randn(T, 2, R, 9, device=dev, generator=torch.Generator(device=dev).manual_seed(seed))
+    O.furthest_point_sample, O.ball_query = fps_gpu, bq_gpu
+    try:
+        def one():
+            feat = O.encode(sd_dev, clouds_dev)
+            rep = feat.unsqueeze(1).repeat(1, K, 1).view(R, -1)
+            cen = center.unsqueeze(1).repeat(1, K, 1).view(R, -1)
+            return O.pc_sampler(sd_dev, rep, cen, x0_dev, noise, T)
+        one()
+        torch.cuda.synchronize()
+        ms = []
+        for _ in range(steps):
+            a, b = torch.cuda.Event(True), torch.cuda.Event(True)
+            a.record()
+            pose = one()
+            b.record()
+            torch.cuda.synchronize()
+            ms.append(a.elapsed_time(b))
+        ok = bool(torch.isfinite(pose).all())
+    except Exception as e:  # noqa: BLE001
+        return {"unavailable": f"{type(e).__name__}: {str(e)[:200]}"}
+    finally:
+        O.furthest_point_sample, O.ball_query = fps_cpu, bq_cpu
+    t = float(np.mean(ms))
+    return {"value": R / (t / 1000.0), "unit": UNIT, "ms_per_step": t, "steps": steps, "finite": ok,
+            "what": "oracle port of the reference on torch CUDA eager fp32 (TF32 off) + the reference's own pointnet2 CUDA kernels "
+                    "(oracle/_ref) for FPS / ball query; same 64-object batch, device-resident inputs; context only"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -273,12 +353,13 @@ def main():
     ap.add_argument("--config", type=int, default=2, choices=[2, 3])
     ap.add_argument("--ref-objects", type=int, default=64, help="objects per step of the CPU reference arm / cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="headline + e2e only (no config-3 / ODE / saturating / GPU-torch keys)")
     ap.add_argument("--sampler", default="pc", choices=["pc", "ode"],
                     help="pc = BASELINE.json's metric (T=500 predictor-corrector steps, the default and the headline); ode = the "
-                         "reference's shipped recipe (scripts/eval_single.sh: RK45 probability-flow ODE, T0=0.55) as an extra line")
+                         "reference's shipped recipe (scripts/eval_single.sh: RK45 probability-flow ODE, T0=0.55) as its own line")
     ap.add_argument("--precision", default="auto", choices=["auto", "bf16x3", "fp32", "f16x2"],
-                    help="dense layers of the sampler: tcgen05 bf16x3 (auto when the shape allows) or the fp32 FFMA parity kernel; "
-                         "f16x2 = EXPERIMENTAL two-product tensor-core kernel (fp16 weight images), never chosen by auto")
+                    help="dense layers of the sampler: tcgen05 f16x2 (auto when the shape allows: fp16 hi/lo activations x one fp16 weight "
+                         "image, two products), tcgen05 bf16x3 (three products) or the fp32 FFMA parity kernel")
     args = ap.parse_args()
 
     from genpose_b200 import distributed as D
@@ -291,12 +372,10 @@ def main():
     import torch.distributed as dist
     from genpose_b200 import lib, ops, synth
     from genpose_b200.pipeline import PosePipeline
+    from genpose_b200.sde import init_sde
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py --impl ours needs a CUDA device (there is no CPU fallback)")
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local_rank)
     rank, world, local_rank = D.init_from_env("nccl")
     dev = torch.device("cuda", local_rank)
     peaks = load_peaks()
@@ -306,51 +385,66 @@ def main():
 
     # ---- synthetic workload: each rank owns its own 64 objects (weak scaling) ------------------------------
     seed = 100 + rank
+    extras = not args.no_extras and world == 1                 # the extra keys are single-GPU measurements
     sd = synth.make_state_dict(0, kappa=-0.3)
-    esd = synth.make_state_dict(100, kappa=-0.3) if args.config == 3 else None
-    pipe = PosePipeline(sd, esd, sampler="pc", sampling_steps=T_STEPS, noise_mode="philox", precision=args.precision)
-    eng = pipe.score_agent.net.engine
-    eeng = pipe.energy_agent.net.engine if esd is not None else None
+    esd = synth.make_state_dict(100, kappa=-0.3) if (args.config == 3 or extras) else None
+    pipe2 = PosePipeline(sd, None, sampler="pc", sampling_steps=T_STEPS, noise_mode="philox", precision=args.precision)
+    pipe3 = PosePipeline(sd, esd, sampler="pc", sampling_steps=T_STEPS, noise_mode="philox", precision=args.precision) if esd is not None else None
+    pipe = pipe3 if args.config == 3 else pipe2
+    eng = pipe2.score_agent.net.engine
+    eeng = pipe3.energy_agent.net.engine if pipe3 is not None else None
     clouds_host = torch.from_numpy(synth.make_clouds(B_PER_GPU, seed)).pin_memory()
     clouds_dev = clouds_host.to(dev)
     center_dev = clouds_dev.mean(dim=1).contiguous()
     R = B_PER_GPU * K_CAND
-    use_tc = args.precision in ("bf16x3", "f16x2") or (args.precision == "auto" and eng.tc_supported(R, K_CAND))
-    precision = args.precision if args.precision in ("bf16x3", "f16x2") else ("bf16x3" if use_tc else "fp32")
+    if args.precision == "auto":
+        precision = ops.AUTO_TC_PRECISION if eng.tc_supported(R, K_CAND) else "fp32"
+    else:
+        precision = args.precision
+    use_tc = precision != "fp32"
     tc_products = 2 if precision == "f16x2" else 3
     x0_dev = torch.from_numpy(synth.make_prior_noise(R, seed)).to(dev)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
     gathered = torch.empty(world * B_PER_GPU, K_CAND, 9, device=dev) if world > 1 else None
     out_host = torch.empty(B_PER_GPU, K_CAND, 9).pin_memory()
+    side = torch.cuda.Stream()
 
-    side = torch.cuda.Stream() if eeng is not None else None
-
-    def step_resident(i, ev=None):
+    def step_resident(i, ev=None, config=args.config, ev3=None):
         feat = eng.encode(clouds_dev)
         ob = eng.object_bias(feat)
         if ev:
             ev[0].record()
+        if config == 3:
+            enc_done = torch.cuda.Event()
+            enc_done.record()
         pose = eng.sample_pc(ob, center_dev, x0_dev, K_CAND, T_STEPS, seed=i, precision=precision)
         if ev:
             ev[1].record()
         res = pose
-        if eeng is not None:
-            # the energy net's own encoder pass is launched once the sampler is in flight and runs beside it, on the 48 SMs the
-            # sampler's 100 CTAs leave free (the resident clouds are long complete), like PosePipeline.run
+        if config == 3:
+            side.wait_event(enc_done)                                       # behind the score net's encoder, beside the sampler
+            # the energy net's own encoder pass runs on a side stream beside the sampler (the resident clouds are long complete),
+            # like PosePipeline.run; then energy -> rank -> pool
             with torch.cuda.stream(side):
                 eob = eeng.object_bias(eeng.encode(clouds_dev))
             eob.record_stream(torch.cuda.current_stream())
             torch.cuda.current_stream().wait_stream(side)
+            if ev3:
+                ev3[0].record()
             en = eeng.energy(eob, center_dev, pose, K_CAND, 1e-5)
+            if ev3:
+                ev3[1].record()
             _, _, res = ops.rank_pool(pose.view(B_PER_GPU, K_CAND, 9), en.view(B_PER_GPU, K_CAND, 2))
+            if ev3:
+                ev3[2].record()
         if world > 1:
             dist.all_gather_into_tensor(gathered, pose.view(B_PER_GPU, K_CAND, 9))
         return res
 
-    def step_e2e(i):
+    def step_e2e(i, the_pipe=None):
         pts = clouds_host.to(dev, non_blocking=True)                        # H2D from pinned memory
         data = PosePipeline.make_batch(pts)                                 # runner's batch dict (evaluation_single.py:394-403)
-        out = pipe.run(data, repeat_num=K_CAND)                             # PoseNet.pred_func [+ get_energy + rank/pool]
+        out = (the_pipe or pipe).run(data, repeat_num=K_CAND)               # PoseNet.pred_func [+ get_energy + rank/pool]
         pose = out["pred_pose"]
         if world > 1:
             dist.all_gather_into_tensor(gathered, pose.contiguous())
@@ -358,61 +452,56 @@ def main():
         torch.cuda.current_stream().synchronize()
         return out_host
 
-    def pipelined_resident(n):
-        """The same K steps as a stream of batches: batch i+1's encoder is launched on a side stream as soon as batch i's
-        sampler is in flight and runs beside it (the sampler holds 100 of the 148 SMs).  Reported as the extra key
-        `pipelined` only; `value` stays the strictly sequential number.  The L2 flush between iterations is inside the
-        bracket here (its ~0.1 ms per step is counted)."""
-        ps = torch.cuda.Stream()
-        main = torch.cuda.current_stream()
-        with torch.cuda.stream(ps):
-            ob_next = eng.object_bias(eng.encode(clouds_dev))
+    def pipelined_stream(n):
+        """The same K steps as a stream of batches through PosePipeline.run_stream itself: batch i+1's encoder is launched on a side
+        stream before batch i's sampler is enqueued and runs beside it.  Reported as the extra key `pipelined` only; `value` stays
+        the strictly sequential number.  The L2 flush between iterations is inside the bracket here (its ~0.1 ms per step is counted)."""
+        def batches():
+            for i in range(n):
+                flush.fill_(i & 0xFF)
+                yield {"pts": clouds_dev, "pts_center": center_dev}
         a, b = torch.cuda.Event(True), torch.cuda.Event(True)
         torch.cuda.synchronize()
         a.record()
-        for i in range(n):
-            main.wait_stream(ps)
-            ob = ob_next
-            flush.fill_(i & 0xFF)
-            pose = eng.sample_pc(ob, center_dev, x0_dev, K_CAND, T_STEPS, seed=i, precision=precision)
+        for pose in pipe2.run_stream(batches(), repeat_num=K_CAND):
             if world > 1:
-                dist.all_gather_into_tensor(gathered, pose.view(B_PER_GPU, K_CAND, 9))
-            if i + 1 < n:
-                with torch.cuda.stream(ps):
-                    ob_next = eng.object_bias(eng.encode(clouds_dev))
-                ob_next.record_stream(main)
+                dist.all_gather_into_tensor(gathered, pose.contiguous())
         b.record()
         torch.cuda.synchronize()
         return a.elapsed_time(b)
 
     def saturating_sampler(n):
-        """the tensor-roofline fraction is also reported at the largest batch the tensor-core sampler holds
-        (every co-resident 4-CTA cluster owns a 128-row tile), sampler launch alone.  Extra key `roofline.saturating_batch`."""
-        b_sat = int(lib.load().gpb_sampler_tc_max_rows(K_CAND)) // K_CAND
-        if b_sat <= B_PER_GPU:
-            return None
-        r_sat = b_sat * K_CAND
-        clouds = torch.from_numpy(synth.make_clouds(b_sat, seed + 1000)).to(dev)
-        ob = eng.object_bias(eng.encode(clouds))
-        cen = clouds.mean(dim=1).contiguous()
-        x0 = torch.from_numpy(synth.make_prior_noise(r_sat, seed + 1000)).to(dev)
-        ms = []
-        for i in range(3 + n):
-            flush.fill_(i & 0xFF)
-            a, b = torch.cuda.Event(True), torch.cuda.Event(True)
-            torch.cuda.synchronize()
-            a.record()
-            eng.sample_pc(ob, cen, x0, K_CAND, T_STEPS, seed=i, precision=precision)
-            b.record()
-            torch.cuda.synchronize()
-            if i >= 3:
-                ms.append(a.elapsed_time(b))
-        k = float(np.mean(ms))
-        tf = r_sat * T_STEPS * FLOP_PER_CAND_STEP / (k / 1000.0) / 1e12
-        return {"objects": b_sat, "rows": r_sat, "kernel_ms": k, "achieved": tf, "frac": tf / peaks["bf16_tflops_sustained"],
-                "candidates_per_s_sampler_only": r_sat / (k / 1000.0)}
+        """the tensor-roofline fraction is also reported at a SATURATING batch — one 128-row tile on every SM (the
+        tensor-core sampler's team of 1; 148 tiles = 378 objects x 50 candidates on a B200), sampler launch alone — and at the
+        reference's own evaluation batch (scripts/eval_single.sh:7, 256 objects).  Extra key `roofline.saturating_batch`."""
+        out = {}
+        b_max = int(lib.load().gpb_sampler_tc_max_rows(K_CAND)) // K_CAND
+        for tag, b_sat in (("eval_single_batch_256", 256), ("one_tile_per_sm", b_max)):
+            if b_sat <= B_PER_GPU or b_sat > b_max:
+                continue
+            r_sat = b_sat * K_CAND
+            clouds = torch.from_numpy(synth.make_clouds(b_sat, seed + 1000)).to(dev)
+            ob = eng.object_bias(eng.encode(clouds))
+            cen = clouds.mean(dim=1).contiguous()
+            x0 = torch.from_numpy(synth.make_prior_noise(r_sat, seed + 1000)).to(dev)
+            ms = []
+            for i in range(3 + n):
+                flush.fill_(i & 0xFF)
+                a, b = torch.cuda.Event(True), torch.cuda.Event(True)
+                torch.cuda.synchronize()
+                a.record()
+                eng.sample_pc(ob, cen, x0, K_CAND, T_STEPS, seed=i, precision=precision)
+                b.record()
+                torch.cuda.synchronize()
+                if i >= 3:
+                    ms.append(a.elapsed_time(b))
+            k = float(np.mean(ms))
+            tf = r_sat * T_STEPS * FLOP_PER_CAND_STEP / (k / 1000.0) / 1e12
+            out[tag] = {"objects": b_sat, "rows": r_sat, "tiles": (r_sat + 127) // 128, "kernel_ms": k, "achieved": tf,
+                        "frac": tf / peaks["bf16_tflops_sustained"], "candidates_per_s_sampler_only": r_sat / (k / 1000.0)}
+        return out or None
 
-    def timed(fn, n, with_kernel_events=False):
+    def timed(fn, n, with_kernel_events=False, **kw):
         per_step, kernel_ms = [], []
         for i in range(n):
             flush.fill_(i & 0xFF)                                           # evict L2 between timed iterations
@@ -420,7 +509,7 @@ def main():
             kev = (torch.cuda.Event(True), torch.cuda.Event(True)) if with_kernel_events else None
             torch.cuda.synchronize()
             a.record()
-            fn(i, kev) if with_kernel_events else fn(i)
+            fn(i, kev, **kw) if with_kernel_events else fn(i, **kw)
             b.record()
             torch.cuda.synchronize()
             per_step.append(a.elapsed_time(b))
@@ -449,11 +538,9 @@ def main():
     launches = lib.launch_count() - launches0
     per_step_e2e, _ = timed(step_e2e, args.steps)
     sync_all()
-    pipelined_ms = pipelined_resident(args.steps) if args.config == 2 else None
-    sync_all()
-    saturating = saturating_sampler(min(args.steps, 5)) if (args.config == 2 and use_tc and rank == 0) else None
-    sync_all()
     clock_info = clocks.stop() if rank == 0 else None
+    pipelined_ms = pipelined_stream(args.steps) if args.config == 2 else None
+    sync_all()
 
     total_ms = torch.tensor([sum(per_step), sum(per_step_e2e), pipelined_ms or 0.0], device=dev, dtype=torch.float64)
     if world > 1:
@@ -463,40 +550,109 @@ def main():
     value = cands / (total_ms[0] / 1000.0)
     e2e_value = cands / (total_ms[1] / 1000.0)
 
+    # ---- extra keys (single GPU): config 3, the shipped ODE recipe, saturating batches, the GPU-torch context baseline ----
+    extra = {}
+    if extras and rank == 0:
+        n_x = max(3, min(args.steps, 5))
+        if args.config == 2:
+            for i in range(3):
+                step_resident(i, config=3)
+                step_e2e(i, the_pipe=pipe3)
+            ms3, kms = [], {"gpb_energy": [], "rank_pool": []}
+            for i in range(n_x):
+                flush.fill_(i & 0xFF)
+                a, b = torch.cuda.Event(True), torch.cuda.Event(True)
+                ev3 = [torch.cuda.Event(True) for _ in range(3)]
+                torch.cuda.synchronize()
+                a.record()
+                step_resident(i, config=3, ev3=ev3)
+                b.record()
+                torch.cuda.synchronize()
+                ms3.append(a.elapsed_time(b))
+                kms["gpb_energy"].append(ev3[0].elapsed_time(ev3[1]))
+                kms["rank_pool"].append(ev3[1].elapsed_time(ev3[2]))
+            ms3e, _ = timed(step_e2e, n_x, the_pipe=pipe3)
+            t3, t3e = float(np.mean(ms3)), float(np.mean(ms3e))
+            extra["config3"] = {
+                "workload": "BASELINE configs[2]: config 2 + energy network (own encoder pass) + rank + top-60% mean pool -> [B,4,4]",
+                "value": R / (t3 / 1000.0), "unit": UNIT, "ms_per_step": t3, "steps": n_x,
+                "e2e": {"value": R / (t3e / 1000.0), "unit": UNIT, "ms_per_step": t3e,
+                        "api": "PoseNet.pred_func + PoseNet.get_energy + rank_pool (PosePipeline.run), host buffers"},
+                "kernel_ms": {k: float(np.mean(v)) for k, v in kms.items()},
+                "note": "the energy net's encoder runs on a side stream beside the sampler; gpb_energy = trunk_eval at t = 1e-5 "
+                        "(3200 rows x 0.5335 MFLOP + object bias), rank_pool = sort + quaternion eigen-mean per object: both latency-bound, "
+                        "microseconds against the sampler's milliseconds"}
+        # the reference's shipped recipe on the same batch (scripts/eval_single.sh: ode, T0 = 0.55)
+        ve_prior = init_sde("ve")[0]
+        torch.manual_seed(rank)
+        x0_ode = ve_prior((R, 9), T=0.55).to(dev).contiguous()
+        stats_box = {}
+
+        def ode_step(i, ev=None):
+            ob = eng.object_bias(eng.encode(clouds_dev))
+            if ev:
+                ev[0].record()
+            pose, stats_box["s"] = eng.sample_ode(ob, center_dev, x0_ode, K_CAND, T0=0.55, precision=precision)
+            if ev:
+                ev[1].record()
+            return pose
+        for i in range(3):
+            ode_step(i)
+        ms_o, k_o = timed(ode_step, n_x, with_kernel_events=True)
+        st = stats_box["s"].cpu().tolist()
+        t_o, k_o = float(np.mean(ms_o)), float(np.mean(k_o))
+        tf_o = R * st[0] * FLOP_PER_CAND_STEP / (k_o / 1000.0) / 1e12
+        extra["ode_recipe"] = {
+            "workload": "scripts/eval_single.sh recipe on the same 64-object batch: cond_ode_sampler, T0=0.55, rtol=atol=1e-5, K=50",
+            "value": R / (t_o / 1000.0), "unit": UNIT, "ms_per_step": t_o, "steps": n_x, "nfev": st[0], "accepted": st[1], "rejected": st[2],
+            "roofline": {"kernel": "tc_ode_sampler_kernel" if use_tc else "ode_sampler_kernel", "bound": "tensor", "kernel_ms": k_o,
+                         "achieved": tf_o, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": tf_o / peaks["bf16_tflops_sustained"],
+                         "algorithmic_flop_per_launch": R * st[0] * FLOP_PER_CAND_STEP,
+                         "note": "nfev x rows x 0.5335 MFLOP / kernel time; between evaluation groups the float64 RK45 controller runs with the tensor pipe idle"}}
+        if use_tc:
+            sat = saturating_sampler(n_x)
+            if sat:
+                extra["saturating_batch"] = sat
+        extra["gpu_torch_baseline"] = gpu_torch_baseline(sd, clouds_dev, x0_dev, K_CAND, T_STEPS, steps=2)
+    sync_all()
+
     if rank == 0:
         k_ms = float(np.mean(kernel_ms))
         ach = R * T_STEPS * FLOP_PER_CAND_STEP / (k_ms / 1000.0) / 1e12
         peak = peaks["bf16_tflops_sustained"]
+        kernel_name = ("tc_pc_sampler_kernel" if use_tc else "pc_sampler_kernel")
+        traffic, traffic_src = profiled_traffic(kernel_name, precision, R, T_STEPS) if use_tc else (None, None)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": total_ms[0] / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": ("bf16x3 (bf16 tensor-core operands, error-compensated split, fp32 accumulate)" if precision == "bf16x3" else
-                      "f16x2 (bf16 hi/lo activations x fp16 weights, fp32 accumulate; experimental)") if use_tc else "f32",
+            "dtype": {"f16x2": "f16x2 (fp16 hi/lo activations x one fp16 weight image on tcgen05, two products per K-step, fp32 accumulate in TMEM)",
+                      "bf16x3": "bf16x3 (bf16 hi/lo operands on tcgen05, error-compensated three-product split, fp32 accumulate in TMEM)",
+                      "fp32": "f32"}[precision],
             "data": "synthetic", "config": workload_config(args, world),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(clouds_host.numel() * 4 + R * 9 * 4),
                     "d2h_bytes_per_step": int(out_host.numel() * 4), "ms_per_step": total_ms[1] / args.steps,
                     "api": "PoseNet.pred_func(data, repeat_num=50)" + (" + PoseNet.get_energy + rank_pool" if args.config == 3 else "")},
             "gpu_launches": int(launches),
-            "roofline": {"kernel": (("tc_pc_sampler_kernel<w16>" if precision == "f16x2" else "tc_pc_sampler_kernel") if use_tc
-                                    else "pc_sampler_kernel") + " (+ time_bias_table_kernel)",
+            "roofline": {"kernel": kernel_name + (f" [{precision}, tile team of 4 CTAs]" if use_tc else "") + " (+ time_bias_table_kernel)",
                          "bound": "tensor", "achieved": ach, "peak": peak,
                          "unit": "TFLOP/s", "frac": ach / peak,
-                         # dram__bytes_read.sum + dram__bytes_write.sum of one 3200-row x 500-step launch, `ncu --set full`
-                         # (profiles/r1m_ncu_tc_sampler.csv: 3,025,920 read + 768 written); only meaningful for that shape and kernel
-                         "traffic": 3026688 if (precision == "bf16x3" and R == 3200 and T_STEPS == 500) else None, "kernel_ms": k_ms,
+                         "traffic": traffic, "traffic_source": traffic_src, "kernel_ms": k_ms,
                          "peak_kind": "bf16_tflops_sustained, " + peaks["source"],
-                         "note": (f"tcgen05 {precision}: every algorithmic MAC costs {tc_products} tensor-core MACs, so the tensor pipe does {tc_products}x `achieved`"
+                         "note": (f"tcgen05 {precision}: every algorithmic MAC costs {tc_products} tensor-core MACs, so the tensor pipe does {tc_products}x `achieved`; "
+                                  "at 3200 rows (25 tiles) a step is one dependent chain of 3 layers + team exchange + one grid-wide norm, so the "
+                                  "fraction is latency-bound here; roofline.saturating_batch is the same kernel with every SM holding a tile"
                                   if use_tc else "fp32 FFMA parity path: the tensor pipe is idle; fraction of the fp32-FFMA peak "
                                   "(148 SM x 128 lanes x 2 x clk) is reported as frac_ffma"),
                          "algorithmic_flop_per_launch": R * T_STEPS * FLOP_PER_CAND_STEP},
             "clocks": clock_info,
         }
-        if saturating is not None:
-            line["roofline"]["saturating_batch"] = saturating
+        if "saturating_batch" in extra:
+            line["roofline"]["saturating_batch"] = extra.pop("saturating_batch")
         if pipelined_ms is not None:
             line["pipelined"] = {"value": cands / (total_ms[2] / 1000.0), "unit": UNIT, "ms_per_step": total_ms[2] / args.steps,
-                                 "note": "extra, not the headline: the same K steps as a stream of batches, batch i+1's encoder on a side "
-                                         "stream beside batch i's sampler; the L2 flush between iterations is inside this bracket"}
+                                 "note": "extra, not the headline: the same K steps as a stream of batches through PosePipeline.run_stream, batch "
+                                         "i+1's encoder on a side stream beside batch i's sampler; the L2 flush between iterations is inside this bracket"}
+        line.update(extra)
         if clock_info and clock_info.get("sm_mhz"):
             ffma_peak = 148 * 128 * 2 * clock_info["sm_mhz"] * 1e6 / 1e12
             line["roofline"]["frac_ffma"] = ach / ffma_peak

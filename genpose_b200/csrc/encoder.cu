@@ -14,6 +14,8 @@
 //                      ABSOLUTE xyz, max over points (atomicMax on non-negative floats).
 //
 // BatchNorm (eval) is folded into W and b on the host (genpose_b200/weights.py); all math is fp32 FFMA.
+#include <mutex>
+
 #include "common.cuh"
 
 namespace gpb {
@@ -118,6 +120,34 @@ __device__ __forceinline__ void fps_level(const float *sx, const float *sy, cons
         }
     }
     __syncthreads();
+}
+
+// The same chain as two kernels, so that levels 2 and 3 (218 of the 896 dependent rounds... 384 rounds) can run on a side stream
+// BESIDE level 1's set abstraction, which needs new_xyz1 only: fps_l1_kernel = level 1, fps_l23_kernel = levels 2 and 3 from new_xyz1.
+__global__ void __launch_bounds__(kFps3Threads)
+fps_l1_kernel(const float *__restrict__ pts /* [B,1024,3] */, float *__restrict__ nx1, int *__restrict__ idx1) {
+    __shared__ float s0[3][1024], s1[3][512];
+    __shared__ unsigned long long warp_best[2][8];
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const float *p = pts + (size_t)b * 1024 * 3;
+    for (int i = tid; i < 1024 * 3; i += kFps3Threads) s0[i % 3][i / 3] = p[i];
+    __syncthreads();
+    fps_level<1024, 512>(s0[0], s0[1], s0[2], s1[0], s1[1], s1[2], idx1 ? idx1 + (size_t)b * 512 : nullptr, warp_best);
+    for (int i = tid; i < 512 * 3; i += kFps3Threads) nx1[(size_t)b * 512 * 3 + i] = s1[i % 3][i / 3];
+}
+__global__ void __launch_bounds__(kFps3Threads)
+fps_l23_kernel(const float *__restrict__ nx1 /* [B,512,3] */, float *__restrict__ nx2, float *__restrict__ nx3, int *__restrict__ idx2,
+               int *__restrict__ idx3) {
+    __shared__ float s1[3][512], s2[3][256], s3[3][128];
+    __shared__ unsigned long long warp_best[2][8];
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const float *p = nx1 + (size_t)b * 512 * 3;
+    for (int i = tid; i < 512 * 3; i += kFps3Threads) s1[i % 3][i / 3] = p[i];
+    __syncthreads();
+    fps_level<512, 256>(s1[0], s1[1], s1[2], s2[0], s2[1], s2[2], idx2 ? idx2 + (size_t)b * 256 : nullptr, warp_best);
+    fps_level<256, 128>(s2[0], s2[1], s2[2], s3[0], s3[1], s3[2], idx3 ? idx3 + (size_t)b * 128 : nullptr, warp_best);
+    for (int i = tid; i < 256 * 3; i += kFps3Threads) nx2[(size_t)b * 256 * 3 + i] = s2[i % 3][i / 3];
+    for (int i = tid; i < 128 * 3; i += kFps3Threads) nx3[(size_t)b * 128 * 3 + i] = s3[i % 3][i / 3];
 }
 
 __global__ void __launch_bounds__(kFps3Threads)
@@ -588,6 +618,26 @@ constexpr size_t kEncTcL2Const = 2048, kEncTcL2Img0 = (64 * 64 + 64 * 128) * 4, 
 constexpr size_t kEncTcGaOff = kEncTcL2Off + 2 * kEncTcL2Const + kEncTcL2Img0 + kEncTcL2Img1;   // GroupAll block (ga_tc.cu) last
 }  // namespace gpb
 
+// A side stream per device for the work that may run beside the caller's stream inside one encoder pass (fork / join with events
+// created per call, so concurrent callers on different streams do not share state beyond the side stream's ordering).
+static cudaStream_t encoder_side_stream() {
+    static std::mutex mu;
+    static cudaStream_t side[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    std::lock_guard<std::mutex> lock(mu);
+    if (!side[dev]) {
+        // highest priority: its few small CTAs (B x 256 threads) must be placed ahead of the set-abstraction grids they run beside
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        if (cudaStreamCreateWithPriority(&side[dev], cudaStreamNonBlocking, hi) != cudaSuccess) {
+            cudaGetLastError();
+            side[dev] = nullptr;
+        }
+    }
+    return side[dev];
+}
+
 static int encode_impl(const float *pts, int B, const float *enc_w, const uint8_t *enc_tc, float *pts_feat, void *workspace,
                        size_t workspace_bytes, int *fps_idx1, int *fps_idx2, int *fps_idx3, void *stream) {
     GPB_REQUIRE(B >= 0, "encode: B < 0");
@@ -603,8 +653,29 @@ static int encode_impl(const float *pts, int B, const float *enc_w, const uint8_
     cudaStream_t st = (cudaStream_t)stream;
     int rc;
 
-    fps3_kernel<<<B, kFps3Threads, 0, st>>>(pts, w.nx1, w.nx2, w.nx3, fps_idx1, fps_idx2, fps_idx3);
-    GPB_LAUNCHED();
+    // Furthest-point sampling is 896 dependent arg-max rounds on B CTAs: level 1 (512 rounds) first, then levels 2 and 3 (384 rounds)
+    // on a side stream beside level 1's set abstraction, which only needs new_xyz1; joined in front of level 2.
+    cudaStream_t side = encoder_side_stream();
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    if (side && (cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+                 cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming) != cudaSuccess)) {
+        cudaGetLastError();
+        if (ev_fork) cudaEventDestroy(ev_fork);
+        ev_fork = ev_join = nullptr;
+        side = nullptr;
+    }
+    if (side) {
+        fps_l1_kernel<<<B, kFps3Threads, 0, st>>>(pts, w.nx1, fps_idx1);
+        GPB_LAUNCHED();
+        GPB_CUDA(cudaEventRecord(ev_fork, st));
+        GPB_CUDA(cudaStreamWaitEvent(side, ev_fork, 0));
+        fps_l23_kernel<<<B, kFps3Threads, 0, side>>>(w.nx1, w.nx2, w.nx3, fps_idx2, fps_idx3);
+        GPB_LAUNCHED();
+        GPB_CUDA(cudaEventRecord(ev_join, side));
+    } else {
+        fps3_kernel<<<B, kFps3Threads, 0, st>>>(pts, w.nx1, w.nx2, w.nx3, fps_idx1, fps_idx2, fps_idx3);
+        GPB_LAUNCHED();
+    }
 
     // level 1 (no input features)
     if ((rc = launch_sa<0, 0>(pts, w.nx1, nullptr, enc_w, w.feat1, B, st))) return rc;
@@ -615,6 +686,11 @@ static int encode_impl(const float *pts, int B, const float *enc_w, const uint8_
         if ((rc = launch_sa<0, 1>(pts, w.nx1, nullptr, enc_w, w.feat1, B, st))) return rc;
     }
 
+    if (side) {   // new_xyz2 / new_xyz3 (and the caller's fps_idx2 / fps_idx3) are complete from here on
+        GPB_CUDA(cudaStreamWaitEvent(st, ev_join, 0));
+        cudaEventDestroy(ev_fork);          // released by the runtime once the recorded work has completed
+        cudaEventDestroy(ev_join);
+    }
     // level 2: U = W1_feat . feat1 per source point, then the grouped part
     {
         constexpr MlpSpec m0 = enc_spec(1, 0), m1 = enc_spec(1, 1);

@@ -118,6 +118,73 @@ static __constant__ double kRkA[6][5] = {
 static __constant__ double kRkB[6] = {35.0 / 384, 0, 500.0 / 1113, 125.0 / 192, -2187.0 / 6784, 11.0 / 84};
 static __constant__ double kRkE[7] = {-71.0 / 57600, 0, 71.0 / 16695, -71.0 / 1920, 17253.0 / 339200, -22.0 / 525, 1.0 / 40};
 
+// RK45's dense-output polynomial (scipy/integrate/_ivp/rk.py, RK45.P; RkDenseOutput._call_impl): y(t) = y_old + h * K^T . P . (x, x^2, x^3, x^4),
+// x = (t - t_old) / h, K = the seven stage derivatives of the accepted step
+static __constant__ double kRkP[7][4] = {
+    {1.0, -8048581381.0 / 2820520608.0, 8663915743.0 / 2820520608.0, -12715105075.0 / 11282082432.0},
+    {0.0, 0.0, 0.0, 0.0},
+    {0.0, 131558114200.0 / 32700410799.0, -68118460800.0 / 10900136933.0, 87487479700.0 / 32700410799.0},
+    {0.0, -1754552775.0 / 470086768.0, 14199869525.0 / 1410260304.0, -10690763975.0 / 1880347072.0},
+    {0.0, 127303824393.0 / 49829197408.0, -318862633887.0 / 49829197408.0, 701980252875.0 / 199316789632.0},
+    {0.0, -282668133.0 / 205662961.0, 2019193451.0 / 616988883.0, -1453857185.0 / 822651844.0},
+    {0.0, 40617522.0 / 29380423.0, -110615467.0 / 29380423.0, 69997945.0 / 29380423.0}};
+
+// Trajectory output of the ODE samplers — the reference's `xs` (samplers.py:206, :220-224).  All zero when not requested.
+//   t_eval == NULL : out [cap][R][9], state 0 = the start, state i = the solver's i-th ACCEPTED step (solve_ivp's res.y when
+//                    t_eval is None); states beyond cap are dropped (stats[1] tells how many exist)
+//   t_eval != NULL : out [n_eval][R][9], the dense output at t_eval (np.linspace(T0, eps, num_steps), strictly decreasing float64)
+// Every state is written as the reference returns it: rotation part Gram-Schmidt-normalised in float64, translation + pts_center.
+struct OdeProcess {
+    double *out;
+    const double *t_eval;
+    int cap, n_eval;
+};
+
+__device__ __forceinline__ void ode_write_state(double *o, const double *v, const float *ctr) {
+    const double n1 = fmax(sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]), 1e-12);
+    const double b0 = v[0] / n1, b1 = v[1] / n1, b2 = v[2] / n1;
+    const double d = b0 * v[3] + b1 * v[4] + b2 * v[5];
+    const double c0 = v[3] - d * b0, c1 = v[4] - d * b1, c2 = v[5] - d * b2;
+    const double n2 = fmax(sqrt(c0 * c0 + c1 * c1 + c2 * c2), 1e-12);
+    o[0] = b0; o[1] = b1; o[2] = b2;
+    o[3] = c0 / n2; o[4] = c1 / n2; o[5] = c2 / n2;
+#pragma unroll
+    for (int c = 6; c < 9; ++c) o[c] = v[c] + (double)ctr[c - 6];
+}
+
+// One row's trajectory output for an accepted step from (t_old, y_old) to (t_new, y_new) with stage derivatives K_0..K_6
+// (K(j, c) returns component c of stage j).  `n_acc` = number of accepted steps including this one; `te_next` = first t_eval
+// index not yet emitted (advanced identically by every caller: pass write = false for rows that only keep the count).
+template <typename KFn>
+__device__ __noinline__ void ode_emit_step(const OdeProcess &pr, int R, int row, const float *ctr, bool write, int n_acc, int &te_next,
+                                           double t_old, double t_new, double h, const double *y_old, const double *y_new, KFn K) {
+    if (pr.t_eval == nullptr) {
+        if (write && n_acc < pr.cap) ode_write_state(pr.out + ((size_t)n_acc * R + row) * 9, y_new, ctr);
+        return;
+    }
+    while (te_next < pr.n_eval) {
+        const double te = __ldg(pr.t_eval + te_next);
+        if (!(te >= t_new)) break;                         // direction < 0: this step covers t_eval values in [t_new, t_old]
+        if (write) {
+            const double x = (te - t_old) / h;
+            const double p1 = x, p2 = x * x, p3 = p2 * x, p4 = p3 * x;
+            double v[9];
+#pragma unroll
+            for (int c = 0; c < 9; ++c) v[c] = 0.0;
+#pragma unroll
+            for (int j = 0; j < 7; ++j) {
+                const double w = kRkP[j][0] * p1 + kRkP[j][1] * p2 + kRkP[j][2] * p3 + kRkP[j][3] * p4;
+#pragma unroll
+                for (int c = 0; c < 9; ++c) v[c] += K(j, c) * w;
+            }
+#pragma unroll
+            for (int c = 0; c < 9; ++c) v[c] = y_old[c] + h * v[c];
+            ode_write_state(pr.out + ((size_t)te_next * R + row) * 9, v, ctr);
+        }
+        ++te_next;
+    }
+}
+
 // workspace shared by the samplers (gpb_sampler_workspace_bytes)
 struct SamplerWs {
     float *tb_table;     // [T,768]

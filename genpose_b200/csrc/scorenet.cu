@@ -451,6 +451,7 @@ struct OdeParams {
     double *pose;              // [R,9] out (float64, :206-207)
     int *stats;                // [4] nfev, accepted, rejected, status
     int tiles_per_cta;
+    OdeProcess proc;           // optional trajectory output (the reference's in_process_sample)
 };
 
 // f(t, Y) for every owned row: Y (double, global [R,9]) -> Kout (double, global [R,9]).
@@ -536,6 +537,32 @@ ode_sampler_kernel(OdeParams p) {
 
     for_owned([&](size_t e) { p.y[e] = (double)p.x0[e]; });          // y0 = float64(init_x) (:205)
     __syncthreads();
+    // trajectory output (the reference's `xs`, samplers.py:206, :220-224): one thread per owned row
+    int te_next = 0;
+    auto emit_rows = [&](int n_acc_now, double t_old, double t_new, double h_step) {
+        for (int lt = 0; lt < p.tiles_per_cta; ++lt) {
+            const int tile = blockIdx.x + lt * gridDim.x;
+            if (tile >= n_tiles) break;
+            const int row = tile * kRT + tid;
+            if (tid < kRT && row < p.R) {
+                int te = te_next;
+                const double *kb = p.Kst + (size_t)row * 9;
+                ode_emit_step(p.proc, p.R, row, p.pts_center + (size_t)(row / p.K) * 3, true, n_acc_now, te, t_old, t_new, h_step,
+                              p.y + (size_t)row * 9, p.ynew + (size_t)row * 9,
+                              [&](int j, int c) -> double { return __ldcg(kb + (size_t)j * NE + c); });
+            }
+        }
+        ode_emit_step(p.proc, p.R, 0, p.pts_center, false, n_acc_now, te_next, t_old, t_new, h_step, p.y, p.ynew,
+                      [&](int, int) -> double { return 0.0; });          // every thread advances the t_eval cursor identically
+    };
+    if (p.proc.out && p.proc.t_eval == nullptr && p.proc.cap > 0) {       // state 0 = the start
+        for (int lt = 0; lt < p.tiles_per_cta; ++lt) {
+            const int tile = blockIdx.x + lt * gridDim.x;
+            if (tile >= n_tiles) break;
+            const int row = tile * kRT + tid;
+            if (tid < kRT && row < p.R) ode_write_state(p.proc.out + (size_t)row * 9, p.y + (size_t)row * 9, p.pts_center + (size_t)(row / p.K) * 3);
+        }
+    }
 
     const double t0 = (double)p.T0, t_bound = (double)kSamplingEps;   // eps = 1e-5 as a Python float
     const double tb_exact = 1e-5;
@@ -633,6 +660,11 @@ ode_sampler_kernel(OdeParams p) {
             }
         }
         if (status != 0) break;
+        if (p.proc.out) {
+            __syncthreads();
+            emit_rows(n_acc, t, t_new, h);
+            __syncthreads();
+        }
         // accept: y <- y_new, f <- f_new (FSAL)
         for_owned([&](size_t e) {
             p.y[e] = p.ynew[e];
@@ -804,11 +836,13 @@ extern "C" int gpb_sample_pc(const float *x0, int R, int K, int num_steps, float
 
 extern "C" int gpb_sample_ode(const float *x0, int R, int K, double T0, double rtol, double atol, int denoise_steps,
                               const float *obj_bias, const float *W, const float *pts_center, double *pose, int *stats,
+                              double *process, int process_cap, const double *t_eval, int n_t_eval,
                               void *workspace, size_t workspace_bytes, void *stream) {
     GPB_REQUIRE(R >= 0 && K >= 1, "sample_ode: need R >= 0, K >= 1");
     if (R == 0) return GPB_OK;
     GPB_REQUIRE(x0 && obj_bias && W && pts_center && pose && workspace, "sample_ode: NULL buffer");
     GPB_REQUIRE(T0 > 1e-5 && rtol > 0 && atol > 0, "sample_ode: need T0 > eps and positive tolerances");
+    GPB_REQUIRE(!process || (t_eval ? n_t_eval > 0 : process_cap > 0), "sample_ode: process output needs process_cap > 0 or t_eval / n_t_eval");
     GPB_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "sample_ode: workspace must be 256-byte aligned");
     SamplerWs w = carve_sampler(workspace, R, 1);
     if (workspace_bytes < w.bytes) {
@@ -829,6 +863,7 @@ extern "C" int gpb_sample_ode(const float *x0, int R, int K, double T0, double r
     p.obj_bias = obj_bias; p.W = W; p.pts_center = pts_center;
     p.y = w.y; p.ynew = w.ynew; p.Kst = w.Kst; p.partial = reinterpret_cast<double *>(w.partial); p.barrier = w.barrier;
     p.pose = pose; p.stats = stats; p.tiles_per_cta = (n_tiles + grid - 1) / grid;
+    p.proc = OdeProcess{process, process ? t_eval : nullptr, process_cap, n_t_eval};
     GPB_CUDA(cudaFuncSetAttribute(ode_sampler_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     void *args[] = {&p};
     GPB_CUDA(cudaLaunchCooperativeKernel((void *)ode_sampler_kernel, dim3(grid), dim3(kNT), args, smem, st));

@@ -205,6 +205,32 @@ __device__ __forceinline__ bool elect_one_sync() {
     return pred != 0;
 }
 
+// ---- packed fp32 pairs (Blackwell FADD2 / FFMA2: one issue slot for two lanes of fp32 math) ------------------------------------------
+// The row warps' epilogues are issue-bound (two warps per scheduler, ~600-700 instructions per thread and layer), so halving the
+// instruction count of their adds and multiply-adds shortens the step's critical path.  A pair lives in one 64-bit register: x = low.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack_f32x2(float lo, float hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack_f32x2(f32x2 v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 add_f32x2(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 sub_f32x2(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 fma_f32x2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+
 // ---- bf16 hi/lo splitting ----------------------------------------------------------------------------------------
 // x = hi + lo + O(2^-17 |x|), both bf16: hi = rn(x), lo = rn(x - hi)
 __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16 &hi, __nv_bfloat16 &lo) {
@@ -218,8 +244,8 @@ __device__ __forceinline__ uint32_t pack_bf16(__nv_bfloat16 a, __nv_bfloat16 b) 
 __device__ __forceinline__ void split_bf16x2(float a, float b, uint32_t &hi, uint32_t &lo) {
     const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);            // .x = a (low half), .y = b
     hi = *reinterpret_cast<const uint32_t *>(&h);
-    const float ra = a - __uint_as_float(hi << 16);
-    const float rb = b - __uint_as_float(hi & 0xffff0000u);
+    float ra, rb;
+    unpack_f32x2(sub_f32x2(pack_f32x2(a, b), pack_f32x2(__uint_as_float(hi << 16), __uint_as_float(hi & 0xffff0000u))), ra, rb);
     const __nv_bfloat162 l = __floats2bfloat162_rn(ra, rb);
     lo = *reinterpret_cast<const uint32_t *>(&l);
 }
@@ -231,7 +257,9 @@ __device__ __forceinline__ void split_bf16x2(float a, float b, uint32_t &hi, uin
 __device__ __forceinline__ void relu_split_f16x2(float a, float b, uint32_t &hi, uint32_t &lo) {
     asm("cvt.rz.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(b), "f"(a));      // d = {upper half: first source, lower half: second}
     const float2 h = __half22float2(*reinterpret_cast<const __half2 *>(&hi));
-    asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(b - h.y), "f"(a - h.x));
+    float ra, rb;
+    unpack_f32x2(sub_f32x2(pack_f32x2(a, b), pack_f32x2(h.x, h.y)), ra, rb);
+    asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(rb), "f"(ra));
 }
 
 }  // namespace tc

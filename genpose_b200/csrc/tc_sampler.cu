@@ -113,6 +113,7 @@ struct TcOdeParams {
     float *tb_cta;      // [gridDim][6][768] time biases of the evaluation group in flight (private per CTA)
     double *pose;       // [R,9] float64 out (samplers.py:206-207)
     int *stats;         // [4] nfev, accepted, rejected, status (optional)
+    OdeProcess proc;    // optional trajectory output (the reference's in_process_sample)
 };
 
 struct TcPcParams {
@@ -152,8 +153,10 @@ __device__ __forceinline__ void relu_split32(const uint32_t (&v)[32], const floa
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
         const float2 bb = *reinterpret_cast<const float2 *>(bias + 2 * j);
-        if constexpr (kF16) relu_split_f16x2(__uint_as_float(v[2 * j]) + bb.x, __uint_as_float(v[2 * j + 1]) + bb.y, hi[j], lo[j]);
-        else split_bf16x2(fmaxf(__uint_as_float(v[2 * j]) + bb.x, 0.f), fmaxf(__uint_as_float(v[2 * j + 1]) + bb.y, 0.f), hi[j], lo[j]);
+        float a, b;
+        unpack_f32x2(add_f32x2(pack_f32x2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])), pack_f32x2(bb.x, bb.y)), a, b);   // one FADD2
+        if constexpr (kF16) relu_split_f16x2(a, b, hi[j], lo[j]);
+        else split_bf16x2(fmaxf(a, 0.f), fmaxf(b, 0.f), hi[j], lo[j]);
     }
 }
 
@@ -688,32 +691,46 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
             B = s_redd[9];
             slot = (slot + 1) & 3;
         };
+        int te_next = 0;                                                      // trajectory output: first t_eval index not yet written
         if constexpr (kOde) {
             if (cs == 0) {
 #pragma unroll
                 for (int c = 0; c < 9; ++c) sY[c * 128 + r] = (double)x[c];   // y0 = float64(init_x) (samplers.py:205)
+                if (od.proc.out && od.proc.t_eval == nullptr && leader && valid && od.proc.cap > 0) {   // state 0 = the start
+                    double y0[9];
+#pragma unroll
+                    for (int c = 0; c < 9; ++c) y0[c] = (double)x[c];
+                    ode_write_state(od.proc.out + (size_t)row * 9, y0, p.pts_center + (size_t)(row / p.K) * 3);
+                }
             }
             // the time biases of the first group are computed inside the first evaluation (tb_pending, below)
         }
 
         // relu(acc + obj_bias + t_bias) . O over one 32-column block whose first stacked hidden unit is n (one head per block)
+        // Packed fp32 pairs (FADD2 / FFMA2): even and odd columns accumulate in the two halves of one 64-bit register per output
+        // component and are added at the end — 12 instead of 20 issue slots per four columns.
         auto head_block = [&](const uint32_t (&v)[32], int n, float &o0, float &o1, float &o2) {
             const float *ob = obt_row + n;
             const float *w0 = sOw + (size_t)(3 * (n >> 8)) * 256 + (n & 255);
+            f32x2 a0 = pack_f32x2(o0, 0.f), a1 = pack_f32x2(o1, 0.f), a2 = pack_f32x2(o2, 0.f);
 #pragma unroll
             for (int j4 = 0; j4 < 8; ++j4) {
                 const float4 o4 = *reinterpret_cast<const float4 *>(ob + 4 * j4);
                 const float4 wa = *reinterpret_cast<const float4 *>(w0 + 4 * j4);
                 const float4 wb = *reinterpret_cast<const float4 *>(w0 + 256 + 4 * j4);
                 const float4 wc = *reinterpret_cast<const float4 *>(w0 + 512 + 4 * j4);
-                const float h0 = fmaxf(__uint_as_float(v[4 * j4 + 0]) + o4.x, 0.f);
-                const float h1 = fmaxf(__uint_as_float(v[4 * j4 + 1]) + o4.y, 0.f);
-                const float h2 = fmaxf(__uint_as_float(v[4 * j4 + 2]) + o4.z, 0.f);
-                const float h3 = fmaxf(__uint_as_float(v[4 * j4 + 3]) + o4.w, 0.f);
-                o0 = fmaf(h3, wa.w, fmaf(h2, wa.z, fmaf(h1, wa.y, fmaf(h0, wa.x, o0))));
-                o1 = fmaf(h3, wb.w, fmaf(h2, wb.z, fmaf(h1, wb.y, fmaf(h0, wb.x, o1))));
-                o2 = fmaf(h3, wc.w, fmaf(h2, wc.z, fmaf(h1, wc.y, fmaf(h0, wc.x, o2))));
+                float h0, h1, h2, h3;
+                unpack_f32x2(add_f32x2(pack_f32x2(__uint_as_float(v[4 * j4 + 0]), __uint_as_float(v[4 * j4 + 1])), pack_f32x2(o4.x, o4.y)), h0, h1);
+                unpack_f32x2(add_f32x2(pack_f32x2(__uint_as_float(v[4 * j4 + 2]), __uint_as_float(v[4 * j4 + 3])), pack_f32x2(o4.z, o4.w)), h2, h3);
+                const f32x2 p01 = pack_f32x2(fmaxf(h0, 0.f), fmaxf(h1, 0.f)), p23 = pack_f32x2(fmaxf(h2, 0.f), fmaxf(h3, 0.f));
+                a0 = fma_f32x2(p23, pack_f32x2(wa.z, wa.w), fma_f32x2(p01, pack_f32x2(wa.x, wa.y), a0));
+                a1 = fma_f32x2(p23, pack_f32x2(wb.z, wb.w), fma_f32x2(p01, pack_f32x2(wb.x, wb.y), a1));
+                a2 = fma_f32x2(p23, pack_f32x2(wc.z, wc.w), fma_f32x2(p01, pack_f32x2(wc.x, wc.y), a2));
             }
+            float e, od;
+            unpack_f32x2(a0, e, od); o0 = e + od;
+            unpack_f32x2(a1, e, od); o1 = e + od;
+            unpack_f32x2(a2, e, od); o2 = e + od;
         };
 
         for (int step = 0; kOde || step < p.T; ++step) {
@@ -1092,6 +1109,21 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
                             if (rejected) factor = fmin(1.0, factor);
                             h_abs *= factor;
                             ++n_acc;
+                            if (od.proc.out) {   // trajectory output (rare: --save_video / return_process); K_0..K_5 from L2, K_6 = f_new
+                                double yo[9], yn[9], k6[9];
+#pragma unroll
+                                for (int c = 0; c < 9; ++c) {
+                                    yo[c] = sY[c * 128 + r];
+                                    yn[c] = sYn[c * 128 + r];
+                                    k6[c] = kc[c];
+                                }
+                                const float *kbase = Kmine;
+                                const size_t kstride = kst;
+                                ode_emit_step(od.proc, p.R, valid ? row : 0, p.pts_center + (size_t)((valid ? row : 0) / p.K) * 3, leader && valid,
+                                              n_acc, te_next, t_cur, t_next, h, yo, yn, [&](int j, int c) -> double {
+                                                  return j < 6 ? (double)__ldcg(kbase + (size_t)j * kstride + c) : k6[c];
+                                              });
+                            }
                             // accept: y <- y_new, K0 <- K6 = f_new (FSAL), t <- t + h clipped to the bound
 #pragma unroll
                             for (int c = 0; c < 9; ++c) sY[c * 128 + r] = sYn[c * 128 + r];
@@ -1478,9 +1510,11 @@ extern "C" int gpb_sample_pc_tc16(const float *x0, int R, int K, int num_steps, 
 
 static int sample_ode_tc_impl(bool w16, const float *x0, int R, int K, double T0, double rtol, double atol, int denoise_steps,
                               const float *obj_bias, const float *W, const void *tc_stream, const float *pts_center, double *pose,
-                              int *stats, void *workspace, size_t workspace_bytes, unsigned long long *dbg, int dbg_evals,
+                              int *stats, double *process, int process_cap, const double *t_eval, int n_t_eval,
+                              void *workspace, size_t workspace_bytes, unsigned long long *dbg, int dbg_evals,
                               void *stream) {
     GPB_REQUIRE(R >= 0 && K >= 1, "sample_ode_tc: need R >= 0, K >= 1");
+    GPB_REQUIRE(!process || (t_eval ? n_t_eval > 0 : process_cap > 0), "sample_ode_tc: process output needs process_cap > 0 or t_eval / n_t_eval");
     if (R == 0) return GPB_OK;
     GPB_REQUIRE(x0 && obj_bias && W && tc_stream && pts_center && pose && workspace, "sample_ode_tc: NULL buffer");
     GPB_REQUIRE(T0 > 1e-5 && rtol > 0 && atol > 0, "sample_ode_tc: need T0 > eps and positive tolerances");
@@ -1509,6 +1543,7 @@ static int sample_ode_tc_impl(bool w16, const float *x0, int R, int K, double T0
     tp.ode.T0 = T0; tp.ode.rtol = rtol; tp.ode.atol = atol; tp.ode.denoise_steps = denoise_steps;
     tp.ode.Kst = w.Kst; tp.ode.partial = reinterpret_cast<double *>(w.partial); tp.ode.tb_cta = w.tb_cta;
     tp.ode.pose = pose; tp.ode.stats = stats;
+    tp.ode.proc = OdeProcess{process, process ? t_eval : nullptr, process_cap, n_t_eval};
     return launch_tc_sampler(*v, "sample_ode_tc", tp, n_tiles, st);
 }
 
@@ -1516,15 +1551,16 @@ extern "C" int gpb_sample_ode_tc_dbg(const float *x0, int R, int K, double T0, d
                                      const float *obj_bias, const float *W, const void *tc_stream, const float *pts_center, double *pose,
                                      int *stats, void *workspace, size_t workspace_bytes, unsigned long long *dbg, int dbg_evals,
                                      void *stream) {
-    return sample_ode_tc_impl(false, x0, R, K, T0, rtol, atol, denoise_steps, obj_bias, W, tc_stream, pts_center, pose, stats, workspace,
-                              workspace_bytes, dbg, dbg_evals, stream);
+    return sample_ode_tc_impl(false, x0, R, K, T0, rtol, atol, denoise_steps, obj_bias, W, tc_stream, pts_center, pose, stats, nullptr, 0,
+                              nullptr, 0, workspace, workspace_bytes, dbg, dbg_evals, stream);
 }
 
 extern "C" int gpb_sample_ode_tc16(const float *x0, int R, int K, double T0, double rtol, double atol, int denoise_steps,
                                    const float *obj_bias, const float *W, const void *tc16_stream, const float *pts_center, double *pose,
-                                   int *stats, void *workspace, size_t workspace_bytes, void *stream) {
-    return sample_ode_tc_impl(true, x0, R, K, T0, rtol, atol, denoise_steps, obj_bias, W, tc16_stream, pts_center, pose, stats, workspace,
-                              workspace_bytes, nullptr, 0, stream);
+                                   int *stats, double *process, int process_cap, const double *t_eval, int n_t_eval,
+                                   void *workspace, size_t workspace_bytes, void *stream) {
+    return sample_ode_tc_impl(true, x0, R, K, T0, rtol, atol, denoise_steps, obj_bias, W, tc16_stream, pts_center, pose, stats, process,
+                              process_cap, t_eval, n_t_eval, workspace, workspace_bytes, nullptr, 0, stream);
 }
 
 extern "C" int gpb_sample_pc_tc(const float *x0, int R, int K, int num_steps, float snr, const float *obj_bias, const float *W,
@@ -1537,7 +1573,8 @@ extern "C" int gpb_sample_pc_tc(const float *x0, int R, int K, int num_steps, fl
 
 extern "C" int gpb_sample_ode_tc(const float *x0, int R, int K, double T0, double rtol, double atol, int denoise_steps,
                                  const float *obj_bias, const float *W, const void *tc_stream, const float *pts_center, double *pose,
-                                 int *stats, void *workspace, size_t workspace_bytes, void *stream) {
-    return gpb_sample_ode_tc_dbg(x0, R, K, T0, rtol, atol, denoise_steps, obj_bias, W, tc_stream, pts_center, pose, stats, workspace,
-                                 workspace_bytes, nullptr, 0, stream);
+                                 int *stats, double *process, int process_cap, const double *t_eval, int n_t_eval,
+                                 void *workspace, size_t workspace_bytes, void *stream) {
+    return sample_ode_tc_impl(false, x0, R, K, T0, rtol, atol, denoise_steps, obj_bias, W, tc_stream, pts_center, pose, stats, process,
+                              process_cap, t_eval, n_t_eval, workspace, workspace_bytes, nullptr, 0, stream);
 }

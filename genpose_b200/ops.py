@@ -9,7 +9,7 @@ import torch
 from . import arch, lib, weights
 
 # what precision="auto" means for the samplers when the tensor-core kernels accept the shape
-AUTO_TC_PRECISION = "bf16x3"
+AUTO_TC_PRECISION = "f16x2"
 
 
 def _chk(t: torch.Tensor, dtype, name: str) -> int:
@@ -209,18 +209,33 @@ class Engine:
 
     # ---- a10: ODE sampler --------------------------------------------------------------------------------
     def sample_ode(self, obj_bias: torch.Tensor, pts_center: torch.Tensor, x0: torch.Tensor, K: int, T0: float = 1.0,
-                   rtol: float = 1e-5, atol: float = 1e-5, denoise_steps: int = 1000, precision: str = "fp32", team: int = 0):
+                   rtol: float = 1e-5, atol: float = 1e-5, denoise_steps: int = 1000, precision: str = "fp32", team: int = 0,
+                   return_process: bool = False, t_eval=None, process_cap: int = 96):
         """cond_ode_sampler (samplers.py:163-227): RK45 with SciPy's controller on device -> (pose [R,9] float64, stats [4]).
-        precision and team as in sample_pc."""
+        precision and team as in sample_pc.  return_process: additionally the trajectory `xs` the reference returns
+        (samplers.py:206, :220-224) as float64 [n, R, 9] — the solver's accepted states (n = accepted + 1) or, with
+        t_eval (float64 times, decreasing from T0 to eps: np.linspace(T0, eps, num_steps), :203), RK45's dense output there."""
         R = x0.shape[0]
         precision = self._resolve_precision("sample_ode", precision, R, K)
         L = lib.load()
         ws = self._workspace("samp", L.gpb_sampler_workspace_bytes(R, 1))
         pose = torch.empty(R, 9, dtype=torch.float64, device=self.device)
         stats = torch.zeros(4, dtype=torch.int32, device=self.device)
+        process, te, n_te = None, None, 0
+        if return_process:
+            if t_eval is not None:
+                te = torch.as_tensor(t_eval, dtype=torch.float64).to(self.device).contiguous()
+                n_te = int(te.numel())
+                if n_te < 1 or (n_te > 1 and not bool((te[1:] < te[:-1]).all())):
+                    raise lib.GenPoseB200Error("sample_ode: t_eval must be strictly decreasing (np.linspace(T0, eps, num_steps))")
+                process = torch.empty(n_te, R, 9, dtype=torch.float64, device=self.device)
+            else:
+                process = torch.empty(int(process_cap), R, 9, dtype=torch.float64, device=self.device)
         head = (_chk(x0, torch.float32, "x0"), R, K, float(T0), float(rtol), float(atol), int(denoise_steps),
                 _chk(obj_bias, torch.float32, "obj_bias"), self.trunk_w.data_ptr())
-        tail = (_chk(pts_center, torch.float32, "pts_center"), pose.data_ptr(), stats.data_ptr(), ws.data_ptr(), ws.numel(), _stream())
+        tail = (_chk(pts_center, torch.float32, "pts_center"), pose.data_ptr(), stats.data_ptr(),
+                0 if process is None else process.data_ptr(), int(process_cap), 0 if te is None else te.data_ptr(), n_te,
+                ws.data_ptr(), ws.numel(), _stream())
         if precision != "fp32":
             lib.check(L.gpb_set_tc_team(int(team)), "set_tc_team")
         if precision == "bf16x3":
@@ -229,7 +244,14 @@ class Engine:
             lib.check(L.gpb_sample_ode_tc16(*head, self.trunk_tc16().data_ptr(), *tail), "sample_ode_tc16")
         else:
             lib.check(L.gpb_sample_ode(*head, *tail), "sample_ode")
-        return pose, stats
+        if not return_process:
+            return pose, stats
+        if te is None:
+            n = int(stats[1]) + 1                              # start + accepted steps (synchronises: the trajectory is a visualisation path)
+            if n > process_cap:
+                raise lib.GenPoseB200Error(f"sample_ode: {n} trajectory states exceed process_cap={process_cap}; raise it")
+            process = process[:n]
+        return pose, stats, process
 
     # ---- a12: energy ------------------------------------------------------------------------------------------
     def energy(self, obj_bias: torch.Tensor, pts_center: torch.Tensor, pose: torch.Tensor, K: int, t: float = 1e-5) -> torch.Tensor:

@@ -48,9 +48,11 @@ class PosePipeline:
             self.energy_agent = PoseNet(default_cfg(sampler, sampling_steps, "energy", noise_mode, precision))
             self.energy_agent.net.load_state_dict(energy_state_dict)
             # The energy network has its own encoder (evaluation_single.py:431) whose input is the same cloud, and the
-            # tensor-core sampler holds only 100 of the 148 SMs: the second encoder pass runs on a side stream, on the SMs
-            # the sampler leaves free, instead of after it.
+            # tensor-core sampler holds only 100 of the 148 SMs at 64 objects: the second encoder pass runs on a side stream, on
+            # the SMs the sampler leaves free, instead of after it.  It is ordered BEHIND the score network's encoder (an event
+            # recorded between that encoder and the sampler), so the two encoder passes do not slow each other on the critical path.
             self._side = torch.cuda.Stream()
+            self.score_agent.on_features_ready = self._mark_score_encoder_done
 
     def _mark_clouds_ready(self):
         """Call on entry, before the score path is enqueued: whatever produced the clouds on the main stream is ordered
@@ -58,6 +60,10 @@ class PosePipeline:
         if self._side is not None:
             self._clouds_ready = torch.cuda.Event()
             self._clouds_ready.record(torch.cuda.current_stream())
+
+    def _mark_score_encoder_done(self, data):
+        self._clouds_ready = torch.cuda.Event()
+        self._clouds_ready.record(torch.cuda.current_stream())
 
     def _energy_features_async(self, data):
         """Start the energy net's encoder on the side stream -> pts_feat (join with _energy_rank_pool).  It waits for the
@@ -121,9 +127,14 @@ class PosePipeline:
         side = self._side if self._side is not None else torch.cuda.Stream()
         main = torch.cuda.current_stream()
 
-        def encode(data):
-            ready = torch.cuda.Event()
-            ready.record(main)
+        def clouds_ready():
+            ev = torch.cuda.Event()
+            ev.record(main)
+            return ev
+
+        def encode(data, ready):
+            """Encoder + object bias of `data` on the side stream; it waits only for `ready` (recorded on the main stream when the
+            batch was pulled, i.e. BEFORE the previous batch's sampler was enqueued), never for that sampler."""
             side.wait_event(ready)
             with torch.cuda.stream(side):
                 ob = eng.object_bias(eng.encode(data["pts"].float().contiguous(), precision=net.precision))
@@ -132,8 +143,10 @@ class PosePipeline:
 
         it = iter(batches)
         cur = next(it, None)
-        ob = encode(cur) if cur is not None else None
+        ob = encode(cur, clouds_ready()) if cur is not None else None
         while cur is not None:
+            nxt = next(it, None)                      # pull the next batch (its producer may enqueue copies on the main stream) ...
+            nxt_ready = clouds_ready() if nxt is not None else None      # ... and mark it ready before this batch's sampler is enqueued
             main.wait_stream(side)
             B = cur["pts"].shape[0]
             R = B * repeat_num
@@ -141,9 +154,7 @@ class PosePipeline:
             noise, seed = net._step_noise(net.cfg.sampling_steps, R, cur["pts"].device)          # (None, key) in philox mode
             pose = eng.sample_pc(ob, cur["pts_center"].float().contiguous(), x0.float().contiguous(), repeat_num,
                                  net.cfg.sampling_steps, step_noise=noise, seed=seed, snr=0.16, precision=net.precision)
-            nxt = next(it, None)
             if nxt is not None:
-                ob = encode(nxt)
+                ob = encode(nxt, nxt_ready)
             yield pose.reshape(B, repeat_num, 9)
             cur = nxt
-

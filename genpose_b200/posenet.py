@@ -29,6 +29,7 @@ class GFObjectPose:
             if (getattr(cfg, "energy_mode", "IP"), getattr(cfg, "s_theta_mode", "score"), getattr(cfg, "norm_energy", "identical")) \
                     != ("IP", "score", "identical"):
                 raise NotImplementedError("energy net: only energy_mode IP / s_theta_mode score / norm_energy identical")
+        self.is_energy_net = getattr(cfg, "posenet_mode", "score") == "energy"
         self._state: Optional[Dict[str, torch.Tensor]] = None
         self.engine: Optional[ops.Engine] = None
         # noise for the PC sampler: 'philox' (in-kernel, throughput) or 'torch' (torch.randn_like draws in the
@@ -85,6 +86,14 @@ class GFObjectPose:
         self.engine = ops.Engine(self._state, device="cuda" if str(self.device) == "cuda" else self.device)
         return self
 
+    def _require_score_net(self, what: str):
+        """An energy network's score is the autograd gradient of its energy (PoseEnergyNet.forward(return_item='score'),
+        energynet.py:187-198): f/std + x . df/dx / std, not the trunk output f/std a score network returns.  Only the energy itself
+        (inference: PoseNet.get_energy, evaluation_single.py:339-343) is implemented for --posenet_mode energy."""
+        if self.is_energy_net:
+            raise NotImplementedError(f"{what} on an energy network (--posenet_mode energy) needs the gradient of the energy; "
+                                      "only mode='energy' / PoseNet.get_energy is implemented for it")
+
     def _eng(self) -> ops.Engine:
         if self.engine is None:
             raise lib.GenPoseB200Error("GFObjectPose has no weights: call load_state_dict()/PoseNet.load_ckpt() first")
@@ -111,6 +120,7 @@ class GFObjectPose:
                           step_noise=None):
         """Fast path used by PoseNet.pred_func: K candidates per object WITHOUT repeating the features.
         pts_feat [B,1024], pts_center [B,3] -> res [B*K,9] (+ process)."""
+        self._require_score_net("sample_candidates")
         eng = self._eng()
         B = pts_feat.shape[0]
         R = B * repeat_num
@@ -126,17 +136,23 @@ class GFObjectPose:
                 step_noise, seed = self._step_noise(num_steps, R, pts_feat.device)
             out = eng.sample_pc(ob, center, x0.float().contiguous(), repeat_num, num_steps, step_noise=step_noise,
                                 seed=seed, snr=0.16, return_process=return_process, precision=self.precision)
-            return out if return_process else (None, out)
+            return (out[1], out[0]) if return_process else (None, out)          # (in_process_sample [R,T,9], res [R,9]) like samplers.py:160
         elif sampler == "ode":
             T0 = self.T if T0 is None else T0
             prior = self.prior_fn((R, arch.POSE_DIM), T=T0).to(pts_feat.device)                            # samplers.py:180
             x0 = prior if init_x is None else init_x + prior
             num_steps = self.cfg.sampling_steps
-            pose, stats = eng.sample_ode(ob, center, x0.float().contiguous(), repeat_num, T0=T0, rtol=1e-5, atol=1e-5,
-                                         denoise_steps=1000 if num_steps is None else num_steps, precision=self.precision)
+            kw = dict(T0=T0, rtol=1e-5, atol=1e-5, denoise_steps=1000 if num_steps is None else num_steps, precision=self.precision)
+            if not return_process:
+                pose, stats = eng.sample_ode(ob, center, x0.float().contiguous(), repeat_num, **kw)
+                self.last_ode_stats = stats
+                return None, pose
+            # in_process_sample (samplers.py:201-206, :220-224): SciPy's accepted states, or its dense output at
+            # t_eval = np.linspace(T, eps, num_steps) when --sampling_steps is set; [n, R, 9] -> [R, n, 9] like xs.permute(1, 0, 2)
+            t_eval = None if num_steps is None else np.linspace(float(T0), float(self.sampling_eps), int(num_steps))
+            pose, stats, process = eng.sample_ode(ob, center, x0.float().contiguous(), repeat_num, return_process=True, t_eval=t_eval, **kw)
             self.last_ode_stats = stats
-            # in_process_sample: the reference returns SciPy's accepted steps; we return the final state only
-            return (pose, pose.unsqueeze(1)) if return_process else (None, pose)
+            return process.permute(1, 0, 2), pose
         raise NotImplementedError(sampler)
 
     def forward(self, data, mode="score", init_x=None, T0=None):
@@ -152,6 +168,8 @@ class GFObjectPose:
             t0 = float(t.reshape(-1)[0])
             if not bool((t == t.reshape(-1)[0]).all()):
                 raise NotImplementedError("per-row time values: both samplers and get_energy(T=...) use a batch-constant t")
+            if mode == "score":
+                self._require_score_net("forward(mode='score')")
             ob = eng.object_bias(feat)
             if mode == "score":
                 return eng.trunk_eval(ob, pose, 1, t0, divide_mode=1)

@@ -24,6 +24,9 @@ class PoseNet:
         self.model_dir = f"./results/ckpts/{getattr(cfg, 'log_dir', 'debug')}"          # posenet_agent.py:36
         self.prior_fn, self.marginal_prob_fn, self.sde_fn, self.sampling_eps, self.T = init_sde(cfg.sde_mode)
         self.net = self.build_net()
+        # optional callable(data) invoked inside pred_func once data['pts_feat'] has been enqueued (before the sampler is): lets a
+        # pipeline order side-stream work behind the encoder instead of beside it (genpose_b200.pipeline.PosePipeline)
+        self.on_features_ready = None
 
     def get_network(self, name):
         if name == "GFObjectPose":
@@ -59,6 +62,8 @@ class PoseNet:
         self.net.eval()
         with torch.no_grad():
             data["pts_feat"] = self.net(data, mode="pts_feature")                       # :422 (side effect kept)
+            if self.on_features_ready is not None:
+                self.on_features_ready(data)
             bs = data["pts"].shape[0]
             self.pts_feature = True
             repeated_init_x = None if init_x is None else init_x.unsqueeze(1).repeat(1, repeat_num, 1).view(bs * repeat_num, -1)
@@ -75,7 +80,9 @@ class PoseNet:
                 zeros = torch.zeros(bs, repeat_num, 2, device=pose_f.device)           # equal energies: stable order = identity
                 _, _, rt = ops.rank_pool(pose_f, zeros, ratio=1.0)
                 pred_pose_q_wxyz = _poses_to_quat(res.float()).reshape(bs, repeat_num, -1)
-                average = torch.cat([_matrix_to_quat(rt[:, :3, :3]), rt[:, :3, 3]], dim=-1)
+                q_avg = _matrix_to_quat(rt[:, :3, :3])
+                q_avg = ((q_avg[:, 0:1] > 0).float() - 0.5) * 2 * q_avg                 # oriented w > 0 (utils/misc.py:247)
+                average = torch.cat([q_avg, rt[:, :3, 3]], dim=-1)
                 if return_process:
                     return pred_pose, pred_pose_q_wxyz, average, in_process_sample
                 return pred_pose, pred_pose_q_wxyz, average

@@ -152,10 +152,19 @@ GPB_API int gpb_sample_pc_tc_dbg(const float *x0, int R, int K, int num_steps, f
  *   x0 [R,9] f32        already-noised start (sigma(T0)*randn, plus init_x when tracking, :180)
  *   T0, rtol, atol      float64, as the Python floats the reference hands to solve_ivp (samplers.py:178, :205)
  *   pose [R,9] f64 out  (the reference returns float64, :206-207)
- *   stats [4] i32 out   optional: nfev, accepted, rejected, status */
+ *   stats [4] i32 out   optional: nfev, accepted, rejected, status
+ *   process             optional trajectory, the reference's in_process_sample (`xs`, samplers.py:206, :220-224), float64,
+ *                       every state with its rotation part normalised and pts_center added like the reference's:
+ *                         t_eval == NULL: [process_cap][R][9] — state 0 = the start, state i = the i-th ACCEPTED RK45
+ *                           step (solve_ivp's res.y with t_eval=None); stats[1] + 1 states exist, those beyond
+ *                           process_cap are dropped
+ *                         t_eval != NULL: [n_t_eval][R][9] — RK45's dense output at t_eval[0..n_t_eval), device float64,
+ *                           strictly decreasing from T0 to eps (np.linspace(T0, eps, num_steps), samplers.py:203)
+ *                       NULL = no trajectory (then process_cap, t_eval, n_t_eval are ignored) */
 GPB_API int gpb_sample_ode(const float *x0, int R, int K, double T0, double rtol, double atol, int denoise_steps,
                    const float *obj_bias, const float *trunk_weights, const float *pts_center, double *pose,
-                   int *stats, void *workspace, size_t workspace_bytes, void *stream);
+                   int *stats, double *process, int process_cap, const double *t_eval, int n_t_eval,
+                   void *workspace, size_t workspace_bytes, void *stream);
 
 /* largest R gpb_sample_pc_tc / gpb_sample_ode_tc accept on the current device for K candidates per object (0 = K too
  * small or no device): every 128-row tile needs one co-resident team of CTAs, and a team may be a single CTA, so
@@ -174,7 +183,8 @@ GPB_API int gpb_set_tc_team(int team);
  * Constraints: K >= 43, R <= gpb_sampler_tc_max_rows(K); otherwise use gpb_sample_ode. */
 GPB_API int gpb_sample_ode_tc(const float *x0, int R, int K, double T0, double rtol, double atol, int denoise_steps,
                       const float *obj_bias, const float *trunk_weights, const void *tc_stream, const float *pts_center,
-                      double *pose, int *stats, void *workspace, size_t workspace_bytes, void *stream);
+                      double *pose, int *stats, double *process, int process_cap, const double *t_eval, int n_t_eval,
+                      void *workspace, size_t workspace_bytes, void *stream);
 
 /* profiling aid: as gpb_sample_ode_tc, additionally records clock64 stamps of CTA 0 for the first dbg_evals evaluations
  * into dbg [2][dbg_evals][16] (row thread 0 | MMA warp); see tools/tc_ode_phase_times.py. */
@@ -197,7 +207,8 @@ GPB_API int gpb_sample_pc_tc16(const float *x0, int R, int K, int num_steps, flo
                        void *workspace, size_t workspace_bytes, unsigned long long *dbg, void *stream);
 GPB_API int gpb_sample_ode_tc16(const float *x0, int R, int K, double T0, double rtol, double atol, int denoise_steps,
                         const float *obj_bias, const float *trunk_weights, const void *tc16_stream, const float *pts_center,
-                        double *pose, int *stats, void *workspace, size_t workspace_bytes, void *stream);
+                        double *pose, int *stats, double *process, int process_cap, const double *t_eval, int n_t_eval,
+                        void *workspace, size_t workspace_bytes, void *stream);
 
 /* replaces PoseNet.get_energy's arithmetic after the encoder (networks/posenet_agent.py:508-523 ->
  * PoseEnergyNet.get_energy energynet.py:143-198, 'IP' decoupled): energy [B,K,2] = (rot, trans). */

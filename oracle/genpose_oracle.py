@@ -215,6 +215,7 @@ def pc_sampler(sd, pts_feat, pts_center, x0, step_noise, num_steps: int, snr: fl
     x = x0.to(dtype).clone()
     time_steps = torch.linspace(1.0, EPS, num_steps).to(dtype) if dtype == torch.float32 else \
         torch.linspace(1.0, EPS, num_steps, dtype=torch.float32).to(dtype)      # linspace is fp32 in the reference (:118)
+    time_steps = time_steps.to(x.device)                                        # (device-agnostic: bench.py's GPU-torch context baseline)
     step_size = time_steps[0] - time_steps[1]                                   # :119
     noise_norm = np.sqrt(9)                                                     # :120
     pf = pts_feat.to(dtype)
@@ -222,7 +223,7 @@ def pc_sampler(sd, pts_feat, pts_center, x0, step_noise, num_steps: int, snr: fl
     mean_x = None
     for i in range(num_steps):
         ts = time_steps[i]
-        bt = torch.ones(R, 1, dtype=dtype) * ts                                 # :125
+        bt = torch.ones(R, 1, dtype=dtype, device=x.device) * ts                # :125
         grad = score(sd, pf, x, bt, dtype)                                      # :129
         grad_norm = torch.norm(grad.reshape(R, -1), dim=-1).mean()              # :130  ONE scalar per batch
         ls = 2 * (snr * noise_norm / grad_norm) ** 2                            # :131
@@ -344,7 +345,7 @@ def rk45_integrate(fun, t0: float, t_bound: float, y0: np.ndarray, rtol: float, 
 
 
 def ode_sampler(sd, pts_feat, pts_center, x0, T0: float = 1.0, rtol: float = 1e-5, atol: float = 1e-5,
-                num_steps=None, denoise: bool = True, return_stats: bool = False):
+                num_steps=None, denoise: bool = True, return_stats: bool = False, return_process: bool = False):
     """cond_ode_sampler, samplers.py:163-227 (T=T0, eps=1e-5).  x0 [R,9] is the already-noised
     start (prior sample at T0, plus init_x when tracking, :180).  State float64 on the host,
     score in fp32 (:191), drift-free VE: dx/dt = -0.5 g(t)^2 score.  NumPy-1.23 value-based
@@ -377,6 +378,22 @@ def ode_sampler(sd, pts_feat, pts_center, x0, T0: float = 1.0, rtol: float = 1e-
     x = x.clone()
     x[:, :-3] = normalize_rotation(x[:, :-3])                                   # :225
     x[:, -3:] += pts_center.to(x.dtype)                                         # :226
+    if return_process:
+        # the reference's `xs` (samplers.py:201-206, :220-224) through SciPy itself: accepted states, or the dense output at
+        # t_eval = np.linspace(T, eps, num_steps) when num_steps is given; rotations normalised, pts_center added
+        from scipy import integrate
+        t_eval = None if num_steps is None else np.linspace(T0, EPS, num_steps)
+        res = integrate.solve_ivp(ode_func, (T0, EPS), y0, rtol=rtol, atol=atol, method="RK45", t_eval=t_eval)
+        xs = torch.tensor(res.y).T.reshape(-1, R, 9).clone()                    # [n, R, 9] float64
+        n = xs.shape[0]
+        flat = xs.reshape(n * R, 9)
+        flat[:, :-3] = normalize_rotation(flat[:, :-3])
+        xs = flat.reshape(n, R, 9)
+        xs[:, :, -3:] += pts_center.to(xs.dtype).unsqueeze(0)
+        process = xs.permute(1, 0, 2)                                           # [R, n, 9]
+        if return_stats:
+            return x, dict(nfev=nfev, accepted=n_acc, rejected=n_rej), process
+        return x, process
     if return_stats:
         return x, dict(nfev=nfev, accepted=n_acc, rejected=n_rej)
     return x

@@ -41,6 +41,12 @@ CASES = {
     "pc_B2_K5_T500": dict(sampler="pc", B=2, K=5, T=500, seed=2, kappa=-0.3, energy=True),
     "ode_B3_K4_T055": dict(sampler="ode", B=3, K=4, T0=0.55, seed=3, kappa=0.3, energy=True),
     "ode_B2_K3_T100": dict(sampler="ode", B=2, K=3, T0=1.0, seed=4, kappa=0.05, energy=False),
+    # K = 50 (the candidates per object every BASELINE config and scripts/eval_single.sh:8 use): the cases the tensor-core samplers
+    # accept (a 128-row tile must span <= 4 objects), so those kernels are held to reference-generated vectors directly
+    "pc_B3_K50_T500": dict(sampler="pc", B=3, K=50, T=500, seed=5, kappa=-0.3, energy=True),
+    "ode_B3_K50_T055": dict(sampler="ode", B=3, K=50, T0=0.55, seed=6, kappa=0.3, energy=True),
+    # no stabilising linear field at all (kappa = 0): a short chain shows the error of the undamped reference dynamics
+    "pc_B3_K50_T12_kappa0": dict(sampler="pc", B=3, K=50, T=12, seed=7, kappa=0.0, energy=False),
 }
 
 

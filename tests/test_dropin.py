@@ -132,6 +132,49 @@ def test_agent_end_to_end_on_gpu(tmp_path):
     assert torch.equal(sp.cpu(), sp_ref) and torch.equal(se.cpu(), se_ref)
 
 
+@pytest.mark.gpu
+def test_pred_func_average_branch_on_gpu():
+    """pred_func(return_average_res=True) (posenet_agent.py:449-461): per-candidate quaternions (get_rot_matrix + pytorch3d
+    matrix_to_quaternion), the eigen-mean quaternion of all K candidates oriented to w > 0 (average_quaternion_batch,
+    utils/misc.py:227-249) and the mean translation — against the oracle's restatement of those functions on the SAME poses."""
+    from genpose_b200 import synth
+    from genpose_b200.config import get_config
+    from genpose_b200.posenet_agent import PoseNet
+    from oracle import genpose_oracle as O
+    T, B, K = 30, 3, 50
+    sd = synth.make_state_dict(9, kappa=synth.stable_kappa(T))
+    agent = PoseNet(get_config(["--sampler_mode", "pc", "--sampling_steps", str(T)]))
+    agent.net.load_state_dict(sd)
+    data = synth.batch_from_clouds(synth.make_clouds(B, 9), device="cuda")
+    torch.manual_seed(2)
+    pred_pose, pred_q, average = agent.pred_func(data=data, repeat_num=K, save_path=None, return_average_res=True)
+    torch.manual_seed(2)
+    four = agent.pred_func(data=data, repeat_num=K, save_path=None, return_average_res=True, return_process=True)
+    assert len(four) == 4 and torch.equal(four[0], pred_pose) and four[3].shape[:2] == (B, K)
+    assert pred_pose.shape == (B, K, 9) and pred_q.shape == (B, K, 7) and average.shape == (B, 7)
+    res = pred_pose.reshape(B * K, 9).cpu()
+    q_ref = O.matrix_to_quaternion(O.get_rot_matrix(res[:, :6]))
+    ref_q = torch.cat([q_ref, res[:, 6:]], dim=-1).reshape(B, K, 7)
+    assert float((pred_q.cpu() - ref_q).abs().max()) <= 1e-5
+    avg_q = O.average_quaternion_batch(ref_q[:, :, :4])
+    assert bool((average[:, 0] > 0).all())
+    assert float((average[:, :4].cpu() - avg_q).abs().max()) <= 2e-5
+    assert float((average[:, 4:].cpu() - ref_q[:, :, 4:].mean(dim=1)).abs().max()) <= 1e-5 * max(1.0, float(ref_q[:, :, 4:].abs().max()))
+
+
+def test_energy_agent_refuses_score_and_sampling():
+    """An energy network's score is the gradient of its energy (energynet.py:187-198), not the trunk output: the score / sampling
+    entry points raise instead of silently returning f / std."""
+    from genpose_b200.config import get_config
+    from genpose_b200.posenet import GFObjectPose
+    from genpose_b200.sde import init_sde
+    cfg = get_config(["--sampler_mode", "pc", "--sampling_steps", "10", "--posenet_mode", "energy"])
+    net = GFObjectPose(cfg, *init_sde(cfg.sde_mode))
+    for call in (lambda: net.sample_candidates(None, None, 5, "pc"), lambda: net._require_score_net("forward(mode='score')")):
+        with pytest.raises(NotImplementedError):
+            call()
+
+
 def test_poses_to_RTs_is_the_runners_loop():
     """pipeline.poses_to_RTs against the literal per-candidate loop of pred_pose_batch (runners/evaluation_single.py:325-332)."""
     import numpy as np

@@ -67,7 +67,7 @@ def test_gather_and_group(ops):
 # ------------------------------------------------------------------------------------------------------
 # fused path against the reference goldens
 # ------------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("name", _cases.golden_names())
+@pytest.mark.parametrize("name", [n for n in _cases.golden_names() if "kappa0" not in n])      # kappa0: tests/test_gpu_tc_teams.py::test_undamped_dynamics_golden
 def test_fused_path_matches_reference_golden(ops, name):
     case, g, inp = _cases.load(name)
     B, K = case["B"], case["K"]

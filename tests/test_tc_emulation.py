@@ -80,3 +80,23 @@ def test_f16_activation_split_matches_its_definition():
     assert float(((hi + lo - a).abs()[big] / a[big]).max()) <= 2.0 ** -20
     assert float((hi + lo - a).abs().max()) <= 2.0 ** -20 * 300 + 2.0 ** -25
     assert float(E.split_act_f16(torch.tensor([1e6, -3.0]))[0][0]) == E.FP16_MAX and float(E.split_act_f16(torch.tensor([-3.0]))[0][0]) == 0.0
+
+
+def test_undamped_golden_separates_the_two_arithmetics():
+    """pc_B3_K50_T12_kappa0 (a vector made by the UNMODIFIED reference, no stabilising field, T = 12): sampler fed the reference's own
+    features.  Three products: 0.05 of the parity bound.  Two products (fp16 weights): 1.24x the bound (3.2e-3 on ~30 m translations)
+    — the number the B200 kernel reproduces to the digit (tests/test_gpu_tc_teams.py::test_undamped_dynamics_golden), which is why
+    `precision='bf16x3'` stays available as the high-fidelity choice."""
+    from tests import _cases
+    case, g, inp = _cases.load("pc_B3_K50_T12_kappa0")
+    data = synth.batch_from_clouds(inp["clouds"])
+    feat = torch.from_numpy(g["ref_pts_feat"])
+    ref = g["ref_pred_pose"]
+    frac = {}
+    for terms in (3, "x2"):
+        with E.emulated_score(terms=terms):
+            tc, _ = O.pred_func_pc(inp["sd"], data, case["K"], case["T"], torch.from_numpy(inp["x0"]), torch.from_numpy(inp["step_noise"]),
+                                   pts_feat=feat)
+        frac[terms] = float((np.abs(tc.numpy() - ref) / (1e-3 + 5e-5 * np.abs(ref))).max())
+    assert frac[3] < 0.2, frac
+    assert 0.5 < frac["x2"] < 2.0, frac

@@ -1,11 +1,17 @@
 """Turn the raw ncu artefacts of a GPU round (gpurun_out/<tag>_*) into small tracked summaries under profiles/.
-    python tools/summarize_ncu.py <tag>
+    python tools/summarize_ncu.py <tag> [name ...]
+A full capture gpurun_out/<tag>_prof_<name>.ncu-rep may come with gpurun_out/<tag>_prof_<name>.shape.json (written by
+tools/profile_target.py: precision, rows, steps of the profiled launch); the summary then gets a companion
+profiles/<tag>_ncu_<name>.meta.json (kernel, shape, DRAM bytes, tensor-pipe %, duration, commit), which bench.py reads for
+`roofline.traffic`.
 """
 import collections
 import csv
+import json
 import os
 import subprocess
 import sys
+import time
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OUT = os.path.join(ROOT, "gpurun_out")
@@ -70,11 +76,37 @@ def full(tag, name):
                         (k.startswith("smsp__average_warp_latency_issue_stalled") and k.endswith(".ratio")):
                     f.write(f"\"{kn}\",{k},{units[hdr.index(k)]},{d[k]}\n")
     print("wrote full-capture summary for", name, len(rows) - 2, "launches")
+    shape_path = os.path.join(OUT, f"{tag}_prof_{name}.shape.json")
+    if os.path.exists(shape_path) and len(rows) > 2:
+        d = dict(zip(hdr, rows[-1]))                      # the last captured launch
+
+        def val(k, scale_units=None):
+            if k not in d:
+                return None
+            v = float(d[k].replace(",", ""))
+            u = units[hdr.index(k)]
+            if scale_units:
+                v *= scale_units.get(u, 1.0)
+            return v
+        byte_units = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        time_units = {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}
+        meta = json.load(open(shape_path))
+        try:
+            commit = subprocess.run(["git", "rev-parse", "--short", "HEAD"], capture_output=True, text=True, cwd=ROOT).stdout.strip()
+        except Exception:
+            commit = None
+        meta.update({"file": f"profiles/{tag}_ncu_{name}.csv", "kernel": d["Kernel Name"], "commit": commit or meta.get("commit"),
+                     "order": int(time.time()),
+                     "dram_bytes": int((val("dram__bytes_read.sum", byte_units) or 0) + (val("dram__bytes_write.sum", byte_units) or 0)),
+                     "tensor_pipe_active_pct": val("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"),
+                     "duration_ms": val("gpu__time_duration.sum", time_units)})
+        json.dump(meta, open(os.path.join(PROF, f"{tag}_ncu_{name}.meta.json"), "w"), indent=1)
+        print("wrote", f"{tag}_ncu_{name}.meta.json", meta)
 
 
 if __name__ == "__main__":
     tag = sys.argv[1]
     os.makedirs(PROF, exist_ok=True)
     launches(tag)
-    for n in ("sampler", "encoder", "tc_sampler", "tc_ode_sampler"):
+    for n in (sys.argv[2:] or ("sampler", "encoder", "tc_sampler", "tc_ode_sampler", "tc_sampler_sat", "energy_rank_pool")):
         full(tag, n)
