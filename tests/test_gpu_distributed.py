@@ -68,7 +68,7 @@ def _worker(rank, world, port, n_objects, K, T, ret):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("n_objects,K,T", [(8, 50, 40), (7, 50, 24), (1, 64, 16)])
+@pytest.mark.parametrize("n_objects,K,T", [(8, 50, 100), (7, 50, 100), (1, 64, 100)])
 def test_sharded_pipeline_world2_nccl(n_objects, K, T):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
@@ -82,4 +82,4 @@ def test_sharded_pipeline_world2_nccl(n_objects, K, T):
     for p in procs:
         p.join(300)
         assert p.exitcode == 0
-    assert all(ret.get(r, (False, 0))[0] for r in range(world)), dict(ret)
+    assert all(ret.get(r, (False, 0))[0] for r in range(world)), f"(ok, worst fraction of the parity bound) per rank: {dict(ret)}"
