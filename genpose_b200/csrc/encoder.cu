@@ -14,6 +14,7 @@
 //                      ABSOLUTE xyz, max over points (atomicMax on non-negative floats).
 //
 // BatchNorm (eval) is folded into W and b on the host (genpose_b200/weights.py); all math is fp32 FFMA.
+#include <cstdlib>
 #include <mutex>
 
 #include "common.cuh"
@@ -618,24 +619,40 @@ constexpr size_t kEncTcL2Const = 2048, kEncTcL2Img0 = (64 * 64 + 64 * 128) * 4, 
 constexpr size_t kEncTcGaOff = kEncTcL2Off + 2 * kEncTcL2Const + kEncTcL2Img0 + kEncTcL2Img1;   // GroupAll block (ga_tc.cu) last
 }  // namespace gpb
 
-// A side stream per device for the work that may run beside the caller's stream inside one encoder pass (fork / join with events
-// created per call, so concurrent callers on different streams do not share state beyond the side stream's ordering).
-static cudaStream_t encoder_side_stream() {
+// Two side streams per device for the work that may run beside the caller's stream inside one encoder pass: [0] (highest priority)
+// furthest-point sampling of levels 2 and 3, [1] the narrow scale of every set-abstraction level.  Fork / join use events created per
+// call, so concurrent callers on different streams share nothing beyond the side streams' own ordering.
+static bool encoder_side_streams(cudaStream_t (&out)[2]) {
     static std::mutex mu;
-    static cudaStream_t side[64] = {};
+    static cudaStream_t side[64][2] = {};
     int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return false;
     std::lock_guard<std::mutex> lock(mu);
-    if (!side[dev]) {
-        // highest priority: its few small CTAs (B x 256 threads) must be placed ahead of the set-abstraction grids they run beside
+    if (!side[dev][0]) {
+        // FPS: a few small CTAs (B x 256 threads) that must be placed ahead of the set-abstraction grids they run beside
         int lo = 0, hi = 0;
         cudaDeviceGetStreamPriorityRange(&lo, &hi);
-        if (cudaStreamCreateWithPriority(&side[dev], cudaStreamNonBlocking, hi) != cudaSuccess) {
+        if (cudaStreamCreateWithPriority(&side[dev][0], cudaStreamNonBlocking, hi) != cudaSuccess ||
+            cudaStreamCreateWithFlags(&side[dev][1], cudaStreamNonBlocking) != cudaSuccess) {
             cudaGetLastError();
-            side[dev] = nullptr;
+            side[dev][0] = side[dev][1] = nullptr;
+            return false;
         }
     }
-    return side[dev];
+    out[0] = side[dev][0];
+    out[1] = side[dev][1];
+    return true;
+}
+
+// `to` waits for everything enqueued on `from` so far (one throw-away event; the runtime releases it when the work has completed)
+static int stream_follows(cudaStream_t to, cudaStream_t from) {
+    cudaEvent_t ev;
+    GPB_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    cudaError_t e = cudaEventRecord(ev, from);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(to, ev, 0);
+    cudaEventDestroy(ev);
+    GPB_CUDA(e);
+    return GPB_OK;
 }
 
 static int encode_impl(const float *pts, int B, const float *enc_w, const uint8_t *enc_tc, float *pts_feat, void *workspace,
@@ -652,76 +669,76 @@ static int encode_impl(const float *pts, int B, const float *enc_w, const uint8_
     GPB_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "encode: workspace must be 256-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
     int rc;
+    // GPB_ENC_SERIAL=1: everything on the caller's stream in program order (the round-1 schedule), for A/B timing
+    static const bool serial = [] { const char *v = getenv("GPB_ENC_SERIAL"); return v && v[0] == '1'; }();
+    cudaStream_t side[2] = {nullptr, nullptr};
+    const bool forked = !serial && encoder_side_streams(side);
+    // the two scales of a level are independent kernels writing disjoint channel ranges of the level's feature tensor: the narrow
+    // scale (index 0) runs on side stream 1 beside the wide one, which stays on the caller's stream
+    cudaStream_t s0 = forked ? side[1] : st;
+    auto fork = [&]() -> int { return forked ? stream_follows(s0, st) : GPB_OK; };     // scale 0 may start: its inputs are complete on `st`
+    auto join = [&]() -> int { return forked ? stream_follows(st, s0) : GPB_OK; };     // the level's output is complete on `st`
 
     // Furthest-point sampling is 896 dependent arg-max rounds on B CTAs: level 1 (512 rounds) first, then levels 2 and 3 (384 rounds)
-    // on a side stream beside level 1's set abstraction, which only needs new_xyz1; joined in front of level 2.
-    cudaStream_t side = encoder_side_stream();
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-    if (side && (cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming) != cudaSuccess ||
-                 cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming) != cudaSuccess)) {
-        cudaGetLastError();
-        if (ev_fork) cudaEventDestroy(ev_fork);
-        ev_fork = ev_join = nullptr;
-        side = nullptr;
-    }
-    if (side) {
+    // on side stream 0 beside level 1's set abstraction, which only needs new_xyz1; joined in front of level 2.
+    if (forked) {
         fps_l1_kernel<<<B, kFps3Threads, 0, st>>>(pts, w.nx1, fps_idx1);
         GPB_LAUNCHED();
-        GPB_CUDA(cudaEventRecord(ev_fork, st));
-        GPB_CUDA(cudaStreamWaitEvent(side, ev_fork, 0));
-        fps_l23_kernel<<<B, kFps3Threads, 0, side>>>(w.nx1, w.nx2, w.nx3, fps_idx2, fps_idx3);
+        if ((rc = stream_follows(side[0], st))) return rc;
+        fps_l23_kernel<<<B, kFps3Threads, 0, side[0]>>>(w.nx1, w.nx2, w.nx3, fps_idx2, fps_idx3);
         GPB_LAUNCHED();
-        GPB_CUDA(cudaEventRecord(ev_join, side));
     } else {
         fps3_kernel<<<B, kFps3Threads, 0, st>>>(pts, w.nx1, w.nx2, w.nx3, fps_idx1, fps_idx2, fps_idx3);
         GPB_LAUNCHED();
     }
 
     // level 1 (no input features)
-    if ((rc = launch_sa<0, 0>(pts, w.nx1, nullptr, enc_w, w.feat1, B, st))) return rc;
+    if ((rc = fork())) return rc;
+    if ((rc = launch_sa<0, 0>(pts, w.nx1, nullptr, enc_w, w.feat1, B, s0))) return rc;
     if (enc_tc) {
         const uint8_t *l1 = enc_tc + kEncTcGaOff + ga_tc_blob_bytes();
         if ((rc = launch_sa1_tc(pts, w.nx1, reinterpret_cast<const float *>(l1), l1 + 2048, w.feat1, B, st))) return rc;
     } else {
         if ((rc = launch_sa<0, 1>(pts, w.nx1, nullptr, enc_w, w.feat1, B, st))) return rc;
     }
+    if ((rc = join())) return rc;
+    if (forked && (rc = stream_follows(st, side[0]))) return rc;   // new_xyz2 / new_xyz3 (and fps_idx2 / fps_idx3) are complete from here on
 
-    if (side) {   // new_xyz2 / new_xyz3 (and the caller's fps_idx2 / fps_idx3) are complete from here on
-        GPB_CUDA(cudaStreamWaitEvent(st, ev_join, 0));
-        cudaEventDestroy(ev_fork);          // released by the runtime once the recorded work has completed
-        cudaEventDestroy(ev_join);
-    }
     // level 2: U = W1_feat . feat1 per source point, then the grouped part
     {
         constexpr MlpSpec m0 = enc_spec(1, 0), m1 = enc_spec(1, 1);
-        if ((rc = launch_point_gemm<96, 64, 4, 8, 128>(w.feat1, 96, enc_w + spec_offset(1, 0) + off_wf(m0), w.u[0], (size_t)B * 512, st))) return rc;
+        if ((rc = fork())) return rc;
+        if ((rc = launch_point_gemm<96, 64, 4, 8, 128>(w.feat1, 96, enc_w + spec_offset(1, 0) + off_wf(m0), w.u[0], (size_t)B * 512, s0))) return rc;
         if ((rc = launch_point_gemm<96, 64, 4, 8, 128>(w.feat1, 96, enc_w + spec_offset(1, 1) + off_wf(m1), w.u[1], (size_t)B * 512, st))) return rc;
         if (enc_tc) {
             const uint8_t *l2 = enc_tc + kEncTcL2Off;
-            if ((rc = launch_sa2_tc(w.nx1, w.nx2, w.u[0], reinterpret_cast<const float *>(l2), l2 + kEncTcL2Const, 0, w.feat2, B, st))) return rc;
+            if ((rc = launch_sa2_tc(w.nx1, w.nx2, w.u[0], reinterpret_cast<const float *>(l2), l2 + kEncTcL2Const, 0, w.feat2, B, s0))) return rc;
             l2 += kEncTcL2Const + kEncTcL2Img0;
             if ((rc = launch_sa2_tc(w.nx1, w.nx2, w.u[1], reinterpret_cast<const float *>(l2), l2 + kEncTcL2Const, 1, w.feat2, B, st))) return rc;
         } else {
-            if ((rc = launch_sa<1, 0>(w.nx1, w.nx2, w.u[0], enc_w, w.feat2, B, st))) return rc;
+            if ((rc = launch_sa<1, 0>(w.nx1, w.nx2, w.u[0], enc_w, w.feat2, B, s0))) return rc;
             if ((rc = launch_sa<1, 1>(w.nx1, w.nx2, w.u[1], enc_w, w.feat2, B, st))) return rc;
         }
+        if ((rc = join())) return rc;
     }
     // level 3
     {
         constexpr MlpSpec m0 = enc_spec(2, 0), m1 = enc_spec(2, 1);
-        if ((rc = launch_point_gemm<256, 128, 8, 4, 256>(w.feat2, 256, enc_w + spec_offset(2, 0) + off_wf(m0), w.u[0], (size_t)B * 256, st))) return rc;
+        if ((rc = fork())) return rc;
+        if ((rc = launch_point_gemm<256, 128, 8, 4, 256>(w.feat2, 256, enc_w + spec_offset(2, 0) + off_wf(m0), w.u[0], (size_t)B * 256, s0))) return rc;
         if ((rc = launch_point_gemm<256, 128, 8, 4, 256>(w.feat2, 256, enc_w + spec_offset(2, 1) + off_wf(m1), w.u[1], (size_t)B * 256, st))) return rc;
         if (enc_tc) {
             const float *consts = reinterpret_cast<const float *>(enc_tc);
             uint8_t *a0_hi = w.ga, *a0_lo = w.ga + (size_t)B * 131072;
-            if ((rc = launch_sa3_tc(w.nx2, w.nx3, w.u[0], consts, enc_tc + kEncTcConstBytes, 0, w.feat3, a0_hi, a0_lo, B, st))) return rc;
+            if ((rc = launch_sa3_tc(w.nx2, w.nx3, w.u[0], consts, enc_tc + kEncTcConstBytes, 0, w.feat3, a0_hi, a0_lo, B, s0))) return rc;
             if ((rc = launch_sa3_tc(w.nx2, w.nx3, w.u[1], consts + 992, enc_tc + kEncTcConstBytes + kEncTcScaleBytes, 1, w.feat3, a0_hi, a0_lo, B,
                                     st)))
                 return rc;
         } else {
-            if ((rc = launch_sa<2, 0>(w.nx2, w.nx3, w.u[0], enc_w, w.feat3, B, st))) return rc;
+            if ((rc = launch_sa<2, 0>(w.nx2, w.nx3, w.u[0], enc_w, w.feat3, B, s0))) return rc;
             if ((rc = launch_sa<2, 1>(w.nx2, w.nx3, w.u[1], enc_w, w.feat3, B, st))) return rc;
         }
+        if ((rc = join())) return rc;
     }
     // level 4 (GroupAll)
     if (enc_tc) return launch_groupall_tc(enc_tc + kEncTcGaOff, w.ga, w.nx3, pts_feat, B, st);

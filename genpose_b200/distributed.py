@@ -49,10 +49,14 @@ def all_gather_objects_dim0(local: torch.Tensor, n_objects: int, world: int, ran
         return local
     bounds = shard_bounds(n_objects, world)
     max_n = max(hi - lo for lo, hi in bounds)
-    pad = torch.zeros((max_n,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    # gloo has no device collectives: CUDA shards are staged through the host there (single-GPU test boxes, CPU-only ranks);
+    # under NCCL the exchange stays on the devices (NVLink / NVSwitch)
+    xdev = torch.device("cpu") if (dist.get_backend() == "gloo" and local.is_cuda) else local.device
+    pad = torch.zeros((max_n,) + tuple(local.shape[1:]), dtype=local.dtype, device=xdev)
     pad[: local.shape[0]] = local
-    gathered = torch.empty((world * max_n,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    gathered = torch.empty((world * max_n,) + tuple(local.shape[1:]), dtype=local.dtype, device=xdev)
     dist.all_gather_into_tensor(gathered, pad)
+    gathered = gathered.to(local.device)
     if all(hi - lo == max_n for lo, hi in bounds):
         return gathered
     parts = [gathered[r * max_n: r * max_n + (hi - lo)] for r, (lo, hi) in enumerate(bounds)]
@@ -75,7 +79,8 @@ def run_sharded(local_fn: Callable[[int, int], Dict[str, torch.Tensor]], n_objec
         box = [None if meta is None else {k: (m[0], m[1]) for k, m in meta.items()}]
         dist.broadcast_object_list(box, src=0)
         if meta is None:
-            dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+            on_gpu = dist.get_backend() == "nccl" or (torch.cuda.is_available() and torch.cuda.is_initialized())
+            dev = torch.device("cuda", torch.cuda.current_device()) if on_gpu else torch.device("cpu")
             meta = {k: (tuple(box[0][k][0]), box[0][k][1], dev) for k in keys}
     if meta is None:
         raise ValueError("run_sharded: no objects at all")
