@@ -627,6 +627,10 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
         int phase = kPhF0, st = 0, gi = 0, gn = 1, slot = 0, nfev = 0, n_acc = 0, n_rej = 0, status = 0;
         unsigned bar_target = 0;
         bool rejected = false, tb_pending = kOde;                             // time biases of the current group still to be computed
+        // Part of the stage combination that does not depend on the evaluation in flight: sum_{j < st} coef_j K_j (float64), built
+        // from the stored stages UNDER that evaluation's layer-1 MMAs, so that only one multiply-add per component is left between the
+        // score and the next input (the combination used to cost ~4.4 k cycles per evaluation on the critical path)
+        double pre[9] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
         const double t_end = 1e-5, direction = -1.0;                          // eps as a Python float; T0 > eps is checked by the host
         double t_cur = (double)od.T0, t_next = 0.0, h = 0.0, h_abs = 0.0, h0 = 0.0, d1 = 0.0, min_step = 0.0;
         const double rtol = (double)od.rtol, atol = (double)od.atol, n_total = (double)p.R * 9.0;
@@ -809,6 +813,23 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
                         fill_obt(0, 0, 256);
                         tb_pending = false;
                     }
+                    if (layer == 0 && cs == 0 && phase == kPhAttempt) {
+                        // stage `st` is being evaluated: the stages before it are in L2 (this thread's own stores).  Coefficients: the
+                        // row a[st+1] for st < 5, the 5th-order weights b for st == 5 (-> y_new), the error weights E for st == 6;
+                        // same summation order as the in-line form it replaces (j ascending, the new stage last).
+                        float kf[6][12];
+#pragma unroll
+                        for (int j = 0; j < 6; ++j) load_k(j, kf[j]);
+                        const int nj = st < 5 ? st : (st == 5 ? 5 : 6);
+#pragma unroll
+                        for (int c = 0; c < 9; ++c) pre[c] = 0.0;
+#pragma unroll
+                        for (int j = 0; j < 6; ++j) {
+                            const double a = st < 5 ? kRkA[st + 1][j < 5 ? j : 0] : (st == 5 ? kRkB[j] : kRkE[j]);
+#pragma unroll
+                            for (int c = 0; c < 9; ++c) pre[c] += (j < nj && valid) ? (double)kf[j][c] * a : 0.0;
+                        }
+                    }
                 }
             }
             // noise of this step, generated while the tensor core runs the head slice (the leader's warps 0-3 own the rows)
@@ -963,7 +984,7 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
                 bool boundary = false, finished = false;
                 double xn[9];                                     // input of the next evaluation (float64, rounded to fp32 on publication)
                 // start one attempt of a step from (t_cur, y, K0): RungeKutta._step_impl, rk.py; returns false when the step size underflows
-                auto begin_attempt = [&]() -> bool {
+                auto begin_attempt = [&](const double *k0_known) -> bool {   // k0_known: K_0 of the step when it is still in registers (FSAL)
                     if (h_abs < min_step) {
                         status = -1;
                         return false;
@@ -973,10 +994,18 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
                     if (direction * (t_next - t_end) > 0) t_next = t_end;
                     h = t_next - t_cur;
                     h_abs = fabs(h);
-                    float k0[12];
-                    load_k(0, k0);
+                    double k0v[9];
+                    if (k0_known) {
 #pragma unroll
-                    for (int c = 0; c < 9; ++c) xn[c] = sY[c * 128 + r] + ((valid ? (double)k0[c] : 0.0) * kRkA[1][0]) * h;
+                        for (int c = 0; c < 9; ++c) k0v[c] = k0_known[c];
+                    } else {
+                        float k0[12];
+                        load_k(0, k0);
+#pragma unroll
+                        for (int c = 0; c < 9; ++c) k0v[c] = valid ? (double)k0[c] : 0.0;
+                    }
+#pragma unroll
+                    for (int c = 0; c < 9; ++c) xn[c] = sY[c * 128 + r] + (k0v[c] * kRkA[1][0]) * h;
                     if (tid == 0) {
                         for (int j = 1; j < 6; ++j) s_times[j - 1] = (float)(t_cur + kRkC[j] * h);
                         s_times[5] = (float)(t_cur + h);
@@ -1047,7 +1076,7 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
                     else h1 = pow(0.01 / fmax(d1, d2), 1.0 / 5.0);
                     h_abs = fmin(fmin(100.0 * h0, h1), fabs(t_end - t_cur));
                     begin_step();
-                    if (!begin_attempt()) begin_denoise();
+                    if (!begin_attempt(nullptr)) begin_denoise();
                     boundary = true;
                 } else if (phase == kPhAttempt) {
                     if (valid && st < 6) store_k(st, kc);                           // K[st] (K[6] = f_new stays in registers)
@@ -1055,18 +1084,10 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
                         // next stage input: y + h * sum_j a[st+1][j] K_j for st < 5, the 5th-order solution y_new (b weights) for st == 5
                         // (the earlier stages come back from L2; every load is issued unconditionally so that all of them are in
                         // flight together, and a stage that does not take part is discarded by the select, not by a branch)
+                        // (the earlier stages' part of the sum was pre-accumulated under this evaluation's MMAs: `pre`)
                         double dy[9];
-                        float kf[5][12];
 #pragma unroll
-                        for (int j = 0; j < 5; ++j) load_k(j, kf[j]);
-#pragma unroll
-                        for (int c = 0; c < 9; ++c) dy[c] = 0.0;
-#pragma unroll
-                        for (int j = 0; j < 5; ++j) {
-                            const double a = st < 5 ? kRkA[st + 1][j] : kRkB[j];
-#pragma unroll
-                            for (int c = 0; c < 9; ++c) dy[c] += (j < st && valid) ? (double)kf[j][c] * a : 0.0;
-                        }
+                        for (int c = 0; c < 9; ++c) dy[c] = pre[c];
                         {
                             const double a = st < 5 ? kRkA[st + 1][st] : kRkB[st];
 #pragma unroll
@@ -1082,16 +1103,8 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
                         // ---- error estimate over the WHOLE batch (one controller, samplers.py:205 / rk.py _estimate_error_norm)
                         double ae = 0.0;
                         double errv[9];
-                        float kf[6][12];
 #pragma unroll
-                        for (int j = 0; j < 6; ++j) load_k(j, kf[j]);
-#pragma unroll
-                        for (int c = 0; c < 9; ++c) errv[c] = 0.0;
-#pragma unroll
-                        for (int j = 0; j < 6; ++j) {
-#pragma unroll
-                            for (int c = 0; c < 9; ++c) errv[c] += valid ? (double)kf[j][c] * kRkE[j] : 0.0;
-                        }
+                        for (int c = 0; c < 9; ++c) errv[c] = pre[c];                     // sum_{j < 6} E_j K_j, pre-accumulated
 #pragma unroll
                         for (int c = 0; c < 9; ++c) {
                             const double err = errv[c] + kc[c] * kRkE[6];
@@ -1103,7 +1116,7 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
                         grid_sum2(ae, 0.0, AE, unused);
                         const double error_norm = sqrt(AE / n_total);
                         const double SAFETY = 0.9, MIN_FACTOR = 0.2, MAX_FACTOR = 10.0, ERR_EXP = -1.0 / 5.0;
-                        bool go_on;
+                        bool go_on, k0_in_regs = false;
                         if (error_norm < 1.0) {
                             double factor = error_norm == 0.0 ? MAX_FACTOR : fmin(MAX_FACTOR, SAFETY * pow(error_norm, ERR_EXP));
                             if (rejected) factor = fmin(1.0, factor);
@@ -1128,6 +1141,7 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
 #pragma unroll
                             for (int c = 0; c < 9; ++c) sY[c * 128 + r] = sYn[c * 128 + r];
                             if (valid) store_k(0, kc);
+                            k0_in_regs = true;
                             t_cur = t_next;
                             go_on = direction * (t_cur - t_end) < 0;
                             if (go_on) begin_step();
@@ -1137,7 +1151,7 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
                             ++n_rej;
                             go_on = true;
                         }
-                        if (go_on && begin_attempt()) {
+                        if (go_on && begin_attempt(k0_in_regs ? kc : nullptr)) {
                             if (tid == 0) st_volatile_shared(&s_allowed, ld_volatile_shared(&s_allowed) + 6);
                         } else {
                             begin_denoise();

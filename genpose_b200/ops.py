@@ -195,16 +195,20 @@ class Engine:
                   _stream())
         head = (_chk(x0, torch.float32, "x0"), R, K, num_steps, float(snr), _chk(obj_bias, torch.float32, "obj_bias"),
                 self.trunk_w.data_ptr())
-        if precision != "fp32":
-            lib.check(L.gpb_set_tc_team(int(team)), "set_tc_team")
-        if precision == "bf16x3":
-            lib.check(L.gpb_sample_pc_tc(*head, self.trunk_tc.data_ptr(), _chk(pts_center, torch.float32, "pts_center"), *common),
-                      "sample_pc_tc")
-        elif precision == "f16x2":
-            lib.check(L.gpb_sample_pc_tc16(*head, self.trunk_tc16().data_ptr(), _chk(pts_center, torch.float32, "pts_center"),
-                                           *common[:-1], 0, common[-1]), "sample_pc_tc16")
-        else:
-            lib.check(L.gpb_sample_pc(*head, _chk(pts_center, torch.float32, "pts_center"), *common), "sample_pc")
+        if precision != "fp32" and team:
+            lib.check(L.gpb_set_tc_team(int(team)), "set_tc_team")          # a forced team size holds for this launch only
+        try:
+            if precision == "bf16x3":
+                lib.check(L.gpb_sample_pc_tc(*head, self.trunk_tc.data_ptr(), _chk(pts_center, torch.float32, "pts_center"), *common),
+                          "sample_pc_tc")
+            elif precision == "f16x2":
+                lib.check(L.gpb_sample_pc_tc16(*head, self.trunk_tc16().data_ptr(), _chk(pts_center, torch.float32, "pts_center"),
+                                               *common[:-1], 0, common[-1]), "sample_pc_tc16")
+            else:
+                lib.check(L.gpb_sample_pc(*head, _chk(pts_center, torch.float32, "pts_center"), *common), "sample_pc")
+        finally:
+            if precision != "fp32" and team:
+                L.gpb_set_tc_team(0)
         return (mean_x, process) if return_process else mean_x
 
     # ---- a10: ODE sampler --------------------------------------------------------------------------------
@@ -236,14 +240,18 @@ class Engine:
         tail = (_chk(pts_center, torch.float32, "pts_center"), pose.data_ptr(), stats.data_ptr(),
                 0 if process is None else process.data_ptr(), int(process_cap), 0 if te is None else te.data_ptr(), n_te,
                 ws.data_ptr(), ws.numel(), _stream())
-        if precision != "fp32":
-            lib.check(L.gpb_set_tc_team(int(team)), "set_tc_team")
-        if precision == "bf16x3":
-            lib.check(L.gpb_sample_ode_tc(*head, self.trunk_tc.data_ptr(), *tail), "sample_ode_tc")
-        elif precision == "f16x2":
-            lib.check(L.gpb_sample_ode_tc16(*head, self.trunk_tc16().data_ptr(), *tail), "sample_ode_tc16")
-        else:
-            lib.check(L.gpb_sample_ode(*head, *tail), "sample_ode")
+        if precision != "fp32" and team:
+            lib.check(L.gpb_set_tc_team(int(team)), "set_tc_team")          # a forced team size holds for this launch only
+        try:
+            if precision == "bf16x3":
+                lib.check(L.gpb_sample_ode_tc(*head, self.trunk_tc.data_ptr(), *tail), "sample_ode_tc")
+            elif precision == "f16x2":
+                lib.check(L.gpb_sample_ode_tc16(*head, self.trunk_tc16().data_ptr(), *tail), "sample_ode_tc16")
+            else:
+                lib.check(L.gpb_sample_ode(*head, *tail), "sample_ode")
+        finally:
+            if precision != "fp32" and team:
+                L.gpb_set_tc_team(0)
         if not return_process:
             return pose, stats
         if te is None:
