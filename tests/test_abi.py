@@ -52,7 +52,9 @@ def test_argument_validation_without_gpu(built):
     for fn in (built.gpb_sample_pc_tc, built.gpb_sample_pc_tc16):
         extra = (None,) if fn is built.gpb_sample_pc_tc16 else ()
         assert fn(None, 0, 50, 500, 0.16, None, None, None, None, None, 0, None, None, None, None, 0, *extra, None) == 0
-    assert built.gpb_sample_ode_tc16(None, 0, 50, 0.55, 1e-5, 1e-5, 1000, None, None, None, None, None, None, None, 0, None) == 0
+    assert built.gpb_sample_ode_tc16(None, 0, 50, 0.55, 1e-5, 1e-5, 1000, None, None, None, None, None, None, None, 0, None, 0, None, 0,
+                                     None) == 0
+    assert built.gpb_set_tc_team(3) == -1 and built.gpb_set_tc_team(0) == 0
 
 
 def test_sass_is_sm100a_only():
