@@ -934,6 +934,10 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
             for (int hh = 0; hh < kTouched; ++hh)
 #pragma unroll
                 for (int c = 0; c < 3; ++c) o[hh][c] += sFpart[r * 12 + 3 * hh + c];
+            // step constants of the update, computed before the team's partials arrive (they depend on t only)
+            const float inv_std = 1.0f / stdv;   // one IEEE division per row and step instead of nine (<= 1.5 ulp from f / std, scorenet.py:217)
+            const float g_sde = sigma * kGCoef, g2_sde = g_sde * g_sde, g_sqrt_step = g_sde * sqrt_step;   // ve_sde diffusion (sde.py:20-24)
+            const float nsum_scale = kNormSumScale * fminf(sigma, 1.0f);   // fixed-point scale of the reduction word: norms grow like 1 / sigma(t)
             float f[9];
             if constexpr (kTeam == 1) {
 #pragma unroll
@@ -1220,7 +1224,6 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
             } else {
                 // ---- every rank: score, batch-mean gradient norm (published by the leaders), update — redundantly, bit-identically ----
                 float gr[9], n2 = 0.f;
-                const float inv_std = 1.0f / stdv;   // one IEEE division per row and step instead of nine (<= 1.5 ulp from f / std, scorenet.py:217)
 #pragma unroll
                 for (int c = 0; c < 9; ++c) {
                     gr[c] = (f[c] + sOw[9 * 256 + c]) * inv_std;
@@ -1235,13 +1238,6 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
                 //      RED.release counter + acquire poll + __ldcg of the partials, 2.8 k + 0.9 k cycles per step; per-warp tagged words
                 //      polled by every warp 8.2 k; tagged tile sums polled by one warp per CTA 4.4 k.)  A tile whose sum is NaN or
                 //      >= 2^22 marks the word poisoned and the step's norm becomes NaN, as it would be (or diverge) in the reference.
-                // the step's constants and the predictor drift (0 - g^2 s) dt do not depend on the batch norm: before the grid wait
-                const float g_sde = sigma * kGCoef, g2_sde = g_sde * g_sde, g_sqrt_step = g_sde * sqrt_step;   // ve_sde diffusion (sde.py:20-24)
-                float pd[9];
-#pragma unroll
-                for (int c = 0; c < 9; ++c) pd[c] = (0.0f - g2_sde * gr[c]) * step_size;
-                // fixed-point scale of the step's reduction word: score norms grow like 1 / sigma(t), so the scale follows min(sigma, 1)
-                const float nsum_scale = kNormSumScale * fminf(sigma, 1.0f);
                 if (leader) {
                     const float wsum = warp_sum(valid ? sqrtf(n2) : 0.f);
                     if (lane == 0) s_red[q] = wsum;
@@ -1255,6 +1251,10 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
                         red_relaxed_add_u64(p.acc + step, (1ull << 56) | (ok ? 0ull : (1ull << 48)) | fx);
                     }
                 }
+                // the predictor drift (0 - g^2 s) dt does not depend on the batch norm: computed while the word is in flight
+                float pd[9];
+#pragma unroll
+                for (int c = 0; c < 9; ++c) pd[c] = (0.0f - g2_sde * gr[c]) * step_size;
                 if (tid == 0) {
                     unsigned long long v;
                     do {
