@@ -123,32 +123,78 @@ __device__ __forceinline__ void fps_level(const float *sx, const float *sy, cons
     __syncthreads();
 }
 
-// The same chain as two kernels, so that levels 2 and 3 (218 of the 896 dependent rounds... 384 rounds) can run on a side stream
-// BESIDE level 1's set abstraction, which needs new_xyz1 only: fps_l1_kernel = level 1, fps_l23_kernel = levels 2 and 3 from new_xyz1.
-__global__ void __launch_bounds__(kFps3Threads)
+// One furthest-point-sampling level with ONE point per thread (threads >= N idle but take part in the barrier): the per-round
+// dependent chain is one distance + one min instead of P of them, and the cross-warp step is a second redux over the (<= 32) warp
+// winners read one per lane instead of every thread scanning all of them.  Same keys, same tie rule, same winner as fps_level.
+template <int N, int M, int NT>
+__device__ __forceinline__ void fps_level_1pt(const float *sx, const float *sy, const float *sz, float *ox, float *oy, float *oz,
+                                              int *idx_out, unsigned long long (*warp_best)[32]) {
+    static_assert(N <= NT && NT <= 1024 && NT % 32 == 0, "fps_level_1pt: one point per thread");
+    constexpr int NW = NT / 32;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool mine = tid < N;
+    const float px = mine ? sx[tid] : 0.f, py = mine ? sy[tid] : 0.f, pz = mine ? sz[tid] : 0.f;
+    float pt = 1e10f;
+    const unsigned pk = mine ? ~__brev((unsigned)tid) : 0u;   // larger = higher priority on ties; an idle thread's key (0, 0) never wins
+    if (tid == 0) {
+        ox[0] = sx[0];
+        oy[0] = sy[0];
+        oz[0] = sz[0];
+        if (idx_out) idx_out[0] = 0;
+    }
+    float cx = sx[0], cy = sy[0], cz = sz[0];
+    for (int j = 1; j < M; ++j) {
+        pt = fminf(dist2_ref(px, py, pz, cx, cy, cz), pt);
+        const unsigned d = mine ? __float_as_uint(pt) : 0u;   // pt >= 0: uint order == float order
+        const unsigned wd = __reduce_max_sync(0xffffffffu, d);
+        const unsigned wk = __reduce_max_sync(0xffffffffu, d == wd ? pk : 0u);
+        if (lane == 0) warp_best[j & 1][warp] = ((unsigned long long)wd << 32) | wk;
+        __syncthreads();
+        const unsigned long long v = lane < NW ? warp_best[j & 1][lane] : 0ull;
+        const unsigned hi = (unsigned)(v >> 32), lo = (unsigned)(v & 0xffffffffull);
+        const unsigned gd = __reduce_max_sync(0xffffffffu, hi);
+        const unsigned gk = __reduce_max_sync(0xffffffffu, hi == gd ? lo : 0u);
+        const int win = (int)__brev(~gk);
+        cx = sx[win];
+        cy = sy[win];
+        cz = sz[win];
+        if (tid == 0) {
+            ox[j] = cx;
+            oy[j] = cy;
+            oz[j] = cz;
+            if (idx_out) idx_out[j] = win;
+        }
+    }
+    __syncthreads();
+}
+
+// The same chain as two kernels, so that levels 2 and 3 (384 of the 896 dependent rounds) can run on a side stream BESIDE level 1's
+// set abstraction, which needs new_xyz1 only: fps_l1_kernel = level 1 (1024 threads, one point each), fps_l23_kernel = levels 2 and 3
+// from new_xyz1 (512 threads).
+__global__ void __launch_bounds__(1024)
 fps_l1_kernel(const float *__restrict__ pts /* [B,1024,3] */, float *__restrict__ nx1, int *__restrict__ idx1) {
     __shared__ float s0[3][1024], s1[3][512];
-    __shared__ unsigned long long warp_best[2][8];
+    __shared__ unsigned long long warp_best[2][32];
     const int b = blockIdx.x, tid = threadIdx.x;
     const float *p = pts + (size_t)b * 1024 * 3;
-    for (int i = tid; i < 1024 * 3; i += kFps3Threads) s0[i % 3][i / 3] = p[i];
+    for (int i = tid; i < 1024 * 3; i += 1024) s0[i % 3][i / 3] = p[i];
     __syncthreads();
-    fps_level<1024, 512>(s0[0], s0[1], s0[2], s1[0], s1[1], s1[2], idx1 ? idx1 + (size_t)b * 512 : nullptr, warp_best);
-    for (int i = tid; i < 512 * 3; i += kFps3Threads) nx1[(size_t)b * 512 * 3 + i] = s1[i % 3][i / 3];
+    fps_level_1pt<1024, 512, 1024>(s0[0], s0[1], s0[2], s1[0], s1[1], s1[2], idx1 ? idx1 + (size_t)b * 512 : nullptr, warp_best);
+    for (int i = tid; i < 512 * 3; i += 1024) nx1[(size_t)b * 512 * 3 + i] = s1[i % 3][i / 3];
 }
-__global__ void __launch_bounds__(kFps3Threads)
+__global__ void __launch_bounds__(512)
 fps_l23_kernel(const float *__restrict__ nx1 /* [B,512,3] */, float *__restrict__ nx2, float *__restrict__ nx3, int *__restrict__ idx2,
                int *__restrict__ idx3) {
     __shared__ float s1[3][512], s2[3][256], s3[3][128];
-    __shared__ unsigned long long warp_best[2][8];
+    __shared__ unsigned long long warp_best[2][32];
     const int b = blockIdx.x, tid = threadIdx.x;
     const float *p = nx1 + (size_t)b * 512 * 3;
-    for (int i = tid; i < 512 * 3; i += kFps3Threads) s1[i % 3][i / 3] = p[i];
+    for (int i = tid; i < 512 * 3; i += 512) s1[i % 3][i / 3] = p[i];
     __syncthreads();
-    fps_level<512, 256>(s1[0], s1[1], s1[2], s2[0], s2[1], s2[2], idx2 ? idx2 + (size_t)b * 256 : nullptr, warp_best);
-    fps_level<256, 128>(s2[0], s2[1], s2[2], s3[0], s3[1], s3[2], idx3 ? idx3 + (size_t)b * 128 : nullptr, warp_best);
-    for (int i = tid; i < 256 * 3; i += kFps3Threads) nx2[(size_t)b * 256 * 3 + i] = s2[i % 3][i / 3];
-    for (int i = tid; i < 128 * 3; i += kFps3Threads) nx3[(size_t)b * 128 * 3 + i] = s3[i % 3][i / 3];
+    fps_level_1pt<512, 256, 512>(s1[0], s1[1], s1[2], s2[0], s2[1], s2[2], idx2 ? idx2 + (size_t)b * 256 : nullptr, warp_best);
+    fps_level_1pt<256, 128, 512>(s2[0], s2[1], s2[2], s3[0], s3[1], s3[2], idx3 ? idx3 + (size_t)b * 128 : nullptr, warp_best);
+    for (int i = tid; i < 256 * 3; i += 512) nx2[(size_t)b * 256 * 3 + i] = s2[i % 3][i / 3];
+    for (int i = tid; i < 128 * 3; i += 512) nx3[(size_t)b * 128 * 3 + i] = s3[i % 3][i / 3];
 }
 
 __global__ void __launch_bounds__(kFps3Threads)
@@ -682,10 +728,10 @@ static int encode_impl(const float *pts, int B, const float *enc_w, const uint8_
     // Furthest-point sampling is 896 dependent arg-max rounds on B CTAs: level 1 (512 rounds) first, then levels 2 and 3 (384 rounds)
     // on side stream 0 beside level 1's set abstraction, which only needs new_xyz1; joined in front of level 2.
     if (forked) {
-        fps_l1_kernel<<<B, kFps3Threads, 0, st>>>(pts, w.nx1, fps_idx1);
+        fps_l1_kernel<<<B, 1024, 0, st>>>(pts, w.nx1, fps_idx1);
         GPB_LAUNCHED();
         if ((rc = stream_follows(side[0], st))) return rc;
-        fps_l23_kernel<<<B, kFps3Threads, 0, side[0]>>>(w.nx1, w.nx2, w.nx3, fps_idx2, fps_idx3);
+        fps_l23_kernel<<<B, 512, 0, side[0]>>>(w.nx1, w.nx2, w.nx3, fps_idx2, fps_idx3);
         GPB_LAUNCHED();
     } else {
         fps3_kernel<<<B, kFps3Threads, 0, st>>>(pts, w.nx1, w.nx2, w.nx3, fps_idx1, fps_idx2, fps_idx3);
