@@ -80,7 +80,7 @@ __device__ void top_eigenvector4(double A[4][4], double *vec) {
 
 __global__ void __launch_bounds__(kMaxK)
 rank_pool_kernel(const float *__restrict__ pose, const float *__restrict__ energy, int K, int keep,
-                 float *__restrict__ sorted_pose, float *__restrict__ sorted_energy, float *__restrict__ pooled) {
+                 float *__restrict__ sorted_pose, float *__restrict__ sorted_energy, float *__restrict__ pooled, int *__restrict__ order) {
     __shared__ float sp[kMaxK][9];
     __shared__ float se[kMaxK][2];
     __shared__ float srt[kMaxK][9];   // sorted pose
@@ -108,6 +108,10 @@ rank_pool_kernel(const float *__restrict__ pose, const float *__restrict__ energ
         if (sorted_energy) {
             sorted_energy[((size_t)b * K + rr) * 2 + 0] = er;
             sorted_energy[((size_t)b * K + rt) * 2 + 1] = et;
+        }
+        if (order) {   // order[b, rank, 0 / 1] = index of the candidate at that rank by rotation / translation energy
+            order[((size_t)b * K + rr) * 2 + 0] = i;
+            order[((size_t)b * K + rt) * 2 + 1] = i;
         }
     }
     __syncthreads();
@@ -159,12 +163,12 @@ rank_pool_kernel(const float *__restrict__ pose, const float *__restrict__ energ
 using namespace gpb;
 
 extern "C" int gpb_rank_pool(const float *pose, const float *energy, int B, int K, int keep, float *sorted_pose,
-                             float *sorted_energy, float *pooled_RT, void *stream) {
+                             float *sorted_energy, float *pooled_RT, int *order, void *stream) {
     GPB_REQUIRE(B >= 0 && K >= 1 && K <= kMaxK, "rank_pool: need B >= 0 and 1 <= K <= %d", kMaxK);
     GPB_REQUIRE(keep >= 1 && keep <= K, "rank_pool: need 1 <= keep <= K");
     if (B == 0) return GPB_OK;
     GPB_REQUIRE(pose && energy, "rank_pool: NULL buffer");
-    rank_pool_kernel<<<B, kMaxK, 0, (cudaStream_t)stream>>>(pose, energy, K, keep, sorted_pose, sorted_energy, pooled_RT);
+    rank_pool_kernel<<<B, kMaxK, 0, (cudaStream_t)stream>>>(pose, energy, K, keep, sorted_pose, sorted_energy, pooled_RT, order);
     GPB_LAUNCHED();
     return GPB_OK;
 }

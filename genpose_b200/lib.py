@@ -42,7 +42,7 @@ SIGNATURES = {
     "gpb_sample_pc_tc16": (_i, [_vp, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _u64, _vp, _vp, _vp, _vp, _sz, _vp, _vp]),
     "gpb_sample_ode_tc16": (_i, [_vp, _i, _i, _d, _d, _d, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _vp, _sz, _vp]),
     "gpb_energy": (_i, [_vp, _i, _i, _f, _vp, _vp, _vp, _vp, _vp]),
-    "gpb_rank_pool": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "gpb_rank_pool": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "gpb_prepare_clouds": (_i, [_vp, _vp, ctypes.c_longlong, ctypes.c_longlong, _i, _i, _i, _vp, ctypes.POINTER(ctypes.c_float), _vp, _u64,
                                 _vp, _vp, _vp]),
     "gpb_selftest_umma": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),

@@ -214,7 +214,7 @@ class Engine:
     # ---- a10: ODE sampler --------------------------------------------------------------------------------
     def sample_ode(self, obj_bias: torch.Tensor, pts_center: torch.Tensor, x0: torch.Tensor, K: int, T0: float = 1.0,
                    rtol: float = 1e-5, atol: float = 1e-5, denoise_steps: int = 1000, precision: str = "fp32", team: int = 0,
-                   return_process: bool = False, t_eval=None, process_cap: int = 96):
+                   return_process: bool = False, t_eval=None, process_cap: int = 192):
         """cond_ode_sampler (samplers.py:163-227): RK45 with SciPy's controller on device -> (pose [R,9] float64, stats [4]).
         precision and team as in sample_pc.  return_process: additionally the trajectory `xs` the reference returns
         (samplers.py:206, :220-224) as float64 [n, R, 9] — the solver's accepted states (n = accepted + 1) or, with
@@ -271,14 +271,17 @@ class Engine:
         return out
 
 
-def rank_pool(pose: torch.Tensor, energy: torch.Tensor, ratio: float = 0.6, want_pooled: bool = True):
+def rank_pool(pose: torch.Tensor, energy: torch.Tensor, ratio: float = 0.6, want_pooled: bool = True, want_order: bool = False):
     """sort_poses_by_energy (reward.py:131-155) + sort_sRT_by_energy(ratio,'average') pooling
-    (sgpa_utils.py:897-954).  pose [B,K,9], energy [B,K,2] -> sorted_pose, sorted_energy, pooled_RT [B,4,4]."""
+    (sgpa_utils.py:897-954).  pose [B,K,9], energy [B,K,2] -> sorted_pose, sorted_energy, pooled_RT [B,4,4]
+    (+ order [B,K,2] int32 = the sort's indices per energy column when want_order)."""
     B, K, _ = pose.shape
     keep = max(1, int(K * ratio))                                   # sgpa_utils.py:912
     sp = torch.empty_like(pose)
     se = torch.empty_like(energy)
     rt = torch.empty(B, 4, 4, dtype=torch.float32, device=pose.device) if want_pooled else None
+    order = torch.empty(B, K, 2, dtype=torch.int32, device=pose.device) if want_order else None
     lib.check(lib.load().gpb_rank_pool(_chk(pose, torch.float32, "pose"), _chk(energy, torch.float32, "energy"), B, K, keep,
-                                       sp.data_ptr(), se.data_ptr(), 0 if rt is None else rt.data_ptr(), _stream()), "rank_pool")
-    return sp, se, rt
+                                       sp.data_ptr(), se.data_ptr(), 0 if rt is None else rt.data_ptr(),
+                                       0 if order is None else order.data_ptr(), _stream()), "rank_pool")
+    return (sp, se, rt, order) if want_order else (sp, se, rt)

@@ -218,10 +218,12 @@ GPB_API int gpb_energy(const float *pose, int R, int K, float t, const float *ob
 /* replaces sort_poses_by_energy (networks/reward.py:131-155) + sort_sRT_by_energy(ratio,'average')
  * (utils/sgpa_utils.py:897-954) + average_quaternion_batch (utils/misc.py:227-249).
  *   pose [B,K,9], energy [B,K,2] -> sorted_pose [B,K,9], sorted_energy [B,K,2], pooled_RT [B,4,4].
- * K <= 128; keep = max(1, int(K * ratio)) is evaluated by the caller (sgpa_utils.py:912).  sorted_pose,
- * sorted_energy and pooled_RT may each be NULL to skip that output. */
+ * K <= 128; keep = max(1, int(K * ratio)) is evaluated by the caller (sgpa_utils.py:912).  order [B,K,2] i32: the
+ * candidate index at every rank by rotation (…,0) and translation (…,1) energy = torch.sort(energy, dim=1, descending=True)'s
+ * indices (reward.py:145), for callers that reorder their own (e.g. float64) copies of the poses.  sorted_pose, sorted_energy,
+ * pooled_RT and order may each be NULL to skip that output. */
 GPB_API int gpb_rank_pool(const float *pose, const float *energy, int B, int K, int keep, float *sorted_pose,
-                  float *sorted_energy, float *pooled_RT, void *stream);
+                  float *sorted_energy, float *pooled_RT, int *order, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
  * (3) BOOK-KEEPING

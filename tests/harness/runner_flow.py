@@ -93,7 +93,7 @@ class StandIn:
         calls["energy"] += 1
         return 0
 
-    def gpb_rank_pool(self, pose, energy, B, K_, keep, sp, se, rt, stream):
+    def gpb_rank_pool(self, pose, energy, B, K_, keep, sp, se, rt, order, stream):
         p, e = arr(pose, (B, K_, 9)), arr(energy, (B, K_, 2))
         for b in range(B):
             o_r = np.argsort(-e[b, :, 0], kind="stable")
@@ -102,7 +102,7 @@ class StandIn:
                 arr(sp, (B, K_, 9))[b] = np.concatenate([p[b, o_r, :6], p[b, o_t, 6:]], axis=1)
             if se:
                 arr(se, (B, K_, 2))[b] = np.stack([e[b, o_r, 0], e[b, o_t, 1]], axis=1)
-        assert not rt
+        assert not rt and not order
         calls["rank_pool"] += 1
         return 0
 

@@ -46,7 +46,7 @@ def test_argument_validation_without_gpu(built):
     # invalid arguments are rejected before any CUDA call, with a message
     assert built.gpb_furthest_point_sampling(1, 4, 8, None, None, None, None) == -1
     assert b"m<=n" in built.gpb_last_error_string()
-    assert built.gpb_rank_pool(None, None, 1, 500, 1, None, None, None, None) == -1
+    assert built.gpb_rank_pool(None, None, 1, 500, 1, None, None, None, None, None) == -1
     assert built.gpb_encode(None, 0, None, None, None, 0, None, None, None, None) == 0      # empty batch is a no-op
     # the samplers: empty batch is a no-op, a too-small K is refused by the tensor-core entries (three- and two-product alike)
     for fn in (built.gpb_sample_pc_tc, built.gpb_sample_pc_tc16):
