@@ -180,7 +180,7 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
     float *sFpart = reinterpret_cast<float *>(smem + kOffFpart);
     float *sMail = reinterpret_cast<float *>(smem + kOffMail);
     __shared__ __align__(8) uint64_t bar_full[kSlots], bar_empty[kSlots], bar_acc_full[2], bar_acc_empty[2], bar_x_ready, bar_a_ready[2],
-        bar_mail[2];
+        bar_h1_ready[4], bar_mail[2];
     __shared__ uint32_t s_tmem_base;
     __shared__ float s_red[8];
     // ODE mode: evaluation bookkeeping shared with the producer / MMA warps, the evaluation group in flight, fp64 reduction scratch
@@ -212,6 +212,7 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
         // interchangeable (four fast warps arriving twice would otherwise complete the first-half phase for all eight)
         mbar_init(&bar_a_ready[0], kTcRowWarps);
         mbar_init(&bar_a_ready[1], kTcRowWarps);
+        for (int qd = 0; qd < 4; ++qd) mbar_init(&bar_h1_ready[qd], kTcRowWarps);   // layer 0 -> layer 1: the A operand in QUARTERS
         mbar_init(&bar_mail[0], 1);                // one local arrive.expect_tx per use; the peers' st.async complete the bytes
         mbar_init(&bar_mail[1], 1);
         fence_mbar_init();
@@ -277,7 +278,7 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
         // one elected lane issues each group of tcgen05.mma / tcgen05.commit.
         const uint32_t ring = smem_u32(sRing);
         const uint32_t t_ahi = tmem_base + kColAhi, t_alo = tmem_base + kColAlo;
-        uint32_t u = 0, it = 0, xr = 0, ar = 0;
+        uint32_t u = 0, it = 0, xr = 0, ar = 0, hr = 0;
         // wait for n_slots consecutive ring slots starting at stream position `it`: lane l polls slot l (one wait latency)
         auto wait_slots = [&](int n_slots) {
             if (lane < n_slots) {
@@ -324,14 +325,73 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
             // ---- units with K = 256: layer 1 (P2: two 128-column units) and this rank's head slice (128 + 64 columns) ----
             for (int unit = 0; unit < 2 + TS::kHeadUnits; ++unit) {
                 if (ds) tq = clock64();
-                // Units 0 and 2 are the first consumers of a freshly written A operand (h1 / pf).  The row warps publish it in
-                // two halves (K columns [0,128) as soon as the first accumulator unit is converted, [128,256) after the second),
-                // so the first 8 K-steps are issued while the second half is still in the epilogue.
-                const bool split = unit == 0 || unit == 2;
+                // Units 0 and 2 are the first consumers of a freshly written A operand (h1 / pf).  The row warps publish pf in two
+                // halves (K columns [0,128) once layer 1's MMAs have released the A region, [128,256) after the second unit's
+                // epilogue), so the first 8 K-steps of the heads are issued while the second half is still being converted; h1 comes
+                // in quarters (below).
+                const bool split = unit == 2;
                 const uint32_t b = u & 1u, n = u >> 1;
                 const uint32_t d = tmem_base + kColD + b * 128u;
                 const bool small = TS::kSmallUnit && unit == 2 + TS::kHeadUnits - 1;   // the 64-column unit (team 4): 2 K-chunks per slot
-                if (!small) {
+                if (unit == 0) {
+                    // Layer 1, unit a: the first consumer of h1, which layer 0's epilogue publishes in QUARTERS (nothing else reads the
+                    // A region then, so a quarter is stored as soon as it is converted).  Row thread (q, cs) converts h1 columns
+                    // [64 cs, 64 cs + 64) of unit a and [128 + 64 cs, ...) of unit b, 32 at a time, so quarter g holds the K-steps
+                    // {base, base + 1, base + 4, base + 5}, base = 8 (g / 2) + 2 (g % 2): four issue groups of 4 K-steps; the
+                    // accumulation order inside the unit changes, nothing else.
+                    constexpr int kUnitSlots = kW16 ? 4 : 8;
+                    if (ds) tq = clock64();
+                    wait_slots(kUnitSlots);
+                    if (ds) { w_full += clock64() - tq; tq = clock64(); }
+                    const uint32_t s_first = it % kSlots;
+                    auto slot_base = [&](int sl) {
+                        uint32_t sidx = s_first + (uint32_t)sl;
+                        sidx = sidx >= (uint32_t)kSlots ? sidx - (uint32_t)kSlots : sidx;
+                        return sidx;
+                    };
+                    for (int g = 0; g < 4; ++g) {
+                        if (ds) tq = clock64();
+                        mbar_wait(&bar_h1_ready[g], hr & 1u);
+                        if (ds) {
+                            w_a += clock64() - tq;
+                            if (g == 0) ds[3] = clock64();
+                            tq = clock64();
+                        }
+                        if (g == 0) mbar_wait(&bar_acc_empty[b], (n & 1u) ^ 1u);
+                        tc_fence_after_sync();
+                        if (ds) { w_acc += clock64() - tq; tq = clock64(); }
+                        const int base = 8 * (g >> 1) + 2 * (g & 1);
+                        if (elect_one_sync()) {
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const int ks = base + (e & 1) + 4 * (e >> 1);             // K-step (16 inputs) of the unit
+                                const uint32_t ac = (uint32_t)ks * 8u;                    // K index / 2
+                                const bool acc = (g | e) != 0;
+                                if constexpr (kW16) {
+                                    const uint32_t sb = ring + slot_base(ks >> 2) * kSlotBytes;
+                                    const uint64_t b_w = make_smem_desc(sb + 2u * (uint32_t)(ks & 3) * kLboB, kLboB, kSbo);
+                                    umma_bf16_ts(d, t_ahi + ac, b_w, idesc128w, acc);
+                                    umma_bf16_ts(d, t_alo + ac, b_w, idesc128w, true);
+                                } else {
+                                    const uint32_t sb = ring + slot_base(ks >> 1) * kSlotBytes;
+                                    const uint64_t b_hi = make_smem_desc(sb + 2u * (uint32_t)(ks & 1) * kLboB, kLboB, kSbo);
+                                    const uint64_t b_lo = make_smem_desc(sb + 8192u + 2u * (uint32_t)(ks & 1) * kLboB, kLboB, kSbo);
+                                    umma_bf16_ts(d, t_ahi + ac, b_hi, idesc128, acc);
+                                    umma_bf16_ts(d, t_alo + ac, b_hi, idesc128, true);
+                                    umma_bf16_ts(d, t_ahi + ac, b_lo, idesc128, true);
+                                }
+                            }
+                            if (g & 1) {   // quarters 2 (g / 2) and 2 (g / 2) + 1 together cover K-steps [8 (g / 2), 8 (g / 2) + 8): their slots are done
+                                for (int sl = 0; sl < kUnitSlots / 2; ++sl) umma_commit(&bar_empty[slot_base((g >> 1) * (kUnitSlots / 2) + sl)]);
+                            }
+                            if (g == 3) umma_commit(&bar_acc_full[b]);
+                        }
+                        __syncwarp();
+                        if (ds) { w_issue += clock64() - tq; tq = clock64(); }
+                    }
+                    ++hr;
+                    it += (uint32_t)kUnitSlots;
+                } else if (!small) {
                     // 8 slots = 16 K-steps, issued as one group (unit 1) or two groups of 4 slots (units 0, 2).  Every slot wait costs
                     // the MMA warp ~250 cycles even when the data is there (measured: groups of 2 slots, 7.45 -> 8.0 ms per launch), so
                     // groups are as large as the A-operand hand-off allows.  (Also measured without effect: a 10th ring slot, one private
@@ -342,8 +402,8 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
                         wait_slots(per);                           // before the operand wait (see layer 0)
                         if (ds) { w_full += clock64() - tq; tq = clock64(); }
                         if (split) {
-                            mbar_wait(&bar_a_ready[g], (ar >> 1) & 1u);   // waits alternate g = 0, 1: phase index of either barrier = ar / 2
-                            ++ar;
+                            mbar_wait(&bar_a_ready[g], ar & 1u);            // one phase of either barrier per step (layer 1 -> heads)
+                            if (g == 1) ++ar;
                         }
                         if (ds) {
                             w_a += clock64() - tq;
@@ -752,6 +812,46 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
 #pragma unroll 1
             for (int layer = 0; layer < 2; ++layer) {
                 const float *bias = sBias + layer * 256 + cs * 64;
+                if (layer == 0) {
+                    // Layer 0 -> layer 1 in QUARTERS.  Nothing but layer 0's own MMAs reads the A region now (the previous step's
+                    // head MMAs completed before x was published), and those need only x in A_hi[0,24): once BOTH layer-0
+                    // accumulators are complete — ten small MMAs, ~0.3 k cycles apart — a 32-column piece of h1 can be stored as
+                    // soon as it is converted.  The MMA warp starts layer 1 on the first quarter (~0.55 k cycles earlier than on
+                    // the first half); quarter g = K-steps {base, base + 1, base + 4, base + 5}, base = 8 (g / 2) + 2 (g % 2).
+                    const uint32_t b0 = u & 1u, n0 = u >> 1, b1 = (u + 1u) & 1u, n1 = (u + 1u) >> 1;
+                    uint32_t v[32], h16[16], l16[16];
+                    mbar_wait(&bar_acc_full[b0], n0 & 1u);
+                    if (ds) ds[1] = clock64();
+                    tc_fence_after_sync();
+                    tmem_ld32(tm_row + kColD + b0 * 128u + (uint32_t)cs * 64u, v);
+                    tmem_ld_wait();
+                    relu_split32<kW16>(v, bias, h16, l16);
+                    mbar_wait(&bar_acc_full[b1], n1 & 1u);          // every layer-0 MMA has read x
+                    tc_fence_after_sync();
+#pragma unroll
+                    for (int qd = 0; qd < 4; ++qd) {
+                        const uint32_t bq = qd < 2 ? b0 : b1;
+                        const uint32_t a_col = (uint32_t)(qd >> 1) * 64u + (uint32_t)cs * 32u + (uint32_t)(qd & 1) * 16u;
+                        tmem_st16(tm_row + kColAhi + a_col, h16);
+                        tmem_st16(tm_row + kColAlo + a_col, l16);
+                        if (qd < 3) {   // the next 32 accumulator columns travel while the stores drain
+                            const uint32_t bn = qd + 1 < 2 ? b0 : b1;
+                            tmem_ld32(tm_row + kColD + bn * 128u + (uint32_t)cs * 64u + (uint32_t)((qd + 1) & 1) * 32u, v);
+                            tmem_ld_wait();
+                        }
+                        tmem_st_wait();
+                        tc_fence_before_sync();
+                        __syncwarp();
+                        if (lane == 0) {
+                            mbar_arrive(&bar_h1_ready[qd]);
+                            if (qd == 0) mbar_arrive(&bar_acc_empty[b0]);      // (its second 32 columns are in registers by now)
+                            if (qd == 2) mbar_arrive(&bar_acc_empty[b1]);
+                        }
+                        if (qd < 3) relu_split32<kW16>(v, bias + (qd + 1 < 2 ? 0 : 128) + ((qd + 1) & 1) * 32, h16, l16);
+                    }
+                    u += 2;
+                    if (ds) ds[2] = clock64();
+                } else {
                 uint32_t hi[32], lo[32];
                 {   // unit a: columns [0,128) of the layer; this thread: [cs*64, +64)
                     const uint32_t b = u & 1u, n = u >> 1;
@@ -804,6 +904,7 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
                     ++u;
                 }
                 if (ds) ds[2 + 2 * layer] = clock64();
+                }
                 if constexpr (kOde) {
                     // First evaluation of a group: its time biases are only needed by the head epilogue, so they are computed
                     // here, after h1 has been handed to the MMA warp — under the layer-1 MMAs instead of in front of layer 0.
