@@ -878,15 +878,16 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
                     tc_fence_after_sync();
                     tmem_st32(tm_row + kColAhi + (uint32_t)cs * 32u, hi);
                     tmem_st32(tm_row + kColAlo + (uint32_t)cs * 32u, lo);
+                    // first half of the new A operand (K columns [0,128)) is in tensor memory: let the MMA warp start on it at once
+                    // (the heads' first eight K-steps then cover the conversion of the second half)
+                    tmem_st_wait();
+                    tc_fence_before_sync();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&bar_a_ready[0]);
                     {
                         uint32_t v[32];
                         tmem_ld32(tm_row + kColD + b * 128u + (uint32_t)cs * 64u, v);
                         tmem_ld_wait();
-                        // first half of the new A operand (K columns [0,128)) is in tensor memory: let the MMA warp start on it
-                        tmem_st_wait();
-                        tc_fence_before_sync();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&bar_a_ready[0]);
                         relu_split32<kW16>(v, bias + 128, hi, lo);
                         tmem_ld32(tm_row + kColD + b * 128u + (uint32_t)cs * 64u + 32u, v);
                         tmem_ld_wait();
