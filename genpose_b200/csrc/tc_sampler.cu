@@ -391,6 +391,7 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
                     }
                     ++hr;
                     it += (uint32_t)kUnitSlots;
+                    if (ds) ds[12] = clock64();                      // layer 1 unit a: all issued
                 } else if (!small) {
                     // 8 slots = 16 K-steps, issued as one group (unit 1) or two groups of 4 slots (units 0, 2).  Every slot wait costs
                     // the MMA warp ~250 cycles even when the data is there (measured: groups of 2 slots, 7.45 -> 8.0 ms per launch), so
@@ -457,6 +458,7 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
                         }
                         __syncwarp();
                         if (ds) { w_issue += clock64() - tq; tq = clock64(); }
+                        if (ds && unit == 1) ds[13] = clock64();     // layer 1 unit b: all issued
                         it += (uint32_t)per;
                     }
                 } else {
