@@ -1,42 +1,44 @@
 // The two samplers on the 5th-generation tensor cores (tcgen05 + TMEM): predictor-corrector (tc_pc_sampler_kernel, the
 // BASELINE metric) and the RK45 probability-flow ODE (tc_ode_sampler_kernel, the reference's shipped recipe).  ONE body
-// (tc_sampler_body<kOde>) evaluates the score network for both; they differ in what the row warps do with the score and in
-// how the number of evaluations is known.
+// (tc_sampler_body<kOde, kW16, kTeam>) evaluates the score network for both; they differ in what the row warps do with the score and
+// in how the number of evaluations is known.
 //
 // Same algorithm, launch contract and update code as pc_sampler_kernel / ode_sampler_kernel (scorenet.cu); only the score network's
-// dense layers change engine: every layer is evaluated by tcgen05.mma (kind::f16, bf16 operands, fp32
-// accumulation in TMEM) as the error-compensated split
-//        A.B ~= Ahi.Bhi + Alo.Bhi + Ahi.Blo          (A = Ahi + Alo, B = Bhi + Blo, all bf16)
-// whose products are exact in fp32, so the result carries ~2^-17 relative error per operand instead of bf16's
-// 2^-9.  Measured in the oracle: final poses move by 2e-5 (single bf16: 9e-3, tf32: 8e-4) against
-// the 1e-3 parity bound.
+// dense layers change engine: every layer is evaluated by tcgen05.mma (kind::f16, fp32 accumulation in TMEM) in one of two
+// error-compensated arithmetics:
+//   kW16 = false ("bf16x3")  A.B ~= Ahi.Bhi + Alo.Bhi + Ahi.Blo   (A = Ahi + Alo, B = Bhi + Blo, all bf16; ~2^-17 per operand)
+//   kW16 = true  ("f16x2")   A.B ~= Ahi.W + Alo.W                 (A = Ahi + Alo fp16, W one fp16 image; layer 0 stays bf16x3)
+// Measured against the oracle: bf16x3 moves final poses by 2e-5 (single bf16: 9e-3, tf32: 8e-4) against the 1e-3
+// parity bound; f16x2 spends more of that bound (0.04-0.9 of it on the damped synthetic checkpoints) for 2/3 of the MMAs and half
+// the weight stream.
 //
-// FOUR CTAs share a 128-row tile of candidates for all T steps ("tile team", rank = blockIdx.x & 3): every rank runs
-// layers 0 and 1 (P1, P2) redundantly — they are the sequential prefix — and then only ITS 192-column slice of the
-// 768 stacked head units (N = 128 + N = 64 MMAs), so the head phase costs one quarter of the tensor time.  The ranks'
-// partial score components (9 per row) are exchanged all-to-all through DISTRIBUTED SHARED MEMORY (the team is a thread-block
-// cluster: st.shared::cluster into every rank's mailbox + remote mbarrier arrival) and summed in a fixed rank order; every rank then applies the update redundantly and bit-identically
-// (same noise stream, same batch-mean norm, which rank 0 of every tile publishes to the grid-wide reduction), so the new
-// pose never has to be sent back.  Inside a CTA nothing of the per-step state leaves the SM:
+// A TEAM of kTeam CTAs (4, 2 or 1; the team is a thread-block cluster) shares a 128-row tile of candidates for all T steps: every
+// rank runs layers 0 and 1 (P1, P2) redundantly — they are the sequential prefix — and then only ITS 768 / kTeam columns of the
+// 768 stacked head units (team 4: N = 128 + N = 64 MMAs), so the head phase costs 1 / kTeam of the tensor time.  The ranks'
+// partial score components are exchanged all-to-all through DISTRIBUTED SHARED MEMORY (st.async into every rank's mailbox, bytes
+// counted by the receiver's mbarrier) and summed in a fixed rank order; every rank then applies the update redundantly and
+// bit-identically (same noise stream, same batch-mean norm, which rank 0 of every tile publishes to the grid-wide reduction), so
+// the new pose never has to be sent back.  A team of 1 has no exchange and no redundancy: one tile per SM, the throughput
+// configuration.  Inside a CTA nothing of the per-step state leaves the SM:
 //   * activations never touch shared memory: the A operand of every layer lives in TENSOR MEMORY (written by the
-//     epilogue with tcgen05.st, lane = row, two bf16 per 32-bit column; consumed by the TS form of tcgen05.mma),
+//     epilogue with tcgen05.st, lane = row, two 16-bit values per 32-bit column; consumed by the TS form of tcgen05.mma),
 //     TMEM map: D0 [0,128) D1 [128,256) accumulators (N = 128 "units", ping-pong), A_hi [256,384), A_lo [384,512);
-//   * the whole 227 KB of shared memory is therefore free for the weight stream: 10 slots x 16 KiB (9 in the ODE kernel,
-//     which keeps its float64 state in shared memory) of pre-tiled bf16 operand images (hi | lo; 1,040 KiB per step,
-//     L2-resident) fetched with cp.async.bulk on mbarriers, up to a ring ahead;
+//   * the whole 227 KB of shared memory is therefore free for the weight stream: 9-12 slots x 16 KiB of pre-tiled operand images
+//     (L2-resident) fetched with cp.async.bulk on mbarriers, up to a ring ahead;
 //   * pose state, noise and score of a row live in the registers of "its" thread.
 // Roles (warp-specialised, 320 threads):
 //   warps 0-7  row warps: warp w owns TMEM lanes 32*(w%4).. (rows) and the column sub-half w/4 of every unit.
-//              Layers 0/1: accumulator -> bias + ReLU -> bf16 hi/lo -> A operand (unit a is held in registers until
-//              the layer's last MMA has consumed the old A).  Heads: relu(acc + obj_bias + t_bias) . O, overlapped
-//              with the next unit's MMAs.  Warps 0-3 then run the grid-wide gradient-norm reduction and the
-//              Langevin / Euler-Maruyama update (noise for the step is generated while the tensor core works);
-//              warps 4-7 meanwhile refresh the (object bias + time bias) table for the next step.
+//              Layer 0: accumulator -> bias + ReLU -> hi/lo -> A operand in QUARTERS (layer 1 starts on the first 32 converted
+//              columns per thread).  Layer 1: the same in halves (unit a is held in registers until the layer's last MMA has
+//              consumed the old A).  Heads: relu(acc + obj_bias + t_bias) . O on packed fp32 pairs (FADD2 / FFMA2), overlapped
+//              with the next unit's MMAs.  Warps 0-3 then run the grid-wide gradient-norm reduction and the Langevin /
+//              Euler-Maruyama update (noise for the step is generated while the tensor core works); warps 4-7 meanwhile refresh
+//              the (object bias + time bias) table for the next step.
 //   warp 8     one elected thread issues every tcgen05.mma / tcgen05.commit; the warp owns the TMEM allocation.
 //   warp 9     one elected thread runs the weight producer.
-// Per step and CTA: layer 0 (10 MMAs), layer 1 (2 x 48 MMAs of 128x128x16), head slice (48 of 128x128x16 + 48 of 128x64x16).
-// History (3200 rows x 500 steps, one B200): A in shared memory + 2-deep weight ring 18.2 ms; A in TMEM, deep ring,
-// warp-uniform issue, one issue group per unit 12.6 ms (one CTA per tile, all three heads); this version: see DESIGN.md §5.
+// Per step and CTA (team 4, f16x2): layer 0 (10 MMAs), layer 1 (2 x 32 MMAs of 128x128x16), head slice (32 of 128x128x16 + 32 of 128x64x16).
+// History (3200 rows x 500 steps, one B200): A in shared memory + 2-deep weight ring 18.2 ms ... round 1 7.05 ms ... this version
+// 5.64 ms: DESIGN.md §5.
 #include <cstdlib>
 #include <initializer_list>
 #include <type_traits>

@@ -9,7 +9,10 @@ arbitrarily slow), that
 No GPU, no product code: a model of the protocol, kept next to the kernel so that a change of the protocol can be tried here first.
     python tools/tc_protocol_sim.py [runs] [steps] [--old-a-ready]
 --old-a-ready models the single 8-count bar_a_ready the kernel had before (both halves arriving on one barrier): the simulator
-finds the early-release race that motivated the split within a few hundred schedules."""
+finds the early-release race that motivated the split within a few hundred schedules.
+Round 2 note: the kernel now publishes layer 0's output in FOUR pieces on four barriers (bar_h1_ready[0..3]) and layer 1's in two
+(bar_a_ready[0..1]) — the same one-barrier-per-piece rule this model established for halves; the model still simulates the
+two-halves form for both hand-offs."""
 import random
 import sys
 
