@@ -80,7 +80,7 @@ template <bool kW16, int kTeam> struct TcStream {
 };
 constexpr uint32_t kLboB64 = 1024;                 // 64-row operand images
 constexpr uint32_t kLboB = 2048, kSbo = 128;       // 128-row operand images
-constexpr int kMaxObjPerTile = 4;
+constexpr int kMaxObjPerTile = 8;                 // objects a 128-row tile may span: K >= 19 candidates per object
 constexpr uint32_t kColD = 0, kColAhi = 256, kColAlo = 384;
 // per-step grid reduction word of the PC kernel: [63:56] arrived tiles, [55:48] poisoned tiles, [47:0] sum of the tile sums as
 // 22.18 fixed point of (tile sum x min(sigma(t), 1)) x up to 255 tiles (a tile sum is 128 row norms |f| / sigma: the limit 2^22 is
@@ -88,22 +88,24 @@ constexpr uint32_t kColD = 0, kColAhi = 256, kColAlo = 384;
 constexpr float kNormSumLimit = 4194304.f, kNormSumScale = 262144.f;
 using TL = TrunkLayout;
 
-// dynamic shared memory map (bytes)
-constexpr uint32_t kOffObt = 0;                                       // [4][768] fp32: obj_bias + t_bias(step)
-constexpr uint32_t kOffOw = kOffObt + kMaxObjPerTile * 768 * 4;       // [9][256] fp32 output layer + [16] bias
-constexpr uint32_t kOffBias = kOffOw + (9 * 256 + 16) * 4;            // p1_b [256] | p2_b [256]
-constexpr uint32_t kOffFpart = kOffBias + 512 * 4;                    // [128][12] fp32 partial scores of column sub-half 1
-constexpr uint32_t kOffMail = kOffFpart + 128 * 12 * 4;               // [2 parities][4 ranks][128][8] fp32: the team's partial sums (DSMEM)
-// then: the team's mailboxes (teams of 2 and 4), the ODE kernel's float64 state y [9][128] | y_new [9][128], and the weight ring,
-// which takes what is left (team 4: 10 slots PC / 9 ODE; team 1: 12 / 11)
+// dynamic shared memory map (bytes): [8 objects][kCols] fp32 obj_bias + t_bias(step) of the rank's head columns | [9][256] fp32 output
+// layer + [16] bias | p1_b [256] | p2_b [256] | [128][12] fp32 scratch (partial scores of column sub-half 1, ODE time-bias scratch) |
+// the team's mailboxes [2 parities][team][128][8] fp32 (DSMEM; teams of 2 and 4) | ODE: float64 state y [9][128] | y_new [9][128] | the
+// weight ring, which takes what is left (team 4: 10 slots PC / 9 ODE; team 1: 11 / 10)
 template <bool kOde, int kTeam> struct TcSmem {
+    static constexpr uint32_t kCols = 768u / kTeam;
+    static constexpr uint32_t kOffObt = 0;
+    static constexpr uint32_t kOffOw = kOffObt + kMaxObjPerTile * kCols * 4u;
+    static constexpr uint32_t kOffBias = kOffOw + (9u * 256u + 16u) * 4u;
+    static constexpr uint32_t kOffFpart = kOffBias + 512u * 4u;
+    static constexpr uint32_t kOffMail = kOffFpart + 128u * 12u * 4u;
     static constexpr uint32_t kMailBytes = kTeam > 1 ? 2u * kTeam * 128u * 8u * 4u : 0u;
     static constexpr uint32_t kOffOdeY = kOffMail + kMailBytes;
     static constexpr uint32_t kOffRing = ((kOffOdeY + (kOde ? 2u * 9u * 128u * 8u : 0u)) + 1023u) & ~1023u;
     static constexpr int kSlots = (int)((227u * 1024u - 1280u - kOffRing) / kSlotBytes);
     static constexpr uint32_t kBytes = kOffRing + kSlots * kSlotBytes;
 };
-static_assert(TcSmem<false, 4>::kSlots == 10 && TcSmem<true, 4>::kSlots == 9 && TcSmem<false, 1>::kSlots == 12 && TcSmem<true, 1>::kSlots == 11,
+static_assert(TcSmem<false, 4>::kSlots == 10 && TcSmem<true, 4>::kSlots == 9 && TcSmem<false, 1>::kSlots == 11 && TcSmem<true, 1>::kSlots == 10,
               "tc sampler shared memory budget");
 
 // probability-flow ODE mode (cond_ode_sampler, samplers.py:163-227): everything PcParams does not already carry
@@ -176,11 +178,11 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
     extern __shared__ __align__(1024) uint8_t smem[];
     constexpr int kSlots = SM::kSlots;
     uint8_t *sRing = smem + SM::kOffRing;
-    float *sObt = reinterpret_cast<float *>(smem + kOffObt);
-    float *sOw = reinterpret_cast<float *>(smem + kOffOw);
-    float *sBias = reinterpret_cast<float *>(smem + kOffBias);
-    float *sFpart = reinterpret_cast<float *>(smem + kOffFpart);
-    float *sMail = reinterpret_cast<float *>(smem + kOffMail);
+    float *sObt = reinterpret_cast<float *>(smem + SM::kOffObt);
+    float *sOw = reinterpret_cast<float *>(smem + SM::kOffOw);
+    float *sBias = reinterpret_cast<float *>(smem + SM::kOffBias);
+    float *sFpart = reinterpret_cast<float *>(smem + SM::kOffFpart);
+    float *sMail = reinterpret_cast<float *>(smem + SM::kOffMail);
     __shared__ __align__(8) uint64_t bar_full[kSlots], bar_empty[kSlots], bar_acc_full[2], bar_acc_empty[2], bar_x_ready, bar_a_ready[2],
         bar_h1_ready[4], bar_mail[2];
     __shared__ uint32_t s_tmem_base;
@@ -227,7 +229,8 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
     }
     if (warp == kTcRowWarps) tmem_alloc(&s_tmem_base, 512);
     if constexpr (!kOde) {
-        for (int i = tid; i < n_obj * 768; i += kTcThreads) sObt[i] = p.obj_bias[(size_t)obj_lo * 768 + i] + p.tb_table[i % 768];   // step 0
+        for (int i = tid; i < n_obj * kCols; i += kTcThreads)                                                                        // step 0
+            sObt[i] = p.obj_bias[(size_t)(obj_lo + i / kCols) * 768 + n_lo + i % kCols] + p.tb_table[n_lo + i % kCols];
     }
     for (int i = tid; i < 9 * 256 + 12; i += kTcThreads) sOw[i] = W[TL::o_w + i];   // o_w then o_b are adjacent
     for (int i = tid; i < 256; i += kTcThreads) {
@@ -538,7 +541,7 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
         const bool valid = row < p.R;
         const bool leader = rank == 0;
         const uint32_t tm_row = tmem_base + ((uint32_t)(q * 32) << 16);
-        const float *obt_row = sObt + (size_t)((valid ? row : p.R - 1) / p.K - obj_lo) * 768;
+        const float *obt_row = sObt + (size_t)((valid ? row : p.R - 1) / p.K - obj_lo) * kCols - n_lo;   // indexed by the stacked unit n in [n_lo, n_lo + kCols)
         const bool dbg = dbg_cta && tid == 0;
 
         float x[9];
@@ -683,7 +686,7 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
         auto fill_obt = [&](int gi, int t0, int nthr) {
             for (int i = tid - t0; i < n_obj * kCols; i += nthr) {
                 const int o = i / kCols, cc = n_lo + i % kCols;
-                sObt[o * 768 + cc] = __ldg(p.obj_bias + (size_t)(obj_lo + o) * 768 + cc) + __ldcg(tb_mine + gi * kCols + i % kCols);
+                sObt[o * kCols + i % kCols] = __ldg(p.obj_bias + (size_t)(obj_lo + o) * 768 + cc) + __ldcg(tb_mine + gi * kCols + i % kCols);
             }
         };
         // solver state, replicated bit-identically in every row thread of every rank (scipy/integrate/_ivp/rk.py, common.py)
@@ -950,18 +953,20 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
                 // x is published would join the layer-0 epilogue late and stall the MMA warp behind it.  Column c0 + 128 j of every
                 // object: the time biases once, then one batch of six independent loads per object.
                 if (cs == 1 && step > 0) {
+                    const float *tbn = p.tb_table + (size_t)step * 768 + n_lo;
+                    const float *obn = p.obj_bias + (size_t)obj_lo * 768 + n_lo;
+                    constexpr int kPer = (kCols + 127) / 128;                  // columns per thread: c0 + 128 j
                     const int c0 = tid - 128;
-                    const float *tbn = p.tb_table + (size_t)step * 768 + c0;
-                    float tb6[6];
+                    float tbv[kPer];
 #pragma unroll
-                    for (int j = 0; j < 6; ++j) tb6[j] = __ldg(tbn + 128 * j);
+                    for (int j = 0; j < kPer; ++j) tbv[j] = c0 + 128 * j < kCols ? __ldg(tbn + c0 + 128 * j) : 0.f;
                     for (int o = 0; o < n_obj; ++o) {
-                        const float *ob = p.obj_bias + (size_t)(obj_lo + o) * 768 + c0;
-                        float v[6];
+                        float v[kPer];
 #pragma unroll
-                        for (int j = 0; j < 6; ++j) v[j] = __ldg(ob + 128 * j);
+                        for (int j = 0; j < kPer; ++j) v[j] = c0 + 128 * j < kCols ? __ldg(obn + (size_t)o * 768 + c0 + 128 * j) : 0.f;
 #pragma unroll
-                        for (int j = 0; j < 6; ++j) sObt[o * 768 + c0 + 128 * j] = v[j] + tb6[j];
+                        for (int j = 0; j < kPer; ++j)
+                            if (c0 + 128 * j < kCols) sObt[o * kCols + c0 + 128 * j] = v[j] + tbv[j];
                     }
                 }
             }
@@ -1561,7 +1566,7 @@ extern "C" int gpb_set_tc_team(int team) {
 // Largest row count R the tensor-core samplers accept on the current device for K candidates per object (0 = not at all):
 // every 128-row tile needs one co-resident CTA (team of 1: one tile per SM), and a tile may span at most kMaxObjPerTile objects.
 extern "C" int gpb_sampler_tc_max_rows(int K) {
-    if (K < 1 || 127 / K + 2 > kMaxObjPerTile) return 0;
+    if (K < 1 || 127 / K + 2 > kMaxObjPerTile) return 0;      // K >= 19
     const int forced = g_forced_team.load();
     int best = 0;
     for (int ti = 0; ti < 3; ++ti) {

@@ -161,7 +161,7 @@ class Engine:
     # ---- a9: PC sampler -------------------------------------------------------------------------------
     @staticmethod
     def tc_supported(R: int, K: int) -> bool:
-        """tcgen05 sampler constraints (asked of the library): a 128-row tile spans <= 4 objects (K >= 43) and every tile
+        """tcgen05 sampler constraints (asked of the library): a 128-row tile spans <= 8 objects (K >= 19) and every tile
         needs one co-resident team of CTAs — 4 per tile up to 33 tiles, 2 up to 66, 1 up to one tile per SM (148 tiles =
         18,944 rows = 378 objects x 50 candidates on a B200)."""
         return 0 < R <= lib.load().gpb_sampler_tc_max_rows(int(K))

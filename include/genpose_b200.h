@@ -130,7 +130,7 @@ GPB_API int gpb_sample_pc(const float *x0, int R, int K, int num_steps, float sn
 
 /* Tensor-core (tcgen05, bf16x3 split, fp32 accumulate in TMEM) variant of gpb_sample_pc: same contract plus
  * `tc_stream`, the bf16 operand-image stream of the trunk (gpb_trunk_tc_stream_bytes() bytes, produced by
- * genpose_b200/weights.py::pack_trunk_tc).  Requires K >= 43 (a 128-row tile may span at most 4 objects) and
+ * genpose_b200/weights.py::pack_trunk_tc).  Requires K >= 19 (a 128-row tile may span at most 8 objects) and
  * ceil(R/128) <= #SMs; otherwise use gpb_sample_pc.  Poses agree with the fp32 path to ~2e-5. */
 GPB_API size_t gpb_trunk_tc_stream_bytes(void);
 GPB_API int gpb_sample_pc_tc(const float *x0, int R, int K, int num_steps, float snr, const float *obj_bias,
@@ -180,7 +180,7 @@ GPB_API int gpb_set_tc_team(int team);
 /* gpb_sample_ode on the tensor cores: the same solver (same controller, float64 state, one error norm over the whole
  * batch) with the score network's dense layers evaluated by tcgen05.mma (bf16x3 split, fp32 accumulation in tensor
  * memory), one team of CTAs per 128-row tile as in gpb_sample_pc_tc.  tc_stream as there.
- * Constraints: K >= 43, R <= gpb_sampler_tc_max_rows(K); otherwise use gpb_sample_ode. */
+ * Constraints: K >= 19, R <= gpb_sampler_tc_max_rows(K); otherwise use gpb_sample_ode. */
 GPB_API int gpb_sample_ode_tc(const float *x0, int R, int K, double T0, double rtol, double atol, int denoise_steps,
                       const float *obj_bias, const float *trunk_weights, const void *tc_stream, const float *pts_center,
                       double *pose, int *stats, double *process, int process_cap, const double *t_eval, int n_t_eval,

@@ -144,7 +144,7 @@ def test_tc_capacity_is_asked_of_the_library_and_auto_falls_back():
     the library (cudaOccupancyMaxActiveClusters), and larger batches run on the FFMA kernels."""
     from genpose_b200 import ops
     L = lib.load()
-    assert L.gpb_sampler_tc_max_rows(1) == 0 and L.gpb_sampler_tc_max_rows(42) == 0
+    assert L.gpb_sampler_tc_max_rows(1) == 0 and L.gpb_sampler_tc_max_rows(18) == 0 and L.gpb_sampler_tc_max_rows(19) > 0
     cap = L.gpb_sampler_tc_max_rows(50)
     assert cap >= 3200 and cap % 128 == 0                       # the bench shape fits
     seed, K, T = 13, 50, 6

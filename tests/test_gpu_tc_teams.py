@@ -266,3 +266,27 @@ def test_ode_trajectory_matches_reference_golden_and_agent_surface():
     assert pred_pose.shape == (B, K, 9) and in_process.shape[:2] == (B, K) and in_process.shape[3] == 9
     np.testing.assert_allclose(pred_pose.cpu().numpy(), g["ref_pred_pose"], rtol=2e-4, atol=1e-3)
     np.testing.assert_allclose(in_process[:, :, -1].cpu().numpy(), g["ref_process_last"], rtol=2e-4, atol=1e-3)
+
+
+@pytest.mark.parametrize("precision,team", [("f16x2", 0), ("bf16x3", 1), ("f16x2", 2)])
+@pytest.mark.parametrize("B,K", [(14, 20), (11, 25), (40, 19)])
+def test_small_candidate_counts_on_tensor_cores(B, K, precision, team):
+    """K >= 19: a 128-row tile spans up to 8 objects, whose (object + time) biases the head epilogue caches (configs/config.py:59's
+    --repeat_num 20 is the smallest count the reference uses).  PC and ODE against the FFMA kernels and the oracle."""
+    T = 40
+    sd, data, eng, feat, ob, cen, x0, sn = _pc_case(B, K, T)
+    assert eng.tc_supported(B * K, K) and not eng.tc_supported(B * 18, 18)
+    args = (ob, cen, torch.from_numpy(x0).cuda(), K, T)
+    noise = torch.from_numpy(sn).cuda()
+    p = eng.sample_pc(*args, step_noise=noise, precision=precision, team=team)
+    p32 = eng.sample_pc(*args, step_noise=noise, precision="fp32")
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(p.cpu().numpy(), p32.cpu().numpy(), rtol=5e-5, atol=1e-3)
+    ref, _ = O.pred_func_pc(sd, data, K, T, torch.from_numpy(x0), torch.from_numpy(sn), pts_feat=feat.cpu())
+    np.testing.assert_allclose(p.cpu().numpy().reshape(B, K, 9), ref.numpy(), rtol=5e-5, atol=1e-3)
+    sdo, datao, engo, feato, obo, ceno, x0o = _ode_case(B, K, 0.55, 60 + B)
+    po, so = engo.sample_ode(obo, ceno, x0o, K, T0=0.55, precision=precision, team=team)
+    po32, so32 = engo.sample_ode(obo, ceno, x0o, K, T0=0.55, precision="fp32")
+    torch.cuda.synchronize()
+    assert int(so[3]) == 0 and abs(int(so[0]) - int(so32[0])) <= 12
+    np.testing.assert_allclose(po.cpu().numpy(), po32.cpu().numpy(), rtol=2e-4, atol=1e-3)
