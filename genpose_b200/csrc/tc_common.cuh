@@ -121,6 +121,12 @@ __device__ __forceinline__ void tc_fence_after_sync() { asm volatile("tcgen05.fe
 
 // 32 lanes x 32 consecutive fp32 columns: thread t of warp w reads TMEM lane 32*(w%4)+t, columns [col, col+32)
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+#if defined(GPB_DBG_SKIP_LDTM) && GPB_DBG_SKIP_LDTM
+    // TIMING EXPERIMENT ONLY (wrong results): no accumulator read-back, to see what the tensor-memory read path costs a step
+#pragma unroll
+    for (int i = 0; i < 32; ++i) r[i] = taddr + i;
+    return;
+#endif
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
         "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"

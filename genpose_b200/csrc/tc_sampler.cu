@@ -90,6 +90,7 @@ using TL = TrunkLayout;
 
 // dynamic shared memory map (bytes): [8 objects][kCols] fp32 obj_bias + t_bias(step) of the rank's head columns | [9][256] fp32 output
 // layer + [16] bias | p1_b [256] | p2_b [256] | [128][12] fp32 scratch (partial scores of column sub-half 1, ODE time-bias scratch) |
+// PC: [18][128] fp32 noise of the step |
 // the team's mailboxes [2 parities][team][128][8] fp32 (DSMEM; teams of 2 and 4) | ODE: float64 state y [9][128] | y_new [9][128] | the
 // weight ring, which takes what is left (team 4: 10 slots PC / 9 ODE; team 1: 11 / 10)
 template <bool kOde, int kTeam> struct TcSmem {
@@ -98,7 +99,9 @@ template <bool kOde, int kTeam> struct TcSmem {
     static constexpr uint32_t kOffOw = kOffObt + kMaxObjPerTile * kCols * 4u;
     static constexpr uint32_t kOffBias = kOffOw + (9u * 256u + 16u) * 4u;
     static constexpr uint32_t kOffFpart = kOffBias + 512u * 4u;
-    static constexpr uint32_t kOffMail = kOffFpart + 128u * 12u * 4u;
+    static constexpr uint32_t kOffNoise = kOffFpart + 128u * 12u * 4u;           // PC: [18][128] fp32 z1 | z2 of the step (column half 1 -> half 0)
+    static constexpr bool kNoiseByHalf1 = !kOde && kTeam > 1;   // (a team of 1 has no idle tail for half 1 and would pay a ring slot)
+    static constexpr uint32_t kOffMail = kOffNoise + (kNoiseByHalf1 ? 18u * 128u * 4u : 0u);
     static constexpr uint32_t kMailBytes = kTeam > 1 ? 2u * kTeam * 128u * 8u * 4u : 0u;
     static constexpr uint32_t kOffOdeY = kOffMail + kMailBytes;
     static constexpr uint32_t kOffRing = ((kOffOdeY + (kOde ? 2u * 9u * 128u * 8u : 0u)) + 1023u) & ~1023u;
@@ -183,6 +186,7 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
     float *sBias = reinterpret_cast<float *>(smem + SM::kOffBias);
     float *sFpart = reinterpret_cast<float *>(smem + SM::kOffFpart);
     float *sMail = reinterpret_cast<float *>(smem + SM::kOffMail);
+    float *sNoise = reinterpret_cast<float *>(smem + SM::kOffNoise);       // PC only
     __shared__ __align__(8) uint64_t bar_full[kSlots], bar_empty[kSlots], bar_acc_full[2], bar_acc_empty[2], bar_x_ready, bar_a_ready[2],
         bar_h1_ready[4], bar_mail[2];
     __shared__ uint32_t s_tmem_base;
@@ -420,6 +424,7 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
                         if (g == 0) mbar_wait(&bar_acc_empty[b], (n & 1u) ^ 1u);
                         tc_fence_after_sync();
                         if (ds) { w_acc += clock64() - tq; tq = clock64(); }
+                        if (ds && unit == 1) ds[14] = clock64();     // layer 1 unit b: waits done, issue starts
                         const uint32_t s_first = it % kSlots;
                         const int kc0 = g * per;
                         if (elect_one_sync()) {
@@ -807,6 +812,22 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
         for (int step = 0; kOde || step < p.T; ++step) {
             unsigned long long *ds = (dbg && step < p.T) ? p.dbg + (size_t)step * 16 : nullptr;
             if (ds) ds[0] = clock64();
+            if constexpr (SM::kNoiseByHalf1) {
+                // The two noise draws of this step (18 normals per row: six Philox blocks + Box-Muller, or 18 loads) are produced by
+                // COLUMN HALF 1, whose warps reach this point during the previous step's tail (exchange, norm, grid word, update
+                // belong to half 0) and would otherwise idle; half 0 picks them up after barrier 3.  They used to be generated by
+                // half 0 between the layer-1 and the head epilogues, i.e. in front of barrier 3 on the step's critical path.
+                if (cs == 1 && valid) {
+                    float za[9], zb[9];
+                    row_noise(p, step, 0, row, za);
+                    row_noise(p, step, 1, row, zb);
+#pragma unroll
+                    for (int c = 0; c < 9; ++c) {
+                        sNoise[c * 128 + r] = za[c];
+                        sNoise[(9 + c) * 128 + r] = zb[c];
+                    }
+                }
+            }
             const float t = kOde ? s_times[gi] : p.ts[step];
             const float sigma = sigma_of_t(t);
             const float stdv = sigma + 1e-7f;
@@ -941,11 +962,12 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
                     }
                 }
             }
-            // noise of this step, generated while the tensor core runs the head slice (the leader's warps 0-3 own the rows)
-            float z1[9], z2[9];
-            if (!kOde && cs == 0 && valid) {
-                row_noise(p, step, 0, row, z1);
-                row_noise(p, step, 1, row, z2);
+            float z1[9], z2[9];                       // noise of this step (PC): written by column half 1 at the top of the step,
+            if constexpr (!kOde && !SM::kNoiseByHalf1) {   // or (team of 1) generated here, under the first head unit's MMAs
+                if (cs == 0 && valid) {
+                    row_noise(p, step, 0, row, z1);
+                    row_noise(p, step, 1, row, z2);
+                }
             }
             if constexpr (!kOde) {
                 // warps 4-7: (object bias + time bias) table of THIS step, while the tensor core runs the head slice (everyone left
@@ -971,6 +993,13 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
                 }
             }
             named_bar_sync(3, kTcRowWarps * 32);      // sObt holds obj_bias + t_bias of THIS step (written by warps 4-7)
+            if (SM::kNoiseByHalf1 && cs == 0 && valid) {   // (before barrier 1: half 1 overwrites the buffer at the top of the next step)
+#pragma unroll
+                for (int c = 0; c < 9; ++c) {
+                    z1[c] = sNoise[c * 128 + r];
+                    z2[c] = sNoise[(9 + c) * 128 + r];
+                }
+            }
             // ---- head slice: relu(acc + obj_bias + t_bias) . O, partial sums per touched head: o[h - hA] (teams 2 and 4 touch two
             //      heads, team 1 all three) ----
             float o[3][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};

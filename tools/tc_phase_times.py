@@ -78,7 +78,8 @@ ev = [("row: step start", row[:, 0]), ("row: L0 acc ready", row[:, 1]), ("row: L
       ("row: partials sent", row[:, 11]), ("row: peers' partials in", row[:, 10]), ("row: norm published", row[:, 14]),
       ("row: grid word complete", row[:, 15]), ("row: x published", row[:, 13]),
       ("mma: x_ready seen", mma[:, 1]), ("mma: L1 unit a first half A ready", mma[:, 3]), ("mma: head128 first half A ready", mma[:, 4]),
-      ("mma: all issued", mma[:, 7]), ("mma: L1 unit a all issued", mma[:, 12]), ("mma: L1 unit b all issued", mma[:, 13])]
+      ("mma: all issued", mma[:, 7]), ("mma: L1 unit a all issued", mma[:, 12]), ("mma: L1 unit b all issued", mma[:, 13]),
+      ("mma: L1 unit b issue starts", mma[:, 14])]
 base = row[:, 0]
 print("timeline (cycles after the row thread's step start; x_ready / x published belong to the step boundary):")
 for name, v in sorted(ev, key=lambda e: np.mean((e[1] - base) % 1e9)):
