@@ -300,20 +300,32 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
         for (int step = 0; kOde || step < p.T; ++step) {
             unsigned long long *ds = (dbg_cta && lane == 0 && step < p.T) ? p.dbg + ((size_t)p.T + step) * 16 : nullptr;   // ODE: T = recorded evaluations
             unsigned long long w_full = 0, w_a = 0, w_acc = 0, tq = 0, w_issue = 0;
+#ifdef GPB_DBG_TRACE
+            // experiment builds only: every wait / issue boundary of ONE step of the MMA warp, behind the [2][T][16] stamp block
+            unsigned long long *trp = (ds && step == p.T / 2) ? p.dbg + (size_t)2 * p.T * 16 : nullptr;
+#define TRS(i) do { if (trp) trp[i] = clock64(); } while (0)
+#else
+#define TRS(i) do { } while (0)
+#endif
             if (ds) ds[0] = clock64();
+            TRS(0);
             // ---- layer 0: h1_pre = x . P1^T   (K = 16; x pieces x1,x2,x3 at A_hi[0,8),[8,16),[16,24); P1 hi|lo per unit)
             // (every slot wait costs ~250 cycles even when the data is there: it is taken BEFORE the wait for the operand it
             // accompanies, where this warp idles anyway, not between that wait and the first MMA)
             wait_slots(1);
+            TRS(1);
             mbar_wait(&bar_x_ready, xr & 1u);
             ++xr;
             if (ds) ds[1] = clock64();
+            TRS(2);
             {
                 const uint32_t s = it % kSlots;
                 for (int half = 0; half < 2; ++half) {
-                    const uint32_t b = u & 1u, n = u >> 1;
-                    mbar_wait(&bar_acc_empty[b], (n & 1u) ^ 1u);
-                    tc_fence_after_sync();
+                    // (no wait for the accumulator: x is published after every head epilogue of the previous step has read its
+                    // accumulators, so x_ready implies both are free — see "accumulator hand-back" at the row warps)
+                    const uint32_t b = u & 1u;
+                    if (half == 0) tc_fence_after_sync();
+                    TRS(3 + 2 * half);
                     const uint32_t d = tmem_base + kColD + b * 128u;
                     const uint64_t bhi = make_smem_desc(ring + s * kSlotBytes + (uint32_t)half * 8192u, kLboB, kSbo);
                     const uint64_t blo = make_smem_desc(ring + s * kSlotBytes + (uint32_t)half * 8192u + 4096u, kLboB, kSbo);
@@ -327,6 +339,7 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
                         umma_commit(&bar_acc_full[b]);
                     }
                     __syncwarp();
+                    TRS(4 + 2 * half);
                     ++u;
                 }
                 ++it;
@@ -351,6 +364,7 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
                     constexpr int kUnitSlots = kW16 ? 4 : 8;
                     if (ds) tq = clock64();
                     wait_slots(kUnitSlots);
+                    TRS(7);
                     if (ds) { w_full += clock64() - tq; tq = clock64(); }
                     const uint32_t s_first = it % kSlots;
                     auto slot_base = [&](int sl) {
@@ -361,13 +375,14 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
                     for (int g = 0; g < 4; ++g) {
                         if (ds) tq = clock64();
                         mbar_wait(&bar_h1_ready[g], hr & 1u);
+                        TRS(8 + 3 * g);
                         if (ds) {
                             w_a += clock64() - tq;
                             if (g == 0) ds[3] = clock64();
                             tq = clock64();
                         }
-                        if (g == 0) mbar_wait(&bar_acc_empty[b], (n & 1u) ^ 1u);
-                        tc_fence_after_sync();
+                        tc_fence_after_sync();      // (accumulator: free once quarter 0 is published, which follows its last read)
+                        TRS(9 + 3 * g);
                         if (ds) { w_acc += clock64() - tq; tq = clock64(); }
                         const int base = 8 * (g >> 1) + 2 * (g & 1);
                         if (elect_one_sync()) {
@@ -396,6 +411,7 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
                             if (g == 3) umma_commit(&bar_acc_full[b]);
                         }
                         __syncwarp();
+                        TRS(10 + 3 * g);
                         if (ds) { w_issue += clock64() - tq; tq = clock64(); }
                     }
                     ++hr;
@@ -410,10 +426,12 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
                     for (int g = 0; g < groups; ++g) {
                         if (ds) tq = clock64();
                         wait_slots(per);                           // before the operand wait (see layer 0)
+                        TRS(unit == 1 ? 20 : 23 + 4 * g);
                         if (ds) { w_full += clock64() - tq; tq = clock64(); }
                         if (split) {
                             mbar_wait(&bar_a_ready[g], ar & 1u);            // one phase of either barrier per step (layer 1 -> heads)
                             if (g == 1) ++ar;
+                            TRS(24 + 4 * g);
                         }
                         if (ds) {
                             w_a += clock64() - tq;
@@ -421,8 +439,12 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
                             if (unit == 2 && g == 0) ds[4] = clock64();
                             tq = clock64();
                         }
-                        if (g == 0) mbar_wait(&bar_acc_empty[b], (n & 1u) ^ 1u);
+                        // accumulator hand-back: unit 1 reuses layer 0's second accumulator (read before h1 quarter 2 was published),
+                        // head units 0 and 1 those of layer 1 (read before pf half 0 / half 1 were published): only head units >= 2
+                        // wait for an explicit release, by the epilogue of head unit - 2
+                        if (g == 0 && unit >= 4) mbar_wait(&bar_acc_empty[b], (n & 1u) ^ 1u);
                         tc_fence_after_sync();
+                        TRS(unit == 1 ? 21 : 25 + 4 * g);
                         if (ds) { w_acc += clock64() - tq; tq = clock64(); }
                         if (ds && unit == 1) ds[14] = clock64();     // layer 1 unit b: waits done, issue starts
                         const uint32_t s_first = it % kSlots;
@@ -467,6 +489,7 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
                             if (g == groups - 1) umma_commit(&bar_acc_full[b]);
                         }
                         __syncwarp();
+                        TRS(unit == 1 ? 22 : 26 + 4 * g);
                         if (ds) { w_issue += clock64() - tq; tq = clock64(); }
                         if (ds && unit == 1) ds[13] = clock64();     // layer 1 unit b: all issued
                         it += (uint32_t)per;
@@ -475,9 +498,10 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
                     if (ds) tq = clock64();
                     constexpr int kSmallSlots = kW16 ? 2 : 4;
                     wait_slots(kSmallSlots);
+                    TRS(31);
                     if (ds) { w_full += clock64() - tq; tq = clock64(); }
-                    mbar_wait(&bar_acc_empty[b], (n & 1u) ^ 1u);
-                    tc_fence_after_sync();
+                    static_assert(!TS::kSmallUnit || TS::kHeadUnits == 2, "the 64-column unit is head unit 1: its accumulator is free once pf is complete");
+                    TRS(32);
                     if (ds) { w_acc += clock64() - tq; tq = clock64(); }
                     const uint32_t s_first = it % kSlots;
                     if (elect_one_sync()) {
@@ -522,6 +546,7 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
                         umma_commit(&bar_acc_full[b]);
                     }
                     __syncwarp();
+                    TRS(33);
                     if (ds) w_issue += clock64() - tq;
                     it += (uint32_t)kSmallSlots;
                 }
@@ -870,6 +895,9 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
                         tmem_st_wait();
                         tc_fence_before_sync();
                         __syncwarp();
+                        // accumulator hand-back: every operand announcement below (h1 quarters, pf halves, x) is made AFTER this warp's
+                        // last read of the accumulator the announced MMAs will overwrite, so the MMA warp waits for bar_acc_empty only
+                        // where no operand hand-off stands in between (head units >= 2); the arrivals keep the phase count uniform
                         if (lane == 0) {
                             mbar_arrive(&bar_h1_ready[qd]);
                             if (qd == 0) mbar_arrive(&bar_acc_empty[b0]);      // (its second 32 columns are in registers by now)
