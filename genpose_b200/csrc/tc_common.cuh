@@ -45,6 +45,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) {
     }
 }
+// The same with the retry loop inside the asm block: the C++ loop above is compiled as a jump to an out-of-line retry block at the
+// end of the kernel and a jump back — two taken branches into cold instruction-cache lines even when the phase is already complete.
+// For the MMA issuer, where every cycle between two issue groups idles the tensor pipe.
+__device__ __forceinline__ void mbar_wait_inline(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t}"
+        ::"r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+}
 
 // ---- thread-block cluster: distributed shared memory + remote mbarrier arrival ------------------------------------
 __device__ __forceinline__ uint32_t cluster_ctarank() {

@@ -289,6 +289,11 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
         const uint32_t t_ahi = tmem_base + kColAhi, t_alo = tmem_base + kColAlo;
         uint32_t u = 0, it = 0, xr = 0, ar = 0, hr = 0;
         // wait for n_slots consecutive ring slots starting at stream position `it`: lane l polls slot l (one wait latency)
+        // f16x2 (one weight image: layer 1 is 8 slots, a team-of-4 rank's head slice 6): fewer, larger issue groups.  The tensor pipe
+        // accepts an MMA only about when it starts it (issue time = execution time), so every wait between two groups idles the pipe:
+        // layer 1 is issued as q0 | q1 | q2 + q3 + unit b behind ONE slot wait, the head slice as first half | second half + 64-column
+        // unit behind one more.  (Three-product arithmetic: layer 1 alone is 16 slots, more than the ring holds.)
+        constexpr bool kFuseL1 = false, kFuseHeads = false;   // (the f16x2 path below fuses; layer 1 of the three-product path is 16 slots)
         auto wait_slots = [&](int n_slots) {
             if (lane < n_slots) {
                 const uint32_t itl = it + (uint32_t)lane;
@@ -297,6 +302,186 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
             __syncwarp();
             tc_fence_after_sync();
         };
+        if constexpr (kW16) {
+        // ---- f16x2 (one fp16 weight image; A = fp16 hi / lo): straight-line issue code ----
+        // The tensor pipe accepts an MMA only about when it starts it (issue time = execution time), so everything this thread does
+        // between two issue groups idles the pipe.  Hence: (1) the step's slot schedule — ring position, descriptor address field and
+        // release barrier of each of its slots — is computed at the top of the step, under the wait for x, and every loop below is
+        // unrolled over it (no index arithmetic behind a wait); (2) few, large groups: layer 1 is q0 | q1 | q2 + q3 + unit b behind ONE
+        // slot wait, a team-of-4 head slice first half | second half + 64-column unit behind one more; (3) no accumulator waits where
+        // an operand hand-off implies the release (see the row warps).
+        constexpr int NS = TS::kSlotsPerCtaStep;
+        constexpr uint32_t kDescHi = ((kSbo >> 4) & 0x3FFFu) | (1u << 14);                      // SBO | descriptor version (bit 46)
+        constexpr uint32_t kLf128 = ((kLboB >> 4) & 0x3FFFu) << 16, kLf64 = ((kLboB64 >> 4) & 0x3FFFu) << 16;
+        constexpr bool kFuseHeads = TS::kSmallUnit;
+        static_assert(8 <= kSlots, "layer 1 waits for its 8 slots at once");
+        static_assert(!kFuseHeads || (TS::kHeadSlots <= kSlots && TS::kHeadUnits == 2), "a team-of-4 head slice waits for all its slots at once");
+        auto desc = [&](uint32_t lo) { return ((uint64_t)kDescHi << 32) | (uint64_t)lo; };
+        const uint32_t empty0 = smem_u32(&bar_empty[0]);
+        uint32_t sring = 0;                                                                     // ring position of the step's first slot
+        for (int step = 0; kOde || step < p.T; ++step) {
+            unsigned long long *ds = (dbg_cta && lane == 0 && step < p.T) ? p.dbg + ((size_t)p.T + step) * 16 : nullptr;   // ODE: T = recorded evaluations
+            unsigned long long w_full = 0, w_a = 0, w_issue = 0, tq = 0;
+            if (ds) ds[0] = clock64();
+            uint32_t dl[NS], eb[NS];
+            {
+                uint32_t s = sring;
+#pragma unroll
+                for (int i = 0; i < NS; ++i) {
+                    dl[i] = ((ring + s * kSlotBytes) >> 4) & 0x3FFFu;   // (the mask matters: in a cluster the shared::cta window address carries the CTA's rank above bit 18)
+                    eb[i] = empty0 + 8u * s;
+                    s = s + 1u == (uint32_t)kSlots ? 0u : s + 1u;
+                }
+                sring = s;
+            }
+            auto commit_slot = [&](int i) { asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(eb[i]) : "memory"); };
+            // one 128-column K-step (16 inputs) of a K = 256 unit: slot i holds four of them
+            auto kstep128 = [&](uint32_t d, int slot, int ks, bool acc) {
+                const uint64_t b_w = desc(dl[slot] + (uint32_t)((2u * (uint32_t)(ks & 3) * kLboB) >> 4) + kLf128);
+                umma_bf16_ts(d, t_ahi + (uint32_t)ks * 8u, b_w, idesc128w, acc);
+                umma_bf16_ts(d, t_alo + (uint32_t)ks * 8u, b_w, idesc128w, true);
+            };
+            // ---- layer 0: h1_pre = x . P1^T   (K = 16; x pieces x1,x2,x3 at A_hi[0,8),[8,16),[16,24); P1 hi|lo per unit) ----
+            wait_slots(1);
+            mbar_wait_inline(&bar_x_ready, xr & 1u);          // (implies both accumulators free: x follows every head epilogue)
+            ++xr;
+            tc_fence_after_sync();
+            if (ds) { ds[1] = clock64(); tq = clock64(); }
+            if (elect_one_sync()) {
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    const uint32_t b = (u + (uint32_t)half) & 1u;
+                    const uint32_t d = tmem_base + kColD + b * 128u;
+                    const uint64_t bhi = desc(dl[0] + (uint32_t)half * 512u + kLf128), blo = desc(dl[0] + (uint32_t)half * 512u + 256u + kLf128);
+                    umma_bf16_ts(d, t_ahi + 0u, bhi, idesc128, false);
+                    umma_bf16_ts(d, t_ahi + 8u, bhi, idesc128, true);
+                    umma_bf16_ts(d, t_ahi + 16u, bhi, idesc128, true);
+                    umma_bf16_ts(d, t_ahi + 0u, blo, idesc128, true);
+                    umma_bf16_ts(d, t_ahi + 8u, blo, idesc128, true);
+                    if (half == 1) commit_slot(0);
+                    umma_commit(&bar_acc_full[b]);
+                }
+            }
+            __syncwarp();
+            if (ds) { w_issue += clock64() - tq; tq = clock64(); }
+            u += 2;
+            it += 1;
+            // ---- layer 1: unit a on the h1 quarters (quarter g = K-steps {base, base + 1, base + 4, base + 5}, base = 8 (g / 2) + 2 (g % 2):
+            //      row thread (q, cs) converts columns [64 cs, 64 cs + 64) of either unit, 32 at a time), unit b behind it ----
+            wait_slots(8);
+            if (ds) { w_full += clock64() - tq; tq = clock64(); }
+            {
+                const uint32_t da = tmem_base + kColD + (u & 1u) * 128u, db = tmem_base + kColD + ((u + 1u) & 1u) * 128u;
+#pragma unroll
+                for (int g = 0; g < 3; ++g) {
+                    mbar_wait_inline(&bar_h1_ready[g == 2 ? 3 : g], hr & 1u);      // quarters 2 and 3 are both there once quarter 1 is issued
+                    tc_fence_after_sync();
+                    if (ds) {
+                        w_a += clock64() - tq;
+                        if (g == 0) ds[3] = clock64();
+                        tq = clock64();
+                    }
+                    if (elect_one_sync()) {
+#pragma unroll
+                        for (int gg = g; gg < (g == 2 ? 4 : g + 1); ++gg) {
+                            const int base = 8 * (gg >> 1) + 2 * (gg & 1);
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const int ks = base + (e & 1) + 4 * (e >> 1);
+                                kstep128(da, 1 + (ks >> 2), ks, (gg | e) != 0);
+                            }
+                            if (gg & 1) {   // quarters 2 (gg / 2), 2 (gg / 2) + 1 cover K-steps [8 (gg / 2), +8): two slots done
+                                commit_slot(1 + (gg >> 1) * 2);
+                                commit_slot(2 + (gg >> 1) * 2);
+                            }
+                        }
+                        if (g == 2) {
+                            umma_commit(&bar_acc_full[u & 1u]);
+#pragma unroll
+                            for (int ks = 0; ks < 16; ++ks) {     // unit b: its accumulator was read before h1 quarter 2 was published
+                                kstep128(db, 5 + (ks >> 2), ks, ks != 0);
+                                if ((ks & 3) == 3) commit_slot(5 + (ks >> 2));
+                            }
+                            umma_commit(&bar_acc_full[(u + 1u) & 1u]);
+                        }
+                    }
+                    __syncwarp();
+                    if (ds) { w_issue += clock64() - tq; tq = clock64(); }
+                }
+                ++hr;
+                u += 2;
+                it += 8;
+            }
+            // ---- this rank's head slice: pf arrives in two halves (K columns [0,128) and [128,256)) ----
+            if (ds) tq = clock64();
+#pragma unroll
+            for (int hu = 0; hu < TS::kFullUnits; ++hu) {
+                const int hs = TS::kCommonSlots + 4 * hu;                 // the unit's first slot
+                const uint32_t b = u & 1u, n = u >> 1;
+                const uint32_t d = tmem_base + kColD + b * 128u;
+                if (hu == 0 || !kFuseHeads) wait_slots(hu == 0 && kFuseHeads ? TS::kHeadSlots : 4);
+                if (ds) { w_full += clock64() - tq; tq = clock64(); }
+#pragma unroll
+                for (int g = 0; g < (hu == 0 ? 2 : 1); ++g) {
+                    if (hu == 0) {
+                        mbar_wait_inline(&bar_a_ready[g], ar & 1u);        // (implies the accumulator of head unit g is free)
+                        if (g == 1) ++ar;
+                        tc_fence_after_sync();
+                    } else if (hu >= 2) {
+                        mbar_wait_inline(&bar_acc_empty[b], (n & 1u) ^ 1u);   // released by the epilogue of head unit hu - 2
+                        tc_fence_after_sync();
+                    }
+                    if (ds) {
+                        w_a += clock64() - tq;
+                        if (hu == 0 && g == 0) ds[4] = clock64();
+                        tq = clock64();
+                    }
+                    if (elect_one_sync()) {
+                        const int k0 = hu == 0 ? 8 * g : 0, k1 = hu == 0 ? 8 * g + 8 : 16;
+#pragma unroll
+                        for (int ks = k0; ks < k1; ++ks) {
+                            kstep128(d, hs + (ks >> 2), ks, ks != 0);
+                            if ((ks & 3) == 3) commit_slot(hs + (ks >> 2));
+                        }
+                        if (k1 == 16) umma_commit(&bar_acc_full[b]);
+                        if constexpr (kFuseHeads) {
+                            if (g == 1) {   // the 64-column unit (head unit 1: free once pf is complete): one fp16 image of K = 128 per slot
+                                const uint32_t d2 = tmem_base + kColD + ((u + 1u) & 1u) * 128u;
+#pragma unroll
+                                for (int ks = 0; ks < 16; ++ks) {
+                                    const int slot = TS::kCommonSlots + 4 + (ks >> 3);
+                                    const uint64_t b_w = desc(dl[slot] + (uint32_t)((2u * (uint32_t)(ks & 7) * kLboB64) >> 4) + kLf64);
+                                    umma_bf16_ts(d2, t_ahi + (uint32_t)ks * 8u, b_w, idesc64w, ks != 0);
+                                    umma_bf16_ts(d2, t_alo + (uint32_t)ks * 8u, b_w, idesc64w, true);
+                                    if ((ks & 7) == 7) commit_slot(slot);
+                                }
+                                umma_commit(&bar_acc_full[(u + 1u) & 1u]);
+                            }
+                        }
+                    }
+                    __syncwarp();
+                    if (ds) { w_issue += clock64() - tq; tq = clock64(); }
+                }
+                ++u;
+                it += 4;
+            }
+            if constexpr (kFuseHeads) {
+                ++u;
+                it += 2;
+            }
+            static_assert(TS::kSmallUnit == kFuseHeads && (TS::kSmallUnit ? TS::kFullUnits == 1 : true), "the 64-column unit exists in teams of 4 only");
+            if (ds) {
+                ds[7] = clock64();
+                ds[8] = w_full;
+                ds[9] = w_a;
+                ds[10] = 0;
+                ds[11] = w_issue;
+            }
+            if constexpr (kOde) {   // the flags were written before the x_ready arrival that released this evaluation
+                if (ld_volatile_shared(&s_final) && step + 1 == ld_volatile_shared(&s_allowed)) break;
+            }
+        }
+        } else {
         for (int step = 0; kOde || step < p.T; ++step) {
             unsigned long long *ds = (dbg_cta && lane == 0 && step < p.T) ? p.dbg + ((size_t)p.T + step) * 16 : nullptr;   // ODE: T = recorded evaluations
             unsigned long long w_full = 0, w_a = 0, w_acc = 0, tq = 0, w_issue = 0;
@@ -363,7 +548,7 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
                     // accumulation order inside the unit changes, nothing else.
                     constexpr int kUnitSlots = kW16 ? 4 : 8;
                     if (ds) tq = clock64();
-                    wait_slots(kUnitSlots);
+                    wait_slots(kFuseL1 ? 2 * kUnitSlots : kUnitSlots);
                     TRS(7);
                     if (ds) { w_full += clock64() - tq; tq = clock64(); }
                     const uint32_t s_first = it % kSlots;
@@ -374,14 +559,15 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
                     };
                     for (int g = 0; g < 4; ++g) {
                         if (ds) tq = clock64();
-                        mbar_wait(&bar_h1_ready[g], hr & 1u);
+                        // (fused: quarters 2 and 3 are both there when quarter 1 has been issued: one wait, on the later of the two)
+                        if (!(kFuseL1 && g == 3)) mbar_wait(&bar_h1_ready[kFuseL1 && g == 2 ? 3 : g], hr & 1u);
                         TRS(8 + 3 * g);
                         if (ds) {
                             w_a += clock64() - tq;
                             if (g == 0) ds[3] = clock64();
                             tq = clock64();
                         }
-                        tc_fence_after_sync();      // (accumulator: free once quarter 0 is published, which follows its last read)
+                        if (!(kFuseL1 && g == 3)) tc_fence_after_sync();      // (accumulator: free once quarter 0 is published, which follows its last read)
                         TRS(9 + 3 * g);
                         if (ds) { w_acc += clock64() - tq; tq = clock64(); }
                         const int base = 8 * (g >> 1) + 2 * (g & 1);
@@ -425,7 +611,9 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
                     const int groups = split ? 2 : 1, per = (split ? 4 : 8) / (kW16 ? 2 : 1);   // (unit 1 in two groups of 4: slower, 7.26 -> 7.35 ms)
                     for (int g = 0; g < groups; ++g) {
                         if (ds) tq = clock64();
-                        wait_slots(per);                           // before the operand wait (see layer 0)
+                        // before the operand wait (see layer 0); fused: unit 1's slots were awaited with unit 0's, the whole head
+                        // slice's (6 slots of this rank) in front of head unit 0
+                        if (unit == 1 ? !kFuseL1 : !(kFuseHeads && g == 1)) wait_slots(kFuseHeads && unit == 2 ? TS::kHeadSlots : per);
                         TRS(unit == 1 ? 20 : 23 + 4 * g);
                         if (ds) { w_full += clock64() - tq; tq = clock64(); }
                         if (split) {
@@ -443,7 +631,7 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
                         // head units 0 and 1 those of layer 1 (read before pf half 0 / half 1 were published): only head units >= 2
                         // wait for an explicit release, by the epilogue of head unit - 2
                         if (g == 0 && unit >= 4) mbar_wait(&bar_acc_empty[b], (n & 1u) ^ 1u);
-                        tc_fence_after_sync();
+                        if (!(kFuseL1 && unit == 1)) tc_fence_after_sync();
                         TRS(unit == 1 ? 21 : 25 + 4 * g);
                         if (ds) { w_acc += clock64() - tq; tq = clock64(); }
                         if (ds && unit == 1) ds[14] = clock64();     // layer 1 unit b: waits done, issue starts
@@ -497,7 +685,7 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
                 } else {
                     if (ds) tq = clock64();
                     constexpr int kSmallSlots = kW16 ? 2 : 4;
-                    wait_slots(kSmallSlots);
+                    if (!kFuseHeads) wait_slots(kSmallSlots);
                     TRS(31);
                     if (ds) { w_full += clock64() - tq; tq = clock64(); }
                     static_assert(!TS::kSmallUnit || TS::kHeadUnits == 2, "the 64-column unit is head unit 1: its accumulator is free once pf is complete");
@@ -562,6 +750,7 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
             if constexpr (kOde) {   // the flags were written before the x_ready arrival that released this evaluation
                 if (ld_volatile_shared(&s_final) && step + 1 == ld_volatile_shared(&s_allowed)) break;
             }
+        }
         }
     } else {
         // =============================== row warps ===============================

@@ -83,4 +83,6 @@ ev = [("row: step start", row[:, 0]), ("row: L0 acc ready", row[:, 1]), ("row: L
 base = row[:, 0]
 print("timeline (cycles after the row thread's step start; x_ready / x published belong to the step boundary):")
 for name, v in sorted(ev, key=lambda e: np.mean((e[1] - base) % 1e9)):
+    if np.all(v == 0):
+        continue                       # stamp not recorded by this path (f16x2 issues layer 1 as fused groups)
     print(f"  {np.mean(v - base):9.0f}  {name}")
