@@ -414,9 +414,9 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
             }
             // ---- this rank's head slice: pf arrives in two halves (K columns [0,128) and [128,256)) ----
             if (ds) tq = clock64();
-#pragma unroll
-            for (int hu = 0; hu < TS::kFullUnits; ++hu) {
-                const int hs = TS::kCommonSlots + 4 * hu;                 // the unit's first slot
+            static_for<0, TS::kFullUnits>([&](auto HU) {   // (a compile-time loop: `#pragma unroll` leaves six units partly rolled, which
+                constexpr int hu = decltype(HU)::value;     //  turns the slot schedule into a local-memory array)
+                constexpr int hs = TS::kCommonSlots + 4 * hu;             // the unit's first slot
                 const uint32_t b = u & 1u, n = u >> 1;
                 const uint32_t d = tmem_base + kColD + b * 128u;
                 if (hu == 0 || !kFuseHeads) wait_slots(hu == 0 && kFuseHeads ? TS::kHeadSlots : 4);
@@ -464,7 +464,7 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
                 }
                 ++u;
                 it += 4;
-            }
+            });
             if constexpr (kFuseHeads) {
                 ++u;
                 it += 2;
