@@ -82,6 +82,10 @@ constexpr uint32_t kLboB64 = 1024;                 // 64-row operand images
 constexpr uint32_t kLboB = 2048, kSbo = 128;       // 128-row operand images
 constexpr int kMaxObjPerTile = 8;                 // objects a 128-row tile may span: K >= 19 candidates per object
 constexpr uint32_t kColD = 0, kColAhi = 256, kColAlo = 384;
+// x (three bf16 pieces, 8 columns each) lives in the LAST 24 columns of A_lo: layer 0's epilogue overwrites them only with its third
+// h1 quarter, which needs the second layer-0 accumulator anyway — so the first two quarters go out as soon as the FIRST accumulator
+// is complete, while the tensor pipe is still on the second (x at the front of A_hi made quarter 0 wait for every layer-0 MMA)
+constexpr uint32_t kColX = kColAlo + 104;
 // per-step grid reduction word of the PC kernel: [63:56] arrived tiles, [55:48] poisoned tiles, [47:0] sum of the tile sums as
 // 22.18 fixed point of (tile sum x min(sigma(t), 1)) x up to 255 tiles (a tile sum is 128 row norms |f| / sigma: the limit 2^22 is
 // 32,768 per row on average at sigma >= 1 and 3.3 M per row at sigma = 0.01)
@@ -286,7 +290,7 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
         // The WHOLE warp runs this loop (uniform control flow => descriptors and TMEM addresses live in uniform registers);
         // one elected lane issues each group of tcgen05.mma / tcgen05.commit.
         const uint32_t ring = smem_u32(sRing);
-        const uint32_t t_ahi = tmem_base + kColAhi, t_alo = tmem_base + kColAlo;
+        const uint32_t t_ahi = tmem_base + kColAhi, t_alo = tmem_base + kColAlo, t_x = tmem_base + kColX;
         uint32_t u = 0, it = 0, xr = 0, ar = 0, hr = 0;
         // wait for n_slots consecutive ring slots starting at stream position `it`: lane l polls slot l (one wait latency)
         // f16x2 (one weight image: layer 1 is 8 slots, a team-of-4 rank's head slice 6): fewer, larger issue groups.  The tensor pipe
@@ -353,11 +357,11 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
                     const uint32_t b = (u + (uint32_t)half) & 1u;
                     const uint32_t d = tmem_base + kColD + b * 128u;
                     const uint64_t bhi = desc(dl[0] + (uint32_t)half * 512u + kLf128), blo = desc(dl[0] + (uint32_t)half * 512u + 256u + kLf128);
-                    umma_bf16_ts(d, t_ahi + 0u, bhi, idesc128, false);
-                    umma_bf16_ts(d, t_ahi + 8u, bhi, idesc128, true);
-                    umma_bf16_ts(d, t_ahi + 16u, bhi, idesc128, true);
-                    umma_bf16_ts(d, t_ahi + 0u, blo, idesc128, true);
-                    umma_bf16_ts(d, t_ahi + 8u, blo, idesc128, true);
+                    umma_bf16_ts(d, t_x + 0u, bhi, idesc128, false);
+                    umma_bf16_ts(d, t_x + 8u, bhi, idesc128, true);
+                    umma_bf16_ts(d, t_x + 16u, bhi, idesc128, true);
+                    umma_bf16_ts(d, t_x + 0u, blo, idesc128, true);
+                    umma_bf16_ts(d, t_x + 8u, blo, idesc128, true);
                     if (half == 1) commit_slot(0);
                     umma_commit(&bar_acc_full[b]);
                 }
@@ -515,11 +519,11 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
                     const uint64_t bhi = make_smem_desc(ring + s * kSlotBytes + (uint32_t)half * 8192u, kLboB, kSbo);
                     const uint64_t blo = make_smem_desc(ring + s * kSlotBytes + (uint32_t)half * 8192u + 4096u, kLboB, kSbo);
                     if (elect_one_sync()) {
-                        umma_bf16_ts(d, t_ahi + 0u, bhi, idesc128, false);
-                        umma_bf16_ts(d, t_ahi + 8u, bhi, idesc128, true);
-                        umma_bf16_ts(d, t_ahi + 16u, bhi, idesc128, true);
-                        umma_bf16_ts(d, t_ahi + 0u, blo, idesc128, true);
-                        umma_bf16_ts(d, t_ahi + 8u, blo, idesc128, true);
+                        umma_bf16_ts(d, t_x + 0u, bhi, idesc128, false);
+                        umma_bf16_ts(d, t_x + 8u, bhi, idesc128, true);
+                        umma_bf16_ts(d, t_x + 16u, bhi, idesc128, true);
+                        umma_bf16_ts(d, t_x + 0u, blo, idesc128, true);
+                        umma_bf16_ts(d, t_x + 8u, blo, idesc128, true);
                         if (half == 1) umma_commit(&bar_empty[s]);
                         umma_commit(&bar_acc_full[b]);
                     }
@@ -784,9 +788,9 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
                 pc[1][j] = pack_bf16(b2[0], b2[1]);
                 pc[2][j] = pack_bf16(b3[0], b3[1]);
             }
-            tmem_st8(tm_row + kColAhi + 0u, pc[0]);
-            tmem_st8(tm_row + kColAhi + 8u, pc[1]);
-            tmem_st8(tm_row + kColAhi + 16u, pc[2]);
+            tmem_st8(tm_row + kColX + 0u, pc[0]);
+            tmem_st8(tm_row + kColX + 8u, pc[1]);
+            tmem_st8(tm_row + kColX + 16u, pc[2]);
             tmem_st_wait();
             tc_fence_before_sync();
             __syncwarp();
@@ -1056,10 +1060,10 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
                 const float *bias = sBias + layer * 256 + cs * 64;
                 if (layer == 0) {
                     // Layer 0 -> layer 1 in QUARTERS.  Nothing but layer 0's own MMAs reads the A region now (the previous step's
-                    // head MMAs completed before x was published), and those need only x in A_hi[0,24): once BOTH layer-0
-                    // accumulators are complete — ten small MMAs, ~0.3 k cycles apart — a 32-column piece of h1 can be stored as
-                    // soon as it is converted.  The MMA warp starts layer 1 on the first quarter (~0.55 k cycles earlier than on
-                    // the first half); quarter g = K-steps {base, base + 1, base + 4, base + 5}, base = 8 (g / 2) + 2 (g % 2).
+                    // head MMAs completed before x was published), and those need only x at the END of A_lo (kColX), which quarters
+                    // 2 and 3 overwrite: quarters 0 and 1 are stored as soon as the FIRST accumulator is converted, the other two
+                    // once the second one is complete.  The MMA warp starts layer 1 on the first quarter;
+                    // quarter g = K-steps {base, base + 1, base + 4, base + 5}, base = 8 (g / 2) + 2 (g % 2).
                     const uint32_t b0 = u & 1u, n0 = u >> 1, b1 = (u + 1u) & 1u, n1 = (u + 1u) >> 1;
                     uint32_t v[32], h16[16], l16[16];
                     mbar_wait(&bar_acc_full[b0], n0 & 1u);
@@ -1068,8 +1072,6 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
                     tmem_ld32(tm_row + kColD + b0 * 128u + (uint32_t)cs * 64u, v);
                     tmem_ld_wait();
                     relu_split32<kW16>(v, bias, h16, l16);
-                    mbar_wait(&bar_acc_full[b1], n1 & 1u);          // every layer-0 MMA has read x
-                    tc_fence_after_sync();
 #pragma unroll
                     for (int qd = 0; qd < 4; ++qd) {
                         const uint32_t bq = qd < 2 ? b0 : b1;
@@ -1077,6 +1079,10 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
                         tmem_st16(tm_row + kColAhi + a_col, h16);
                         tmem_st16(tm_row + kColAlo + a_col, l16);
                         if (qd < 3) {   // the next 32 accumulator columns travel while the stores drain
+                            if (qd == 1) {   // second accumulator: complete = every layer-0 MMA has read x, which quarters 2 and 3 overwrite
+                                mbar_wait(&bar_acc_full[b1], n1 & 1u);
+                                tc_fence_after_sync();
+                            }
                             const uint32_t bn = qd + 1 < 2 ? b0 : b1;
                             tmem_ld32(tm_row + kColD + bn * 128u + (uint32_t)cs * 64u + (uint32_t)((qd + 1) & 1) * 32u, v);
                             tmem_ld_wait();
