@@ -906,10 +906,29 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
             named_bar_sync(5, 256);
         };
         // (object bias + time bias of evaluation `gi` of the group) -> this rank's column slice of sObt, by `nthr` threads from `t0`
-        auto fill_obt = [&](int gi, int t0, int nthr) {
-            for (int i = tid - t0; i < n_obj * kCols; i += nthr) {
-                const int o = i / kCols, cc = n_lo + i % kCols;
-                sObt[o * kCols + i % kCols] = __ldg(p.obj_bias + (size_t)(obj_lo + o) * 768 + cc) + __ldcg(tb_mine + gi * kCols + i % kCols);
+        // Column c0 + nt j of every object: the time biases once, then the object biases of up to four objects as ONE batch of independent
+        // loads (a tile of K = 50 candidates spans three or four objects).  (As a plain loop over (object, column) this was one L2 round
+        // trip per element and thread — 6 in a team of 4, 24 in a team of 1 — and column half 1 came late to the next layer-0 epilogue.)
+        auto fill_obt = [&](int gi, int t0, auto NT) {
+            constexpr int nt = decltype(NT)::value, kPerT = ((int)kCols + nt - 1) / nt;
+            const int c0 = tid - t0;
+            const float *tbn = tb_mine + gi * kCols;
+            const float *obn = p.obj_bias + (size_t)obj_lo * 768 + n_lo;
+            float tbv[kPerT];
+#pragma unroll
+            for (int j = 0; j < kPerT; ++j) tbv[j] = c0 + nt * j < (int)kCols ? __ldcg(tbn + c0 + nt * j) : 0.f;
+            for (int o0 = 0; o0 < n_obj; o0 += 4) {
+                float v[4][kPerT];
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+#pragma unroll
+                    for (int j = 0; j < kPerT; ++j)
+                        v[k][j] = (o0 + k < n_obj && c0 + nt * j < (int)kCols) ? __ldg(obn + (size_t)(o0 + k) * 768 + c0 + nt * j) : 0.f;
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+#pragma unroll
+                    for (int j = 0; j < kPerT; ++j)
+                        if (o0 + k < n_obj && c0 + nt * j < (int)kCols) sObt[(o0 + k) * kCols + c0 + nt * j] = v[k][j] + tbv[j];
             }
         };
         // solver state, replicated bit-identically in every row thread of every rank (scipy/integrate/_ivp/rk.py, common.py)
@@ -928,6 +947,8 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
         // exact; [rank][stage][row][12] floats = three 16-byte words per row and stage, private to this thread, L2-resident
         float *Kmine = reinterpret_cast<float *>(od.Kst) + ((size_t)rank * 7 * p.R + (valid ? row : 0)) * 12;
         const size_t kst = (size_t)p.R * 12;
+        // P (below): [4 ranks][R][10] float64 behind the 4 x 7 x R x 12 floats of the stages (the buffer is sized for float64 stages)
+        double *Pmine = reinterpret_cast<double *>(reinterpret_cast<float *>(od.Kst) + (size_t)4 * 7 * p.R * 12) + ((size_t)rank * p.R + (valid ? row : 0)) * 10;
         auto store_k = [&](int stage, const double (&k)[9]) {
             float4 *dst = reinterpret_cast<float4 *>(Kmine + (size_t)stage * kst);
             __stcg(dst, make_float4((float)k[0], (float)k[1], (float)k[2], (float)k[3]));
@@ -944,6 +965,29 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
                              : "=f"(k[4 * w4]), "=f"(k[4 * w4 + 1]), "=f"(k[4 * w4 + 2]), "=f"(k[4 * w4 + 3])
                              : "l"(src + 4 * w4)
                              : "memory");
+        };
+        // RK45 attempt, column half 1: P = sum_{j < stn - 1} coef_j K_j of the NEXT stage stn >= 2 for this row (see barrier 3); those
+        // stages were stored before the current evaluation's barriers, K_{stn-1} is what half 0 produces in this evaluation's tail.
+        // Teams of 2 and 4 only (in the tail, where half 1 idles); a team of 1 has no exchange, a short tail and a tensor-pipe-bound
+        // evaluation: there half 0 accumulates all of `pre` under the layer-1 MMAs (measured: 2.07 vs 2.14 ms at 256 objects).
+        auto accumulate_P = [&](int stn) {
+            float kf[5][12];
+#pragma unroll
+            for (int j = 0; j < 5; ++j) load_k(j, kf[j]);
+            double P[10];
+#pragma unroll
+            for (int c = 0; c < 10; ++c) P[c] = 0.0;
+#pragma unroll
+            for (int j = 0; j < 5; ++j) {
+                const double a = stn < 5 ? kRkA[stn + 1][j] : (stn == 5 ? kRkB[j] : kRkE[j]);
+#pragma unroll
+                for (int c = 0; c < 9; ++c) P[c] += (j < stn - 1 && valid) ? (double)kf[j][c] * a : 0.0;
+            }
+            if (valid) {                  // (an invalid thread's pointers alias row 0)
+                double2 *pd2 = reinterpret_cast<double2 *>(Pmine);
+#pragma unroll
+                for (int i = 0; i < 5; ++i) __stcg(pd2 + i, make_double2(P[2 * i], P[2 * i + 1]));
+            }
         };
         // two grid-wide float64 sums with ONE barrier; every CTA obtains the identical fixed-order totals
         auto grid_sum2 = [&](double a, double b, double &A, double &B) {
@@ -1030,6 +1074,14 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
         for (int step = 0; kOde || step < p.T; ++step) {
             unsigned long long *ds = (dbg && step < p.T) ? p.dbg + (size_t)step * 16 : nullptr;
             if (ds) ds[0] = clock64();
+#ifdef GPB_DBG_TRACE
+            // experiment builds only: eight extra stamps per step of row thread 0 (slots 0..3) and of thread 128, column half 1 (4..7)
+            unsigned long long *rtr = (dbg_cta && (tid == 0 || tid == 128) && step < p.T) ? p.dbg + (size_t)2 * p.T * 16 + (size_t)step * 8 + (tid >> 5) : nullptr;
+#define RTR(i) do { if (rtr) rtr[i] = clock64(); } while (0)
+#else
+#define RTR(i) do { } while (0)
+#endif
+            RTR(0);
             if constexpr (SM::kNoiseByHalf1) {
                 // The two noise draws of this step (18 normals per row: six Philox blocks + Box-Muller, or 18 loads) are produced by
                 // COLUMN HALF 1, whose warps reach this point during the previous step's tail (exchange, norm, grid word, update
@@ -1107,6 +1159,7 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
                 {   // unit a: columns [0,128) of the layer; this thread: [cs*64, +64)
                     const uint32_t b = u & 1u, n = u >> 1;
                     mbar_wait(&bar_acc_full[b], n & 1u);
+                    RTR(3);
                     if (ds) ds[1 + 2 * layer] = clock64();
                     tc_fence_after_sync();
                     {
@@ -1163,24 +1216,24 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
                     if (layer == 0 && tb_pending) {
                         if (gn == 6) time_biases(std::integral_constant<int, 6>{});
                         else time_biases(std::integral_constant<int, 1>{});
-                        fill_obt(0, 0, 256);
+                        fill_obt(0, 0, std::integral_constant<int, 256>{});
                         tb_pending = false;
                     }
-                    if (layer == 0 && cs == 0 && phase == kPhAttempt) {
-                        // stage `st` is being evaluated: the stages before it are in L2 (this thread's own stores).  Coefficients: the
-                        // row a[st+1] for st < 5, the 5th-order weights b for st == 5 (-> y_new), the error weights E for st == 6;
-                        // same summation order as the in-line form it replaces (j ascending, the new stage last).
-                        float kf[6][12];
+                    if constexpr (kTeam == 1) {
+                        if (layer == 0 && cs == 0 && phase == kPhAttempt) {
+                            // a team of 1: all of pre = sum_{j < st} coef_j K_j here, under the layer-1 MMAs (see accumulate_P / barrier 3)
+                            float kf[6][12];
 #pragma unroll
-                        for (int j = 0; j < 6; ++j) load_k(j, kf[j]);
-                        const int nj = st < 5 ? st : (st == 5 ? 5 : 6);
+                            for (int j = 0; j < 6; ++j) load_k(j, kf[j]);
+                            const int nj = st < 5 ? st : (st == 5 ? 5 : 6);
 #pragma unroll
-                        for (int c = 0; c < 9; ++c) pre[c] = 0.0;
+                            for (int c = 0; c < 9; ++c) pre[c] = 0.0;
 #pragma unroll
-                        for (int j = 0; j < 6; ++j) {
-                            const double a = st < 5 ? kRkA[st + 1][j < 5 ? j : 0] : (st == 5 ? kRkB[j] : kRkE[j]);
+                            for (int j = 0; j < 6; ++j) {
+                                const double a = st < 5 ? kRkA[st + 1][j < 5 ? j : 0] : (st == 5 ? kRkB[j] : kRkE[j]);
 #pragma unroll
-                            for (int c = 0; c < 9; ++c) pre[c] += (j < nj && valid) ? (double)kf[j][c] * a : 0.0;
+                                for (int c = 0; c < 9; ++c) pre[c] += (j < nj && valid) ? (double)kf[j][c] * a : 0.0;
+                            }
                         }
                     }
                 }
@@ -1216,6 +1269,35 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
                 }
             }
             named_bar_sync(3, kTcRowWarps * 32);      // sObt holds obj_bias + t_bias of THIS step (written by warps 4-7)
+            if constexpr (kOde && kTeam > 1) {
+                if (cs == 0 && phase == kPhAttempt) {
+                    // Stage `st` is being evaluated.  The part of the next stage combination that does not depend on this evaluation is
+                    //     pre = sum_{j < st} coef_j K_j,   coef = a[st+1] (st < 5), b (st == 5 -> y_new), E (st == 6 -> error),
+                    // summed j ascending like the in-line form.  Column half 1 accumulated j < st - 1 during the previous evaluation's
+                    // tail, where it idles (P, below); what is left here is ONE multiply-add per component with the newest stage, issued
+                    // behind barrier 3 and complete long before the first head accumulator.  (All of it used to run here in half 0,
+                    // between the layer-0 and layer-1 epilogues: ~4 k cycles — an out-of-line block of ~400 instructions fetched
+                    // from L2 at every evaluation — of which ~2.9 k delayed pf and with it the head MMAs.)
+                    float kl[12];
+                    load_k(st - 1, kl);
+                    double P[10];
+                    if (st >= 2) {
+                        const double2 *ps = reinterpret_cast<const double2 *>(Pmine);
+#pragma unroll
+                        for (int i = 0; i < 5; ++i) {
+                            const double2 v = __ldcg(ps + i);
+                            P[2 * i] = v.x;
+                            P[2 * i + 1] = v.y;
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 10; ++i) P[i] = 0.0;
+                    }
+                    const double a = st < 5 ? kRkA[st + 1][st - 1] : (st == 5 ? kRkB[4] : kRkE[5]);
+#pragma unroll
+                    for (int c = 0; c < 9; ++c) pre[c] = valid ? P[c] + (double)kl[c] * a : 0.0;
+                }
+            }
             if (SM::kNoiseByHalf1 && cs == 0 && valid) {   // (before barrier 1: half 1 overwrites the buffer at the top of the next step)
 #pragma unroll
                 for (int c = 0; c < 9; ++c) {
@@ -1282,7 +1364,8 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
                 } else {
                     if (gi + 1 < gn) {                    // inside an evaluation group: the next time bias is already in tb_mine
                         ++gi;
-                        fill_obt(gi, 128, 128);
+                        fill_obt(gi, 128, std::integral_constant<int, 128>{});
+                        if (kTeam > 1 && gn == 6) accumulate_P(gi + 1);
                         continue;
                     }
                     named_bar_sync(4, 256);               // group boundary: warps 0-3 have decided what comes next
@@ -1938,6 +2021,14 @@ extern "C" int gpb_sample_ode_tc16(const float *x0, int R, int K, double T0, dou
                                    void *workspace, size_t workspace_bytes, void *stream) {
     return sample_ode_tc_impl(true, x0, R, K, T0, rtol, atol, denoise_steps, obj_bias, W, tc16_stream, pts_center, pose, stats, process,
                               process_cap, t_eval, n_t_eval, workspace, workspace_bytes, nullptr, 0, stream);
+}
+
+extern "C" int gpb_sample_ode_tc16_dbg(const float *x0, int R, int K, double T0, double rtol, double atol, int denoise_steps,
+                                       const float *obj_bias, const float *W, const void *tc16_stream, const float *pts_center, double *pose,
+                                       int *stats, void *workspace, size_t workspace_bytes, unsigned long long *dbg, int dbg_evals,
+                                       void *stream) {
+    return sample_ode_tc_impl(true, x0, R, K, T0, rtol, atol, denoise_steps, obj_bias, W, tc16_stream, pts_center, pose, stats, nullptr, 0,
+                              nullptr, 0, workspace, workspace_bytes, dbg, dbg_evals, stream);
 }
 
 extern "C" int gpb_sample_pc_tc(const float *x0, int R, int K, int num_steps, float snr, const float *obj_bias, const float *W,

@@ -38,6 +38,7 @@ SIGNATURES = {
     "gpb_set_tc_team": (_i, [_i]),
     "gpb_sample_ode_tc": (_i, [_vp, _i, _i, _d, _d, _d, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _vp, _sz, _vp]),
     "gpb_sample_ode_tc_dbg": (_i, [_vp, _i, _i, _d, _d, _d, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _i, _vp]),
+    "gpb_sample_ode_tc16_dbg": (_i, [_vp, _i, _i, _d, _d, _d, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _i, _vp]),
     "gpb_trunk_tc16_stream_bytes": (_sz, []),
     "gpb_sample_pc_tc16": (_i, [_vp, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _u64, _vp, _vp, _vp, _vp, _sz, _vp, _vp]),
     "gpb_sample_ode_tc16": (_i, [_vp, _i, _i, _d, _d, _d, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _vp, _sz, _vp]),

@@ -192,6 +192,11 @@ GPB_API int gpb_sample_ode_tc_dbg(const float *x0, int R, int K, double T0, doub
                           const float *obj_bias, const float *trunk_weights, const void *tc_stream, const float *pts_center,
                           double *pose, int *stats, void *workspace, size_t workspace_bytes, unsigned long long *dbg,
                           int dbg_evals, void *stream);
+/* the same for the two-product arithmetic (tc16_stream as gpb_sample_ode_tc16, below) */
+GPB_API int gpb_sample_ode_tc16_dbg(const float *x0, int R, int K, double T0, double rtol, double atol, int denoise_steps,
+                            const float *obj_bias, const float *trunk_weights, const void *tc16_stream, const float *pts_center,
+                            double *pose, int *stats, void *workspace, size_t workspace_bytes, unsigned long long *dbg,
+                            int dbg_evals, void *stream);
 
 /* gpb_sample_pc_tc / gpb_sample_ode_tc with TWO tensor-core products per K-step instead of three ("f16x2"): the activations
  * of layer 1 and of the heads are split into fp16 hi + lo (tensor memory, 21 mantissa bits), their weights are ONE fp16 image
