@@ -11,18 +11,29 @@ sim = importlib.util.module_from_spec(spec)
 spec.loader.exec_module(sim)
 
 
-def _violations(runs, steps, old):
+def _violations(runs, steps, old, **kw):
     bad = 0
     for seed in range(runs):
         try:
-            sim.Sim(steps, old, random.Random(seed)).run()
+            sim.Sim(steps, old, random.Random(seed), **kw).run()
         except sim.Violation:
             bad += 1
     return bad
 
 
 def test_shipped_protocol_has_no_violation():
+    # the f16x2 issuer: no accumulator waits (the operand announcements imply the release), fused issue groups
     assert _violations(300, 3, old=False) == 0
+
+
+def test_explicit_accumulator_waits_have_no_violation():
+    # the three-product issuer keeps one bar_acc_empty wait per unit
+    assert _violations(200, 3, old=False, implied=False) == 0
+
+
+def test_model_sees_a_false_implied_release():
+    # negative control: announcing the second operand half before reading unit b's accumulator breaks the implication
+    assert _violations(50, 2, old=False, late_read=True) > 0
 
 
 def test_model_sees_the_old_a_ready_race():

@@ -7,12 +7,18 @@ arbitrarily slow), that
   * an accumulator is only overwritten after all eight row warps have read the previous unit out of it,
   * a row warp never overwrites an A-operand region that an issued, not yet completed MMA group still reads.
 No GPU, no product code: a model of the protocol, kept next to the kernel so that a change of the protocol can be tried here first.
-    python tools/tc_protocol_sim.py [runs] [steps] [--old-a-ready]
+    python tools/tc_protocol_sim.py [runs] [steps] [--old-a-ready] [--explicit-acc-waits] [--late-read]
 --old-a-ready models the single 8-count bar_a_ready the kernel had before (both halves arriving on one barrier): the simulator
 finds the early-release race that motivated the split within a few hundred schedules.
+Default = the shipped f16x2 issuer (late round 2): NO accumulator waits — every operand announcement of the row warps (operand halves,
+x) follows their last read of the accumulator the announced MMAs overwrite — and fused issue groups (layer 1: first half | second
+half + unit b; heads: first half | second half + the 64-column unit).  --explicit-acc-waits is the protocol before that (one
+bar_acc_empty wait per unit, one group per wait).  --late-read is a negative control: the row warps announce the second operand
+half BEFORE reading unit b's accumulator, which makes the implied release false; the model reports the overwrite.
 Round 2 note: the kernel now publishes layer 0's output in FOUR pieces on four barriers (bar_h1_ready[0..3]) and layer 1's in two
 (bar_a_ready[0..1]) — the same one-barrier-per-piece rule this model established for halves; the model still simulates the
-two-halves form for both hand-offs."""
+two-halves form for both hand-offs, and keeps x inside the first operand half (the kernel moved it to the end of A_lo so that the
+first h1 quarters can be stored while layer 0's second unit still reads x: disjoint columns, not a protocol matter)."""
 import random
 import sys
 
@@ -38,8 +44,9 @@ class MBar:
 
 
 class Sim:
-    def __init__(self, steps, old_a_ready, rng):
+    def __init__(self, steps, old_a_ready, rng, implied=True, late_read=False):
         self.T, self.old, self.rng = steps, old_a_ready, rng
+        self.implied, self.late_read = implied and not old_a_ready, late_read
         self.acc_full = [MBar(f"acc_full{b}", 1) for b in range(2)]
         self.acc_empty = [MBar(f"acc_empty{b}", 8) for b in range(2)]
         self.a_ready = [MBar("a_ready0", 8), MBar("a_ready1", 8)]
@@ -112,16 +119,24 @@ class Sim:
                 yield (lambda b=b, n=n: self.acc_full[b].passed(n & 1))
                 self.write_A((q, 0, cs), tag, who)                     # first half of the new operand (held in registers until now)
                 yield None
-                self.read_D(b, (q, cs), (t, layer, "b"), who)
-                yield None
-                self.a_ready[0].arrive()
-                yield None
+                if not self.old:                                       # (round 2: announced before the next accumulator load)
+                    self.a_ready[0].arrive()
+                    yield None
+                if not self.late_read:
+                    self.read_D(b, (q, cs), (t, layer, "b"), who)
+                    yield None
+                if self.old:
+                    self.a_ready[0].arrive()
+                    yield None
                 self.acc_empty[b].arrive()
                 yield None
                 self.write_A((q, 1, cs), tag, who)
                 yield None
                 self.a_ready[0 if self.old else 1].arrive()
                 yield None
+                if self.late_read:                                     # negative control: the read follows the announcement
+                    self.read_D(b, (q, cs), (t, layer, "b"), who)
+                    yield None
                 u += 1
             yield from self.named_sync(3, w)
             for unit in ("h128", "h64"):
@@ -161,6 +176,29 @@ class Sim:
         for t in range(self.T):
             yield (lambda xr=xr: self.x_ready.passed(xr & 1))
             xr += 1
+            if self.implied:
+                # shipped f16x2 issuer: no accumulator waits, fused groups
+                for half in ("a", "b"):                                # layer 0 (x implies both accumulators free)
+                    b = u & 1
+                    self.issue([(q, 0, 0) for q in allq], ("x", t), b, (t, 0, half), True)
+                    self.pipe.append(("commit", self.acc_full[b]))
+                    u += 1
+                yield None
+                for layer, names, expect in ((1, ("a", "b"), ("h1", t)), (2, ("h128", "h64"), ("pf", t))):
+                    ba, bb = u & 1, (u + 1) & 1
+                    yield (lambda ar=ar: self.a_ready[0].passed((ar >> 1) & 1))
+                    ar += 1
+                    self.issue(first_half, expect, ba, (t, layer, names[0]), True)
+                    yield None
+                    yield (lambda ar=ar: self.a_ready[1].passed((ar >> 1) & 1))
+                    ar += 1
+                    self.issue(second_half, expect, ba, (t, layer, names[0]), False)
+                    self.pipe.append(("commit", self.acc_full[ba]))
+                    self.issue(first_half + second_half, expect, bb, (t, layer, names[1]), True)   # same issue group, no wait
+                    self.pipe.append(("commit", self.acc_full[bb]))
+                    yield None
+                    u += 2
+                continue
             for half in ("a", "b"):                                    # layer 0: both units read x
                 b, n = u & 1, u >> 1
                 yield (lambda b=b, n=n: self.acc_empty[b].passed((n & 1) ^ 1))
@@ -315,15 +353,18 @@ def main():
     runs = int(args[0]) if args else 2000
     steps = int(args[1]) if len(args) > 1 else 3
     old = "--old-a-ready" in sys.argv
+    implied, late = "--explicit-acc-waits" not in sys.argv, "--late-read" in sys.argv
     bad = 0
     for seed in range(runs):
         try:
-            Sim(steps, old, random.Random(seed)).run()
+            Sim(steps, old, random.Random(seed), implied=implied, late_read=late).run()
         except Violation as e:
             bad += 1
             if bad <= 3:
                 print(f"schedule {seed}: {e}")
-    print(f"{runs} random schedules x {steps} steps, protocol = {'single a_ready barrier (old)' if old else 'one a_ready barrier per half'}: "
+    name = "single a_ready barrier (old)" if old else ("one a_ready barrier per half, " + ("implied accumulator release + fused groups (shipped)"
+                                                                                        if implied else "explicit accumulator waits"))
+    print(f"{runs} random schedules x {steps} steps, protocol = {name}{', announcements before the read (negative control)' if late else ''}: "
           f"{bad} violations")
     bad_team = 0
     for seed in range(runs):
@@ -334,7 +375,7 @@ def main():
             if bad_team <= 3:
                 print(f"team schedule {seed}: {e}")
     print(f"{runs} random schedules x {steps + 3} steps, team exchange + grid word (3 teams of 4 ranks): {bad_team} violations")
-    return 1 if ((bad and not old) or bad_team) else 0
+    return 1 if ((bad and not old and not late) or bad_team) else 0
 
 
 if __name__ == "__main__":
