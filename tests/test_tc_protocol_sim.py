@@ -27,7 +27,8 @@ def test_shipped_protocol_has_no_violation():
 
 
 def test_explicit_accumulator_waits_have_no_violation():
-    # the three-product issuer keeps one bar_acc_empty wait per unit
+    # the protocol before that change: one bar_acc_empty wait per unit, one issue group per wait (head units >= 2 of the teams of
+    # 2 and 1 still wait this way)
     assert _violations(200, 3, old=False, implied=False) == 0
 
 
