@@ -1,6 +1,8 @@
 """One step of the PC sampler's MMA warp, boundary by boundary (experiment build only: `make variant NAME=trace EXTRA=-DGPB_DBG_TRACE=1`,
 run with GPB_LIB=genpose_b200/libgenpose_b200_trace.so).  The trace block sits behind the [2][T][16] phase stamps.
-    python tools/tc_mma_trace.py [T] [precision] [team] [objects]"""
+The boundary stamps live in the issue LOOP, which only the three-product arithmetic still runs (the f16x2 issuer is the straight-line
+code this trace led to: profiles/r2x_mma_trace.txt was taken on the f16x2 loop of the commit before it), so bf16x3 is the default here.
+    python tools/tc_mma_trace.py [T] [bf16x3] [team] [objects]"""
 import sys
 
 import numpy as np
@@ -10,7 +12,7 @@ sys.path.insert(0, ".")
 from genpose_b200 import lib, ops, synth  # noqa: E402
 
 T = int(sys.argv[1]) if len(sys.argv) > 1 else 100
-W16 = not (len(sys.argv) > 2 and sys.argv[2] == "bf16x3")
+W16 = len(sys.argv) > 2 and sys.argv[2] == "f16x2"   # (no boundary stamps in the f16x2 issuer: the trace prints only the row side)
 TEAM = int(sys.argv[3]) if len(sys.argv) > 3 else 0
 B, K = (int(sys.argv[4]) if len(sys.argv) > 4 else 64), 50
 eng = ops.Engine(synth.make_state_dict(0, kappa=synth.stable_kappa(T)))
