@@ -1384,17 +1384,12 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
             for (int hh = 0; hh < kTouched; ++hh)
 #pragma unroll
                 for (int c = 0; c < 3; ++c) o[hh][c] += sFpart[r * 12 + 3 * hh + c];
-            // step constants of the update (they depend on t only): computed while the team's partials are in flight — after the send, not
-            // in front of it
-            float inv_std, g_sde, g2_sde, g_sqrt_step, nsum_scale;
-            auto step_constants = [&]() {
-                inv_std = 1.0f / stdv;   // one IEEE division per row and step instead of nine (<= 1.5 ulp from f / std, scorenet.py:217)
-                g_sde = sigma * kGCoef, g2_sde = g_sde * g_sde, g_sqrt_step = g_sde * sqrt_step;   // ve_sde diffusion (sde.py:20-24)
-                nsum_scale = kNormSumScale * fminf(sigma, 1.0f);   // fixed-point scale of the reduction word: norms grow like 1 / sigma(t)
-            };
+            // step constants of the update, computed before the team's partials arrive (they depend on t only)
+            const float inv_std = 1.0f / stdv;   // one IEEE division per row and step instead of nine (<= 1.5 ulp from f / std, scorenet.py:217)
+            const float g_sde = sigma * kGCoef, g2_sde = g_sde * g_sde, g_sqrt_step = g_sde * sqrt_step;   // ve_sde diffusion (sde.py:20-24)
+            const float nsum_scale = kNormSumScale * fminf(sigma, 1.0f);   // fixed-point scale of the reduction word: norms grow like 1 / sigma(t)
             float f[9];
             if constexpr (kTeam == 1) {
-                step_constants();
 #pragma unroll
                 for (int c = 0; c < 9; ++c) f[c] = o[c / 3][c % 3];
                 if (ds) ds[11] = ds[10] = clock64();
@@ -1416,7 +1411,6 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
                     st_async_f2(ra + 16u, o[1][1], o[1][2], rb);
                 }
                 if (ds) ds[11] = clock64();
-                step_constants();
                 mbar_wait_cluster(&bar_mail[par], ((uint32_t)step >> 1) & 1u);
                 if (ds) ds[10] = clock64();
                 const float *mb = sMail + ((size_t)(par * kTeam) * 128 + r) * 8;
@@ -1712,16 +1706,12 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
 #pragma unroll
                 for (int c = 0; c < 9; ++c) pd[c] = (0.0f - g2_sde * gr[c]) * step_size;
                 if (tid == 0) {
-                    // (the reciprocal of the scale is formed while the word is in flight: a float64 division behind the poll was ~0.3 k
-                    // cycles of this one thread with everyone else waiting at the barrier below; the product differs from the quotient by
-                    // at most one float64 ulp, identically in every CTA, before it is rounded to fp32)
-                    const double inv_scale = 1.0 / (double)nsum_scale;
                     unsigned long long v;
                     do {
                         v = ld_relaxed_gpu_u64(p.acc + step);
                     } while ((unsigned)(v >> 56) < (unsigned)n_tiles);
                     const bool poisoned = ((v >> 48) & 255ull) != 0ull;
-                    s_red[4] = poisoned ? __int_as_float(0x7fc00000) : (float)((double)(v & ((1ull << 48) - 1ull)) * inv_scale);
+                    s_red[4] = poisoned ? __int_as_float(0x7fc00000) : (float)((double)(v & ((1ull << 48) - 1ull)) / (double)nsum_scale);
                     if (ds) ds[15] = clock64();
                 }
                 named_bar_sync(2, 128);
