@@ -297,11 +297,6 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
         const uint32_t t_ahi = tmem_base + kColAhi, t_alo = tmem_base + kColAlo, t_x = tmem_base + kColX;
         uint32_t u = 0, it = 0, xr = 0, ar = 0, hr = 0;
         // wait for n_slots consecutive ring slots starting at stream position `it`: lane l polls slot l (one wait latency)
-        // f16x2 (one weight image: layer 1 is 8 slots, a team-of-4 rank's head slice 6): fewer, larger issue groups.  The tensor pipe
-        // accepts an MMA only about when it starts it (issue time = execution time), so every wait between two groups idles the pipe:
-        // layer 1 is issued as q0 | q1 | q2 + q3 + unit b behind ONE slot wait, the head slice as first half | second half + 64-column
-        // unit behind one more.  (Three-product arithmetic: layer 1 alone is 16 slots, more than the ring holds.)
-        constexpr bool kFuseL1 = false, kFuseHeads = false;   // (the f16x2 path below fuses; layer 1 of the three-product path is 16 slots)
         auto wait_slots = [&](int n_slots) {
             if (lane < n_slots) {
                 const uint32_t itl = it + (uint32_t)lane;
@@ -310,20 +305,24 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
             __syncwarp();
             tc_fence_after_sync();
         };
-        if constexpr (kW16) {
-        // ---- f16x2 (one fp16 weight image; A = fp16 hi / lo): straight-line issue code ----
+        // ---- straight-line issue code ----
         // The tensor pipe accepts an MMA only about when it starts it (issue time = execution time), so everything this thread does
         // between two issue groups idles the pipe.  Hence: (1) the step's slot schedule — ring position, descriptor address field and
         // release barrier of each of its slots — is computed at the top of the step, under the wait for x, and every loop below is
-        // unrolled over it (no index arithmetic behind a wait); (2) few, large groups: layer 1 is q0 | q1 | q2 + q3 + unit b behind ONE
-        // slot wait, a team-of-4 head slice first half | second half + 64-column unit behind one more; (3) no accumulator waits where
-        // an operand hand-off implies the release (see the row warps).
+        // unrolled over it (no index arithmetic behind a wait); (2) few, large groups: with f16x2 (one weight image: layer 1 is 8 slots,
+        // a team-of-4 rank's head slice 6) layer 1 is q0 | q1 | q2 + q3 + unit b behind ONE slot wait and the team-of-4 head slice
+        // first half | second half + 64-column unit behind one more; with three products a unit is 8 slots (layer 1 alone is more
+        // than the ring holds), so every unit has its own slot wait; (3) no accumulator waits where an operand hand-off implies the
+        // release (see the row warps).
         constexpr int NS = TS::kSlotsPerCtaStep;
+        constexpr int kUS = kW16 ? 4 : 8;                                                       // slots of a 128-column unit (K = 256)
+        constexpr int kKpS = 16 / kUS;                                                          // K-steps (16 inputs) per slot
         constexpr uint32_t kDescHi = ((kSbo >> 4) & 0x3FFFu) | (1u << 14);                      // SBO | descriptor version (bit 46)
         constexpr uint32_t kLf128 = ((kLboB >> 4) & 0x3FFFu) << 16, kLf64 = ((kLboB64 >> 4) & 0x3FFFu) << 16;
-        constexpr bool kFuseHeads = TS::kSmallUnit;
-        static_assert(8 <= kSlots, "layer 1 waits for its 8 slots at once");
+        constexpr bool kFuseL1 = kW16, kFuseHeads = kW16 && TS::kSmallUnit;
+        static_assert(kUS <= kSlots && (!kFuseL1 || 2 * kUS <= kSlots), "slot waits must fit the ring");
         static_assert(!kFuseHeads || (TS::kHeadSlots <= kSlots && TS::kHeadUnits == 2), "a team-of-4 head slice waits for all its slots at once");
+        static_assert(!TS::kSmallUnit || TS::kFullUnits == 1, "the 64-column unit exists in teams of 4 only (head unit 1)");
         auto desc = [&](uint32_t lo) { return ((uint64_t)kDescHi << 32) | (uint64_t)lo; };
         const uint32_t empty0 = smem_u32(&bar_empty[0]);
         uint32_t sring = 0;                                                                     // ring position of the step's first slot
@@ -343,13 +342,30 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
                 sring = s;
             }
             auto commit_slot = [&](int i) { asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(eb[i]) : "memory"); };
-            // one 128-column K-step (16 inputs) of a K = 256 unit: slot i holds four of them
-            auto kstep128 = [&](uint32_t d, int slot, int ks, bool acc) {
-                const uint64_t b_w = desc(dl[slot] + (uint32_t)((2u * (uint32_t)(ks & 3) * kLboB) >> 4) + kLf128);
-                umma_bf16_ts(d, t_ahi + (uint32_t)ks * 8u, b_w, idesc128w, acc);
-                umma_bf16_ts(d, t_alo + (uint32_t)ks * 8u, b_w, idesc128w, true);
+            // K-step ks (16 inputs) of a 128-column, K = 256 unit whose first slot is `first`.  f16x2: four K-steps per slot, one fp16 image,
+            // products Ahi.W + Alo.W; three products: two K-steps per slot, [hi 8 KiB | lo 8 KiB], Ahi.Bhi + Alo.Bhi + Ahi.Blo
+            auto kstep128 = [&](uint32_t d, int first, int ks, bool acc) {
+                const uint32_t ac = (uint32_t)ks * 8u;                                          // K index / 2
+                if constexpr (kW16) {
+                    const uint64_t b_w = desc(dl[first + (ks >> 2)] + (uint32_t)((2u * (uint32_t)(ks & 3) * kLboB) >> 4) + kLf128);
+                    umma_bf16_ts(d, t_ahi + ac, b_w, idesc128w, acc);
+                    umma_bf16_ts(d, t_alo + ac, b_w, idesc128w, true);
+                } else {
+                    const uint32_t lo = dl[first + (ks >> 1)] + (uint32_t)((2u * (uint32_t)(ks & 1) * kLboB) >> 4) + kLf128;
+                    const uint64_t b_hi = desc(lo), b_lo = desc(lo + (8192u >> 4));
+                    umma_bf16_ts(d, t_ahi + ac, b_hi, idesc128, acc);
+                    umma_bf16_ts(d, t_alo + ac, b_hi, idesc128, true);
+                    umma_bf16_ts(d, t_ahi + ac, b_lo, idesc128, true);
+                }
             };
-            // ---- layer 0: h1_pre = x . P1^T   (K = 16; x pieces x1,x2,x3 at A_hi[0,8),[8,16),[16,24); P1 hi|lo per unit) ----
+            auto unit_ksteps = [&](uint32_t d, int first, int k0, int k1) {                     // K-steps [k0, k1) in order, slots released as they end
+#pragma unroll
+                for (int ks = k0; ks < k1; ++ks) {
+                    kstep128(d, first, ks, ks != 0);
+                    if (ks % kKpS == kKpS - 1) commit_slot(first + ks / kKpS);
+                }
+            };
+            // ---- layer 0: h1_pre = x . P1^T   (K = 16; x pieces x1,x2,x3 at kColX + 0, 8, 16; P1 hi|lo per unit) ----
             wait_slots(1);
             mbar_wait_inline(&bar_x_ready, xr & 1u);          // (implies both accumulators free: x follows every head epilogue)
             ++xr;
@@ -376,7 +392,7 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
             it += 1;
             // ---- layer 1: unit a on the h1 quarters (quarter g = K-steps {base, base + 1, base + 4, base + 5}, base = 8 (g / 2) + 2 (g % 2):
             //      row thread (q, cs) converts columns [64 cs, 64 cs + 64) of either unit, 32 at a time), unit b behind it ----
-            wait_slots(8);
+            wait_slots(kFuseL1 ? 2 * kUS : kUS);
             if (ds) { w_full += clock64() - tq; tq = clock64(); }
             {
                 const uint32_t da = tmem_base + kColD + (u & 1u) * 128u, db = tmem_base + kColD + ((u + 1u) & 1u) * 128u;
@@ -396,38 +412,52 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
 #pragma unroll
                             for (int e = 0; e < 4; ++e) {
                                 const int ks = base + (e & 1) + 4 * (e >> 1);
-                                kstep128(da, 1 + (ks >> 2), ks, (gg | e) != 0);
+                                kstep128(da, 1, ks, (gg | e) != 0);
                             }
-                            if (gg & 1) {   // quarters 2 (gg / 2), 2 (gg / 2) + 1 cover K-steps [8 (gg / 2), +8): two slots done
-                                commit_slot(1 + (gg >> 1) * 2);
-                                commit_slot(2 + (gg >> 1) * 2);
+                            if constexpr (kW16) {
+                                if (gg & 1) {   // quarters 2 (gg / 2), 2 (gg / 2) + 1 cover K-steps [8 (gg / 2), +8): two slots done
+                                    commit_slot(1 + (gg >> 1) * 2);
+                                    commit_slot(2 + (gg >> 1) * 2);
+                                }
+                            } else {            // two K-steps per slot: the quarter's K-step pairs are slots base / 2 and base / 2 + 2
+                                commit_slot(1 + base / 2);
+                                commit_slot(1 + base / 2 + 2);
                             }
                         }
                         if (g == 2) {
                             umma_commit(&bar_acc_full[u & 1u]);
-#pragma unroll
-                            for (int ks = 0; ks < 16; ++ks) {     // unit b: its accumulator was read before h1 quarter 2 was published
-                                kstep128(db, 5 + (ks >> 2), ks, ks != 0);
-                                if ((ks & 3) == 3) commit_slot(5 + (ks >> 2));
+                            if constexpr (kFuseL1) {   // unit b: its accumulator was read before h1 quarter 2 was published
+                                unit_ksteps(db, 1 + kUS, 0, 16);
+                                umma_commit(&bar_acc_full[(u + 1u) & 1u]);
                             }
-                            umma_commit(&bar_acc_full[(u + 1u) & 1u]);
                         }
                     }
                     __syncwarp();
                     if (ds) { w_issue += clock64() - tq; tq = clock64(); }
                 }
                 ++hr;
+                it += (uint32_t)kUS;
+                if constexpr (!kFuseL1) {       // three products: unit b behind its own slot wait (accumulator: see above)
+                    wait_slots(kUS);
+                    if (ds) { w_full += clock64() - tq; tq = clock64(); }
+                    if (elect_one_sync()) {
+                        unit_ksteps(db, 1 + kUS, 0, 16);
+                        umma_commit(&bar_acc_full[(u + 1u) & 1u]);
+                    }
+                    __syncwarp();
+                    if (ds) { w_issue += clock64() - tq; tq = clock64(); }
+                }
+                it += (uint32_t)kUS;
                 u += 2;
-                it += 8;
             }
             // ---- this rank's head slice: pf arrives in two halves (K columns [0,128) and [128,256)) ----
             if (ds) tq = clock64();
             static_for<0, TS::kFullUnits>([&](auto HU) {   // (a compile-time loop: `#pragma unroll` leaves six units partly rolled, which
                 constexpr int hu = decltype(HU)::value;     //  turns the slot schedule into a local-memory array)
-                constexpr int hs = TS::kCommonSlots + 4 * hu;             // the unit's first slot
+                constexpr int hs = TS::kCommonSlots + kUS * hu;           // the unit's first slot
                 const uint32_t b = u & 1u, n = u >> 1;
                 const uint32_t d = tmem_base + kColD + b * 128u;
-                if (hu == 0 || !kFuseHeads) wait_slots(hu == 0 && kFuseHeads ? TS::kHeadSlots : 4);
+                if (hu == 0 || !kFuseHeads) wait_slots(hu == 0 && kFuseHeads ? TS::kHeadSlots : kUS);
                 if (ds) { w_full += clock64() - tq; tq = clock64(); }
 #pragma unroll
                 for (int g = 0; g < (hu == 0 ? 2 : 1); ++g) {
@@ -446,11 +476,7 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
                     }
                     if (elect_one_sync()) {
                         const int k0 = hu == 0 ? 8 * g : 0, k1 = hu == 0 ? 8 * g + 8 : 16;
-#pragma unroll
-                        for (int ks = k0; ks < k1; ++ks) {
-                            kstep128(d, hs + (ks >> 2), ks, ks != 0);
-                            if ((ks & 3) == 3) commit_slot(hs + (ks >> 2));
-                        }
+                        unit_ksteps(d, hs, k0, k1);
                         if (k1 == 16) umma_commit(&bar_acc_full[b]);
                         if constexpr (kFuseHeads) {
                             if (g == 1) {   // the 64-column unit (head unit 1: free once pf is complete): one fp16 image of K = 128 per slot
@@ -471,13 +497,40 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
                     if (ds) { w_issue += clock64() - tq; tq = clock64(); }
                 }
                 ++u;
-                it += 4;
+                it += (uint32_t)kUS;
             });
-            if constexpr (kFuseHeads) {
+            if constexpr (TS::kSmallUnit) {
+                if constexpr (!kFuseHeads) {
+                    // three products, the 64-column unit (head unit 1: free once pf is complete): four slots of two K-chunks of 32 inputs,
+                    // each [hi 4 KiB | lo 4 KiB] at c * 8 KiB
+                    constexpr int first = TS::kCommonSlots + kUS;
+                    const uint32_t d2 = tmem_base + kColD + (u & 1u) * 128u;
+                    wait_slots(4);
+                    if (ds) { w_full += clock64() - tq; tq = clock64(); }
+                    if (elect_one_sync()) {
+#pragma unroll
+                        for (int sl = 0; sl < 4; ++sl) {
+#pragma unroll
+                            for (int c = 0; c < 2; ++c)
+#pragma unroll
+                                for (int j = 0; j < 2; ++j) {
+                                    const uint32_t lo = dl[first + sl] + (uint32_t)((c * 8192u + 2u * (uint32_t)j * kLboB64) >> 4) + kLf64;
+                                    const uint64_t b_hi = desc(lo), b_lo = desc(lo + (4096u >> 4));
+                                    const uint32_t ac = (uint32_t)(2 * sl + c) * 16u + 8u * (uint32_t)j;
+                                    umma_bf16_ts(d2, t_ahi + ac, b_hi, idesc64, (sl | c | j) != 0);
+                                    umma_bf16_ts(d2, t_alo + ac, b_hi, idesc64, true);
+                                    umma_bf16_ts(d2, t_ahi + ac, b_lo, idesc64, true);
+                                }
+                            commit_slot(first + sl);
+                        }
+                        umma_commit(&bar_acc_full[u & 1u]);
+                    }
+                    __syncwarp();
+                    if (ds) { w_issue += clock64() - tq; tq = clock64(); }
+                }
                 ++u;
-                it += 2;
+                it += (uint32_t)(kW16 ? 2 : 4);
             }
-            static_assert(TS::kSmallUnit == kFuseHeads && (TS::kSmallUnit ? TS::kFullUnits == 1 : true), "the 64-column unit exists in teams of 4 only");
             if (ds) {
                 ds[7] = clock64();
                 ds[8] = w_full;
@@ -488,277 +541,6 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
             if constexpr (kOde) {   // the flags were written before the x_ready arrival that released this evaluation
                 if (ld_volatile_shared(&s_final) && step + 1 == ld_volatile_shared(&s_allowed)) break;
             }
-        }
-        } else {
-        for (int step = 0; kOde || step < p.T; ++step) {
-            unsigned long long *ds = (dbg_cta && lane == 0 && step < p.T) ? p.dbg + ((size_t)p.T + step) * 16 : nullptr;   // ODE: T = recorded evaluations
-            unsigned long long w_full = 0, w_a = 0, w_acc = 0, tq = 0, w_issue = 0;
-#ifdef GPB_DBG_TRACE
-            // experiment builds only: every wait / issue boundary of ONE step of the MMA warp, behind the [2][T][16] stamp block
-            unsigned long long *trp = (ds && step == p.T / 2) ? p.dbg + (size_t)2 * p.T * 16 : nullptr;
-#define TRS(i) do { if (trp) trp[i] = clock64(); } while (0)
-#else
-#define TRS(i) do { } while (0)
-#endif
-            if (ds) ds[0] = clock64();
-            TRS(0);
-            // ---- layer 0: h1_pre = x . P1^T   (K = 16; x pieces x1,x2,x3 at A_hi[0,8),[8,16),[16,24); P1 hi|lo per unit)
-            // (every slot wait costs ~250 cycles even when the data is there: it is taken BEFORE the wait for the operand it
-            // accompanies, where this warp idles anyway, not between that wait and the first MMA)
-            wait_slots(1);
-            TRS(1);
-            mbar_wait(&bar_x_ready, xr & 1u);
-            ++xr;
-            if (ds) ds[1] = clock64();
-            TRS(2);
-            {
-                const uint32_t s = it % kSlots;
-                for (int half = 0; half < 2; ++half) {
-                    // (no wait for the accumulator: x is published after every head epilogue of the previous step has read its
-                    // accumulators, so x_ready implies both are free — see "accumulator hand-back" at the row warps)
-                    const uint32_t b = u & 1u;
-                    if (half == 0) tc_fence_after_sync();
-                    TRS(3 + 2 * half);
-                    const uint32_t d = tmem_base + kColD + b * 128u;
-                    const uint64_t bhi = make_smem_desc(ring + s * kSlotBytes + (uint32_t)half * 8192u, kLboB, kSbo);
-                    const uint64_t blo = make_smem_desc(ring + s * kSlotBytes + (uint32_t)half * 8192u + 4096u, kLboB, kSbo);
-                    if (elect_one_sync()) {
-                        umma_bf16_ts(d, t_x + 0u, bhi, idesc128, false);
-                        umma_bf16_ts(d, t_x + 8u, bhi, idesc128, true);
-                        umma_bf16_ts(d, t_x + 16u, bhi, idesc128, true);
-                        umma_bf16_ts(d, t_x + 0u, blo, idesc128, true);
-                        umma_bf16_ts(d, t_x + 8u, blo, idesc128, true);
-                        if (half == 1) umma_commit(&bar_empty[s]);
-                        umma_commit(&bar_acc_full[b]);
-                    }
-                    __syncwarp();
-                    TRS(4 + 2 * half);
-                    ++u;
-                }
-                ++it;
-            }
-            // ---- units with K = 256: layer 1 (P2: two 128-column units) and this rank's head slice (128 + 64 columns) ----
-            for (int unit = 0; unit < 2 + TS::kHeadUnits; ++unit) {
-                if (ds) tq = clock64();
-                // Units 0 and 2 are the first consumers of a freshly written A operand (h1 / pf).  The row warps publish pf in two
-                // halves (K columns [0,128) once layer 1's MMAs have released the A region, [128,256) after the second unit's
-                // epilogue), so the first 8 K-steps of the heads are issued while the second half is still being converted; h1 comes
-                // in quarters (below).
-                const bool split = unit == 2;
-                const uint32_t b = u & 1u, n = u >> 1;
-                const uint32_t d = tmem_base + kColD + b * 128u;
-                const bool small = TS::kSmallUnit && unit == 2 + TS::kHeadUnits - 1;   // the 64-column unit (team 4): 2 K-chunks per slot
-                if (unit == 0) {
-                    // Layer 1, unit a: the first consumer of h1, which layer 0's epilogue publishes in QUARTERS (nothing else reads the
-                    // A region then, so a quarter is stored as soon as it is converted).  Row thread (q, cs) converts h1 columns
-                    // [64 cs, 64 cs + 64) of unit a and [128 + 64 cs, ...) of unit b, 32 at a time, so quarter g holds the K-steps
-                    // {base, base + 1, base + 4, base + 5}, base = 8 (g / 2) + 2 (g % 2): four issue groups of 4 K-steps; the
-                    // accumulation order inside the unit changes, nothing else.
-                    constexpr int kUnitSlots = kW16 ? 4 : 8;
-                    if (ds) tq = clock64();
-                    wait_slots(kFuseL1 ? 2 * kUnitSlots : kUnitSlots);
-                    TRS(7);
-                    if (ds) { w_full += clock64() - tq; tq = clock64(); }
-                    const uint32_t s_first = it % kSlots;
-                    auto slot_base = [&](int sl) {
-                        uint32_t sidx = s_first + (uint32_t)sl;
-                        sidx = sidx >= (uint32_t)kSlots ? sidx - (uint32_t)kSlots : sidx;
-                        return sidx;
-                    };
-                    for (int g = 0; g < 4; ++g) {
-                        if (ds) tq = clock64();
-                        // (fused: quarters 2 and 3 are both there when quarter 1 has been issued: one wait, on the later of the two)
-                        if (!(kFuseL1 && g == 3)) mbar_wait(&bar_h1_ready[kFuseL1 && g == 2 ? 3 : g], hr & 1u);
-                        TRS(8 + 3 * g);
-                        if (ds) {
-                            w_a += clock64() - tq;
-                            if (g == 0) ds[3] = clock64();
-                            tq = clock64();
-                        }
-                        if (!(kFuseL1 && g == 3)) tc_fence_after_sync();      // (accumulator: free once quarter 0 is published, which follows its last read)
-                        TRS(9 + 3 * g);
-                        if (ds) { w_acc += clock64() - tq; tq = clock64(); }
-                        const int base = 8 * (g >> 1) + 2 * (g & 1);
-                        if (elect_one_sync()) {
-#pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                const int ks = base + (e & 1) + 4 * (e >> 1);             // K-step (16 inputs) of the unit
-                                const uint32_t ac = (uint32_t)ks * 8u;                    // K index / 2
-                                const bool acc = (g | e) != 0;
-                                if constexpr (kW16) {
-                                    const uint32_t sb = ring + slot_base(ks >> 2) * kSlotBytes;
-                                    const uint64_t b_w = make_smem_desc(sb + 2u * (uint32_t)(ks & 3) * kLboB, kLboB, kSbo);
-                                    umma_bf16_ts(d, t_ahi + ac, b_w, idesc128w, acc);
-                                    umma_bf16_ts(d, t_alo + ac, b_w, idesc128w, true);
-                                } else {
-                                    const uint32_t sb = ring + slot_base(ks >> 1) * kSlotBytes;
-                                    const uint64_t b_hi = make_smem_desc(sb + 2u * (uint32_t)(ks & 1) * kLboB, kLboB, kSbo);
-                                    const uint64_t b_lo = make_smem_desc(sb + 8192u + 2u * (uint32_t)(ks & 1) * kLboB, kLboB, kSbo);
-                                    umma_bf16_ts(d, t_ahi + ac, b_hi, idesc128, acc);
-                                    umma_bf16_ts(d, t_alo + ac, b_hi, idesc128, true);
-                                    umma_bf16_ts(d, t_ahi + ac, b_lo, idesc128, true);
-                                }
-                            }
-                            if (g & 1) {   // quarters 2 (g / 2) and 2 (g / 2) + 1 together cover K-steps [8 (g / 2), 8 (g / 2) + 8): their slots are done
-                                for (int sl = 0; sl < kUnitSlots / 2; ++sl) umma_commit(&bar_empty[slot_base((g >> 1) * (kUnitSlots / 2) + sl)]);
-                            }
-                            if (g == 3) umma_commit(&bar_acc_full[b]);
-                        }
-                        __syncwarp();
-                        TRS(10 + 3 * g);
-                        if (ds) { w_issue += clock64() - tq; tq = clock64(); }
-                    }
-                    ++hr;
-                    it += (uint32_t)kUnitSlots;
-                    if (ds) ds[12] = clock64();                      // layer 1 unit a: all issued
-                } else if (!small) {
-                    // 8 slots = 16 K-steps, issued as one group (unit 1) or two groups of 4 slots (units 0, 2).  Every slot wait costs
-                    // the MMA warp ~250 cycles even when the data is there (measured: groups of 2 slots, 7.45 -> 8.0 ms per launch), so
-                    // groups are as large as the A-operand hand-off allows.  (Also measured without effect: a 10th ring slot, one private
-                    // copy of the weight stream per tile team — the waits are not L2 hot-line contention — and one 8-slot wait for unit 0.)
-                    const int groups = split ? 2 : 1, per = (split ? 4 : 8) / (kW16 ? 2 : 1);   // (unit 1 in two groups of 4: slower, 7.26 -> 7.35 ms)
-                    for (int g = 0; g < groups; ++g) {
-                        if (ds) tq = clock64();
-                        // before the operand wait (see layer 0); fused: unit 1's slots were awaited with unit 0's, the whole head
-                        // slice's (6 slots of this rank) in front of head unit 0
-                        if (unit == 1 ? !kFuseL1 : !(kFuseHeads && g == 1)) wait_slots(kFuseHeads && unit == 2 ? TS::kHeadSlots : per);
-                        TRS(unit == 1 ? 20 : 23 + 4 * g);
-                        if (ds) { w_full += clock64() - tq; tq = clock64(); }
-                        if (split) {
-                            mbar_wait(&bar_a_ready[g], ar & 1u);            // one phase of either barrier per step (layer 1 -> heads)
-                            if (g == 1) ++ar;
-                            TRS(24 + 4 * g);
-                        }
-                        if (ds) {
-                            w_a += clock64() - tq;
-                            if (unit == 0 && g == 0) ds[3] = clock64();
-                            if (unit == 2 && g == 0) ds[4] = clock64();
-                            tq = clock64();
-                        }
-                        // accumulator hand-back: unit 1 reuses layer 0's second accumulator (read before h1 quarter 2 was published),
-                        // head units 0 and 1 those of layer 1 (read before pf half 0 / half 1 were published): only head units >= 2
-                        // wait for an explicit release, by the epilogue of head unit - 2
-                        if (g == 0 && unit >= 4) mbar_wait(&bar_acc_empty[b], (n & 1u) ^ 1u);
-                        if (!(kFuseL1 && unit == 1)) tc_fence_after_sync();
-                        TRS(unit == 1 ? 21 : 25 + 4 * g);
-                        if (ds) { w_acc += clock64() - tq; tq = clock64(); }
-                        if (ds && unit == 1) ds[14] = clock64();     // layer 1 unit b: waits done, issue starts
-                        const uint32_t s_first = it % kSlots;
-                        const int kc0 = g * per;
-                        if (elect_one_sync()) {
-                            if constexpr (!kW16) {
-#pragma unroll 4
-                            for (int kk = 0; kk < per; ++kk) {
-                                const int kc = kc0 + kk;
-                                uint32_t s = s_first + (uint32_t)kk;
-                                s = s >= (uint32_t)kSlots ? s - (uint32_t)kSlots : s;
-                                const uint32_t sb = ring + s * kSlotBytes;
-#pragma unroll
-                                for (int j = 0; j < 2; ++j) {
-                                    const uint64_t b_hi = make_smem_desc(sb + 2u * j * kLboB, kLboB, kSbo);
-                                    const uint64_t b_lo = make_smem_desc(sb + 8192u + 2u * j * kLboB, kLboB, kSbo);
-                                    const uint32_t ac = (uint32_t)kc * 16u + 8u * j;      // K index / 2
-                                    umma_bf16_ts(d, t_ahi + ac, b_hi, idesc128, (kc | j) != 0);
-                                    umma_bf16_ts(d, t_alo + ac, b_hi, idesc128, true);
-                                    umma_bf16_ts(d, t_ahi + ac, b_lo, idesc128, true);
-                                }
-                                umma_commit(&bar_empty[s]);
-                            }
-                            } else {
-                            // one fp16 image of K = 64 per slot: four K-steps, two products each (Ahi.W, Alo.W)
-#pragma unroll 2
-                            for (int kk = 0; kk < per; ++kk) {
-                                uint32_t s = s_first + (uint32_t)kk;
-                                s = s >= (uint32_t)kSlots ? s - (uint32_t)kSlots : s;
-                                const uint32_t sb = ring + s * kSlotBytes;
-#pragma unroll
-                                for (int j = 0; j < 4; ++j) {
-                                    const uint64_t b_w = make_smem_desc(sb + 2u * j * kLboB, kLboB, kSbo);
-                                    const int ks = (kc0 + kk) * 4 + j;                      // K-step (16 inputs) of the unit
-                                    const uint32_t ac = (uint32_t)ks * 8u;                  // K index / 2
-                                    umma_bf16_ts(d, t_ahi + ac, b_w, idesc128w, ks != 0);
-                                    umma_bf16_ts(d, t_alo + ac, b_w, idesc128w, true);
-                                }
-                                umma_commit(&bar_empty[s]);
-                            }
-                            }
-                            if (g == groups - 1) umma_commit(&bar_acc_full[b]);
-                        }
-                        __syncwarp();
-                        TRS(unit == 1 ? 22 : 26 + 4 * g);
-                        if (ds) { w_issue += clock64() - tq; tq = clock64(); }
-                        if (ds && unit == 1) ds[13] = clock64();     // layer 1 unit b: all issued
-                        it += (uint32_t)per;
-                    }
-                } else {
-                    if (ds) tq = clock64();
-                    constexpr int kSmallSlots = kW16 ? 2 : 4;
-                    if (!kFuseHeads) wait_slots(kSmallSlots);
-                    TRS(31);
-                    if (ds) { w_full += clock64() - tq; tq = clock64(); }
-                    static_assert(!TS::kSmallUnit || TS::kHeadUnits == 2, "the 64-column unit is head unit 1: its accumulator is free once pf is complete");
-                    TRS(32);
-                    if (ds) { w_acc += clock64() - tq; tq = clock64(); }
-                    const uint32_t s_first = it % kSlots;
-                    if (elect_one_sync()) {
-                        if constexpr (kW16) {
-                        // one fp16 image of K = 128 per slot (64 rows): eight K-steps, two products each
-#pragma unroll
-                        for (int sl = 0; sl < 2; ++sl) {
-                            uint32_t s = s_first + (uint32_t)sl;
-                            s = s >= (uint32_t)kSlots ? s - (uint32_t)kSlots : s;
-                            const uint32_t sb = ring + s * kSlotBytes;
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                const uint64_t b_w = make_smem_desc(sb + 2u * j * kLboB64, kLboB64, kSbo);
-                                const int ks = sl * 8 + j;
-                                const uint32_t ac = (uint32_t)ks * 8u;
-                                umma_bf16_ts(d, t_ahi + ac, b_w, idesc64w, ks != 0);
-                                umma_bf16_ts(d, t_alo + ac, b_w, idesc64w, true);
-                            }
-                            umma_commit(&bar_empty[s]);
-                        }
-                        } else {
-#pragma unroll
-                        for (int sl = 0; sl < 4; ++sl) {
-                            uint32_t s = s_first + (uint32_t)sl;
-                            s = s >= (uint32_t)kSlots ? s - (uint32_t)kSlots : s;
-#pragma unroll
-                            for (int c = 0; c < 2; ++c) {                  // K-chunk 2*sl + c: [hi 4 KiB | lo 4 KiB] at c * 8 KiB
-                                const uint32_t sb = ring + s * kSlotBytes + (uint32_t)c * 8192u;
-#pragma unroll
-                                for (int j = 0; j < 2; ++j) {
-                                    const uint64_t b_hi = make_smem_desc(sb + 2u * j * kLboB64, kLboB64, kSbo);
-                                    const uint64_t b_lo = make_smem_desc(sb + 4096u + 2u * j * kLboB64, kLboB64, kSbo);
-                                    const uint32_t ac = (uint32_t)(2 * sl + c) * 16u + 8u * j;
-                                    umma_bf16_ts(d, t_ahi + ac, b_hi, idesc64, (sl | c | j) != 0);
-                                    umma_bf16_ts(d, t_alo + ac, b_hi, idesc64, true);
-                                    umma_bf16_ts(d, t_ahi + ac, b_lo, idesc64, true);
-                                }
-                            }
-                            umma_commit(&bar_empty[s]);
-                        }
-                        }
-                        umma_commit(&bar_acc_full[b]);
-                    }
-                    __syncwarp();
-                    TRS(33);
-                    if (ds) w_issue += clock64() - tq;
-                    it += (uint32_t)kSmallSlots;
-                }
-                ++u;
-            }
-            if (ds) {
-                ds[7] = clock64();
-                ds[8] = w_full;
-                ds[9] = w_a;
-                ds[10] = w_acc;
-                ds[11] = w_issue;
-            }
-            if constexpr (kOde) {   // the flags were written before the x_ready arrival that released this evaluation
-                if (ld_volatile_shared(&s_final) && step + 1 == ld_volatile_shared(&s_allowed)) break;
-            }
-        }
         }
     } else {
         // =============================== row warps ===============================
