@@ -36,9 +36,9 @@
 //              the (object bias + time bias) table for the next step.
 //   warp 8     one elected thread issues every tcgen05.mma / tcgen05.commit; the warp owns the TMEM allocation.  The tensor pipe
 //              accepts an MMA only about when it starts it, so whatever this warp does between two issue groups idles the pipe:
-//              f16x2 runs straight-line issue code over a slot schedule computed under the wait for x, in few large groups
-//              (layer 1: q0 | q1 | q2 + q3 + unit b; team-of-4 heads: first half | second half + 64-column unit), and waits for an
-//              accumulator only where no operand hand-off already implies its release.
+//              straight-line issue code over a slot schedule computed under the wait for x, few large groups (f16x2: layer 1 =
+//              q0 | q1 | q2 + q3 + unit b, team-of-4 heads = first half | second half + 64-column unit; three products: one slot
+//              wait per unit, the ring holds no more), an accumulator wait only where no operand hand-off already implies its release.
 //   warp 9     one elected thread runs the weight producer.
 // Per step and CTA (team 4, f16x2): layer 0 (10 MMAs), layer 1 (2 x 32 MMAs of 128x128x16), head slice (32 of 128x128x16 + 32 of 128x64x16).
 // History (3200 rows x 500 steps, one B200): A in shared memory + 2-deep weight ring 18.2 ms ... round 1 7.05 ms ... this version

@@ -10,7 +10,8 @@ No GPU, no product code: a model of the protocol, kept next to the kernel so tha
     python tools/tc_protocol_sim.py [runs] [steps] [--old-a-ready] [--explicit-acc-waits] [--late-read]
 --old-a-ready models the single 8-count bar_a_ready the kernel had before (both halves arriving on one barrier): the simulator
 finds the early-release race that motivated the split within a few hundred schedules.
-Default = the shipped f16x2 issuer (late round 2): NO accumulator waits — every operand announcement of the row warps (operand halves,
+Default = the shipped issuer (late round 2; the group fusion is the f16x2 form, the three-product form takes a slot wait where
+the fusion is — slot waits are not modelled): NO accumulator waits — every operand announcement of the row warps (operand halves,
 x) follows their last read of the accumulator the announced MMAs overwrite — and fused issue groups (layer 1: first half | second
 half + unit b; heads: first half | second half + the 64-column unit).  --explicit-acc-waits is the protocol before that (one
 bar_acc_empty wait per unit, one group per wait).  --late-read is a negative control: the row warps announce the second operand
