@@ -297,9 +297,9 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
         const uint32_t t_ahi = tmem_base + kColAhi, t_alo = tmem_base + kColAlo, t_x = tmem_base + kColX;
         uint32_t u = 0, it = 0, xr = 0, ar = 0, hr = 0;
         // wait for n_slots consecutive ring slots starting at stream position `it`: lane l polls slot l (one wait latency)
-        auto wait_slots = [&](int n_slots) {
+        auto wait_slots = [&](int n_slots, int first = 0) {
             if (lane < n_slots) {
-                const uint32_t itl = it + (uint32_t)lane;
+                const uint32_t itl = it + (uint32_t)(first + lane);
                 mbar_wait(&bar_full[itl % kSlots], (itl / kSlots) & 1u);
             }
             __syncwarp();
@@ -392,12 +392,15 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
             it += 1;
             // ---- layer 1: unit a on the h1 quarters (quarter g = K-steps {base, base + 1, base + 4, base + 5}, base = 8 (g / 2) + 2 (g % 2):
             //      row thread (q, cs) converts columns [64 cs, 64 cs + 64) of either unit, 32 at a time), unit b behind it ----
-            wait_slots(kFuseL1 ? 2 * kUS : kUS);
+            // (three products: the ring holds 10 of a step's 29 slots, so the stream runs just in time — a unit's slots are awaited in two
+            // halves, or its first MMAs would wait for slots that can only be refilled once the previous unit is nearly through)
+            wait_slots(kFuseL1 ? 2 * kUS : kUS / 2);
             if (ds) { w_full += clock64() - tq; tq = clock64(); }
             {
                 const uint32_t da = tmem_base + kColD + (u & 1u) * 128u, db = tmem_base + kColD + ((u + 1u) & 1u) * 128u;
 #pragma unroll
                 for (int g = 0; g < 3; ++g) {
+                    if (!kFuseL1 && g == 2) wait_slots(kUS / 2, kUS / 2);
                     mbar_wait_inline(&bar_h1_ready[g == 2 ? 3 : g], hr & 1u);      // quarters 2 and 3 are both there once quarter 1 is issued
                     tc_fence_after_sync();
                     if (ds) {
@@ -437,15 +440,18 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
                 }
                 ++hr;
                 it += (uint32_t)kUS;
-                if constexpr (!kFuseL1) {       // three products: unit b behind its own slot wait (accumulator: see above)
-                    wait_slots(kUS);
-                    if (ds) { w_full += clock64() - tq; tq = clock64(); }
-                    if (elect_one_sync()) {
-                        unit_ksteps(db, 1 + kUS, 0, 16);
-                        umma_commit(&bar_acc_full[(u + 1u) & 1u]);
+                if constexpr (!kFuseL1) {       // three products: unit b behind its own slot waits (accumulator: see above)
+#pragma unroll
+                    for (int hf = 0; hf < 2; ++hf) {
+                        wait_slots(kUS / 2, hf * (kUS / 2));
+                        if (ds) { w_full += clock64() - tq; tq = clock64(); }
+                        if (elect_one_sync()) {
+                            unit_ksteps(db, 1 + kUS, 8 * hf, 8 * hf + 8);
+                            if (hf == 1) umma_commit(&bar_acc_full[(u + 1u) & 1u]);
+                        }
+                        __syncwarp();
+                        if (ds) { w_issue += clock64() - tq; tq = clock64(); }
                     }
-                    __syncwarp();
-                    if (ds) { w_issue += clock64() - tq; tq = clock64(); }
                 }
                 it += (uint32_t)kUS;
                 u += 2;
@@ -457,15 +463,20 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
                 constexpr int hs = TS::kCommonSlots + kUS * hu;           // the unit's first slot
                 const uint32_t b = u & 1u, n = u >> 1;
                 const uint32_t d = tmem_base + kColD + b * 128u;
-                if (hu == 0 || !kFuseHeads) wait_slots(hu == 0 && kFuseHeads ? TS::kHeadSlots : kUS);
+                constexpr int kGroups = (hu == 0 || !kW16) ? 2 : 1;       // K halves: pf arrives in halves (unit 0), three-product slots do
+                if (kW16 && (hu == 0 || !kFuseHeads)) wait_slots(hu == 0 && kFuseHeads ? TS::kHeadSlots : kUS);
                 if (ds) { w_full += clock64() - tq; tq = clock64(); }
 #pragma unroll
-                for (int g = 0; g < (hu == 0 ? 2 : 1); ++g) {
+                for (int g = 0; g < kGroups; ++g) {
+                    if constexpr (!kW16) {
+                        wait_slots(kUS / 2, g * (kUS / 2));
+                        if (ds) { w_full += clock64() - tq; tq = clock64(); }
+                    }
                     if (hu == 0) {
                         mbar_wait_inline(&bar_a_ready[g], ar & 1u);        // (implies the accumulator of head unit g is free)
                         if (g == 1) ++ar;
                         tc_fence_after_sync();
-                    } else if (hu >= 2) {
+                    } else if (hu >= 2 && g == 0) {
                         mbar_wait_inline(&bar_acc_empty[b], (n & 1u) ^ 1u);   // released by the epilogue of head unit hu - 2
                         tc_fence_after_sync();
                     }
@@ -475,7 +486,7 @@ __device__ __forceinline__ void tc_sampler_body(const TcPcParams &tp) {
                         tq = clock64();
                     }
                     if (elect_one_sync()) {
-                        const int k0 = hu == 0 ? 8 * g : 0, k1 = hu == 0 ? 8 * g + 8 : 16;
+                        const int k0 = kGroups == 2 ? 8 * g : 0, k1 = kGroups == 2 ? 8 * g + 8 : 16;
                         unit_ksteps(d, hs, k0, k1);
                         if (k1 == 16) umma_commit(&bar_acc_full[b]);
                         if constexpr (kFuseHeads) {
